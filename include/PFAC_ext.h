@@ -1,0 +1,108 @@
+/*
+ * PFAC_ext.h -- additive entry points of the B200-native libpfac.so.
+ *
+ * Nothing in the reference binds these; they exist because (a) the legacy ABI is int-indexed
+ * (reference src/PFAC_CPU.cpp:43,60; src/PFAC_kernel.cu:378) and BASELINE configs 3-5 exceed
+ * 2^31 bytes, (b) multi-GPU shards need "owned positions + tail halo" (what the reference's
+ * test/omp_PFAC.cpp:351-383 does by hand), and (c) the table compiler is host-only code that
+ * tools and CPU tests can run without a GPU.
+ */
+#ifndef PFAC_EXT_H_
+#define PFAC_EXT_H_
+
+#include "PFAC.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- north-star aliases (BASELINE.json names; the reference has no such symbols, see
+ * SURVEY.md section 0.1).  Same signature and result as PFAC_matchFromDeviceReduce
+ * (reference PFAC.h:206); "Inplace" is the reference's PFAC_SPACE_DRIVEN flavour
+ * (src/PFAC_reduce_inplace_kernel.cu:155) whose outputs are identical. */
+PFAC_status_t PFAC_reduceOnDevice(PFAC_handle_t handle, char *d_inputString, size_t size,
+                                  int *d_matched_result, int *d_pos, int *h_num_matched);
+PFAC_status_t PFAC_reduceInplaceOnDevice(PFAC_handle_t handle, char *d_inputString, size_t size,
+                                         int *d_matched_result, int *d_pos, int *h_num_matched);
+
+/* ---- stream control.  The reference only uses the default stream (PFAC/README:135); this
+ * keeps that default and lets a caller move the handle's work to its own cudaStream_t. */
+PFAC_status_t PFAC_setStream(PFAC_handle_t handle, void *cuda_stream);
+
+/* ---- patterns from memory: same grammar as the file form (reference
+ * src/PFAC_reorder_Table.cpp:121-231), image = the bytes the file would hold. */
+PFAC_status_t PFAC_readPatternFromMemory(PFAC_handle_t handle, const char *image, size_t size);
+
+/* ---- shard form of PFAC_matchFromDevice: results for positions [0,n_owned); walks may read
+ * input[0,n_total), n_total >= n_owned (owned bytes followed by the tail halo, which must be
+ * the real following bytes; >= maxPatternLen-1 of them unless the stream ends).  This is the
+ * kernel-level contract the reference's omp_PFAC.cpp:351-377 builds by copying. */
+PFAC_status_t PFAC_matchShardFromDevice(PFAC_handle_t handle, const char *d_inputString,
+                                        size_t n_owned, size_t n_total, int *d_matched_result);
+
+/* ---- 64-bit reduce: positions are long long, count is unsigned long long; sizes >= 2^31 ok */
+PFAC_status_t PFAC_matchFromDeviceReduce64(PFAC_handle_t handle, const char *d_inputString,
+                                           size_t size, int *d_matched_result, long long *d_pos,
+                                           unsigned long long *h_num_matched);
+
+/* shard + 64-bit reduce: emitted position = pos_base + local position (pos_base = global
+ * offset of the shard's first byte).  Multi-GPU use: each rank calls this on its shard, the
+ * ranks exchange *h_num_matched (one 8-byte all-gather) and an exclusive scan of the counts
+ * gives each rank's offset into the global (ID, position) list. */
+PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char *d_inputString,
+                                                size_t n_owned, size_t n_total,
+                                                long long pos_base, int *d_matched_result,
+                                                long long *d_pos,
+                                                unsigned long long *h_num_matched);
+
+/* ---- table compiler, host only (no CUDA calls): pattern image -> reference-numbered trie
+ * -> B200 device layout (dense root row, 2-byte prefilter bitmap, hot/cold bucketed hash
+ * rows). */
+typedef struct PFAC_table *PFAC_table_t;
+
+typedef struct {
+    int num_patterns;      /* k */
+    int num_states;        /* reference numOfStates (counts unused state 0) */
+    int initial_state;     /* k+1 */
+    int max_pattern_len;
+    int num_leaves;        /* final states without out-edges */
+    int num_edges;         /* distinct (state,ch) transitions used for matching */
+    int max_depth;
+    int hot_depth;         /* edges whose source state has depth in [1,hot_depth) are "hot" */
+    unsigned hot_buckets;  /* 16-byte buckets (2 slots) of the shared-memory hash rows */
+    unsigned cold_buckets; /* 16-byte buckets of the global (L2-resident) hash rows */
+    unsigned hash_mul;
+    int hot_max_probe, cold_max_probe;
+    int pre2_bits_set;     /* of 65536: (c0,c1) pairs that survive the prefilter */
+    int root_fanout;       /* valid first bytes */
+    size_t device_bytes;   /* total bytes uploaded */
+} PFAC_tableInfo_t;
+
+PFAC_status_t PFAC_tableCompile(const char *image, size_t size, size_t hot_budget_bytes,
+                                PFAC_table_t *table);
+PFAC_status_t PFAC_tableCompileFile(const char *filename, size_t hot_budget_bytes,
+                                    PFAC_table_t *table);
+PFAC_status_t PFAC_tableDestroy(PFAC_table_t table);
+PFAC_status_t PFAC_tableDump(PFAC_table_t table, FILE *fp);
+PFAC_status_t PFAC_tableDumpToFile(PFAC_table_t table, const char *filename);
+PFAC_status_t PFAC_tableGetInfo(PFAC_table_t table, PFAC_tableInfo_t *info);
+/* read-only views of the layout arrays (valid until PFAC_tableDestroy):
+ * root: 256 int; pre2: 2048 unsigned; hot/cold: 4 unsigned per bucket {key0,val0,key1,val1} */
+PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int **root, const unsigned **pre2,
+                                  const unsigned **hot, const unsigned **cold);
+
+/* info / dump-to-path for a live handle */
+PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);
+PFAC_status_t PFAC_dumpTransitionTableToFile(PFAC_handle_t handle, const char *filename);
+
+/* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
+unsigned long long PFAC_kernelLaunchCount(void);
+
+/* library build tag, e.g. "pfac-b200 sm_100a" */
+const char *PFAC_versionString(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PFAC_EXT_H_ */

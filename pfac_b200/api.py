@@ -1,0 +1,337 @@
+"""ctypes mirror of include/PFAC.h + include/PFAC_ext.h.
+
+Method names follow the C entry points (reference PFAC/include/PFAC.h:87-215):
+PFAC.readPatternFromFile, matchFromHost, matchFromDevice, matchFromDeviceReduce, ...
+Device buffers are anything with .data_ptr() (torch CUDA tensors) or raw integer addresses.
+Every call raises PFACError(status) on a non-success PFAC_status_t, carrying the library's
+own PFAC_getErrorString text.  There is no fallback: if libpfac.so is missing or no B200 is
+present, construction fails.
+"""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "lib", "libpfac.so")
+_lib = None
+
+
+class Status(enum.IntEnum):  # include/PFAC.h (reference PFAC.h:57-70)
+    SUCCESS = 0
+    BASE = 10000
+    ALLOC_FAILED = 10001
+    CUDA_ALLOC_FAILED = 10002
+    INVALID_HANDLE = 10003
+    INVALID_PARAMETER = 10004
+    PATTERNS_NOT_READY = 10005
+    FILE_OPEN_ERROR = 10006
+    LIB_NOT_EXIST = 10007
+    ARCH_MISMATCH = 10008
+    MUTEX_ERROR = 10009
+    INTERNAL_ERROR = 10010
+
+
+class Platform(enum.IntEnum):
+    GPU = 0
+    CPU = 1
+    CPU_OMP = 2
+
+
+class TextureMode(enum.IntEnum):
+    AUTOMATIC = 0
+    TEXTURE_ON = 1
+    TEXTURE_OFF = 2
+
+
+class PerfMode(enum.IntEnum):
+    TIME_DRIVEN = 0
+    SPACE_DRIVEN = 1
+
+
+class TableInfo(ctypes.Structure):
+    _fields_ = [("num_patterns", ctypes.c_int), ("num_states", ctypes.c_int),
+                ("initial_state", ctypes.c_int), ("max_pattern_len", ctypes.c_int),
+                ("num_leaves", ctypes.c_int), ("num_edges", ctypes.c_int),
+                ("max_depth", ctypes.c_int), ("hot_depth", ctypes.c_int),
+                ("hot_buckets", ctypes.c_uint), ("cold_buckets", ctypes.c_uint),
+                ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
+                ("cold_max_probe", ctypes.c_int), ("pre2_bits_set", ctypes.c_int),
+                ("root_fanout", ctypes.c_int), ("device_bytes", ctypes.c_size_t)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class PFACError(RuntimeError):
+    def __init__(self, status, where=""):
+        self.status = int(status)
+        try:
+            text = load_library().PFAC_getErrorString(self.status).decode()
+        except Exception:  # pragma: no cover
+            text = "status %d" % self.status
+        super().__init__("%s%s" % (where + ": " if where else "", text))
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen pfac_b200/lib/libpfac.so (build it with `python -m pfac_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise FileNotFoundError(
+            _LIB_PATH + " is missing: run `python -m pfac_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback.")
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, cp, sz, ip = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)
+    ull = ctypes.c_ulonglong
+    sig = {
+        "PFAC_create": [ctypes.POINTER(vp)],
+        "PFAC_destroy": [vp],
+        "PFAC_setPlatform": [vp, ctypes.c_int],
+        "PFAC_setTextureMode": [vp, ctypes.c_int],
+        "PFAC_setPerfMode": [vp, ctypes.c_int],
+        "PFAC_dumpTransitionTable": [vp, vp],
+        "PFAC_dumpTransitionTableToFile": [vp, cp],
+        "PFAC_readPatternFromFile": [vp, cp],
+        "PFAC_readPatternFromMemory": [vp, cp, sz],
+        "PFAC_matchFromDevice": [vp, vp, sz, vp],
+        "PFAC_matchFromHost": [vp, vp, sz, vp],
+        "PFAC_matchFromDeviceReduce": [vp, vp, sz, vp, vp, ip],
+        "PFAC_matchFromHostReduce": [vp, vp, sz, vp, vp, ip],
+        "PFAC_reduceOnDevice": [vp, vp, sz, vp, vp, ip],
+        "PFAC_reduceInplaceOnDevice": [vp, vp, sz, vp, vp, ip],
+        "PFAC_setStream": [vp, vp],
+        "PFAC_matchShardFromDevice": [vp, vp, sz, sz, vp],
+        "PFAC_matchFromDeviceReduce64": [vp, vp, sz, vp, vp, ctypes.POINTER(ull)],
+        "PFAC_matchShardFromDeviceReduce64": [vp, vp, sz, sz, ctypes.c_longlong, vp, vp,
+                                              ctypes.POINTER(ull)],
+        "PFAC_tableCompile": [cp, sz, sz, ctypes.POINTER(vp)],
+        "PFAC_tableCompileFile": [cp, sz, ctypes.POINTER(vp)],
+        "PFAC_tableDestroy": [vp],
+        "PFAC_tableDump": [vp, vp],
+        "PFAC_tableDumpToFile": [vp, cp],
+        "PFAC_tableGetInfo": [vp, ctypes.POINTER(TableInfo)],
+        "PFAC_tableGetLayout": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                ctypes.POINTER(vp)],
+        "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = ctypes.c_int
+    L.PFAC_getErrorString.argtypes = [ctypes.c_int]
+    L.PFAC_getErrorString.restype = ctypes.c_char_p
+    L.PFAC_versionString.restype = ctypes.c_char_p
+    L.PFAC_kernelLaunchCount.restype = ull
+    _lib = L
+    return L
+
+
+def kernel_launch_count():
+    return int(load_library().PFAC_kernelLaunchCount())
+
+
+def _ptr(x):
+    """Address of a device tensor / numpy array / raw int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError("expected a tensor, ndarray or address, got %r" % type(x))
+
+
+def _check(status, where):
+    if status != 0:
+        raise PFACError(status, where)
+
+
+class PFAC:
+    """One PFAC_handle_t.  Binds to the current CUDA device (reference PFAC.cpp:103-132)."""
+
+    def __init__(self):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        _check(self._L.PFAC_create(ctypes.byref(self._h)), "PFAC_create")
+
+    # -- lifecycle -----------------------------------------------------------------------
+    def destroy(self):
+        if self._h:
+            st = self._L.PFAC_destroy(self._h)
+            self._h = ctypes.c_void_p()
+            _check(st, "PFAC_destroy")
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.destroy()
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- configuration ---------------------------------------------------------------------
+    def setPlatform(self, platform):
+        _check(self._L.PFAC_setPlatform(self._h, int(platform)), "PFAC_setPlatform")
+
+    def setTextureMode(self, mode):
+        _check(self._L.PFAC_setTextureMode(self._h, int(mode)), "PFAC_setTextureMode")
+
+    def setPerfMode(self, mode):
+        _check(self._L.PFAC_setPerfMode(self._h, int(mode)), "PFAC_setPerfMode")
+
+    def setStream(self, stream):
+        """stream: a torch.cuda.Stream, a raw cudaStream_t address, or None (default stream)."""
+        addr = getattr(stream, "cuda_stream", stream) or None
+        _check(self._L.PFAC_setStream(self._h, addr), "PFAC_setStream")
+
+    def readPatternFromFile(self, filename):
+        _check(self._L.PFAC_readPatternFromFile(self._h, os.fsencode(filename)),
+               "PFAC_readPatternFromFile")
+
+    def readPatternFromMemory(self, image):
+        image = bytes(image)
+        _check(self._L.PFAC_readPatternFromMemory(self._h, image, len(image)),
+               "PFAC_readPatternFromMemory")
+
+    def dumpTransitionTable(self, filename):
+        _check(self._L.PFAC_dumpTransitionTableToFile(self._h, os.fsencode(filename)),
+               "PFAC_dumpTransitionTable")
+
+    def tableInfo(self):
+        info = TableInfo()
+        _check(self._L.PFAC_getTableInfo(self._h, ctypes.byref(info)), "PFAC_getTableInfo")
+        return info.as_dict()
+
+    # -- matching: device buffers ----------------------------------------------------------------
+    def matchFromDevice(self, d_input, size, d_result):
+        """d_result[i] (int32) for i<size.  Asynchronous on the handle's stream."""
+        _check(self._L.PFAC_matchFromDevice(self._h, _ptr(d_input), size, _ptr(d_result)),
+               "PFAC_matchFromDevice")
+
+    def matchShardFromDevice(self, d_input, n_owned, n_total, d_result):
+        _check(self._L.PFAC_matchShardFromDevice(self._h, _ptr(d_input), n_owned, n_total,
+                                                 _ptr(d_result)), "PFAC_matchShardFromDevice")
+
+    def matchFromDeviceReduce(self, d_input, size, d_result, d_pos, alias=None):
+        """Returns M; d_result[0..M) ids and d_pos[0..M) int32 positions, ascending position."""
+        n = ctypes.c_int(0)
+        fn = {None: self._L.PFAC_matchFromDeviceReduce, "reduceOnDevice": self._L.PFAC_reduceOnDevice,
+              "reduceInplaceOnDevice": self._L.PFAC_reduceInplaceOnDevice}[alias]
+        _check(fn(self._h, _ptr(d_input), size, _ptr(d_result), _ptr(d_pos), ctypes.byref(n)),
+               "PFAC_matchFromDeviceReduce")
+        return n.value
+
+    def matchFromDeviceReduce64(self, d_input, size, d_result, d_pos64):
+        n = ctypes.c_ulonglong(0)
+        _check(self._L.PFAC_matchFromDeviceReduce64(self._h, _ptr(d_input), size, _ptr(d_result),
+                                                    _ptr(d_pos64), ctypes.byref(n)),
+               "PFAC_matchFromDeviceReduce64")
+        return n.value
+
+    def matchShardFromDeviceReduce64(self, d_input, n_owned, n_total, pos_base, d_result, d_pos64):
+        n = ctypes.c_ulonglong(0)
+        _check(self._L.PFAC_matchShardFromDeviceReduce64(self._h, _ptr(d_input), n_owned, n_total,
+                                                         pos_base, _ptr(d_result), _ptr(d_pos64),
+                                                         ctypes.byref(n)),
+               "PFAC_matchShardFromDeviceReduce64")
+        return n.value
+
+    # -- matching: host buffers --------------------------------------------------------------------
+    def matchFromHost(self, h_input, h_result=None, size=None):
+        """h_input: bytes / uint8 ndarray / pinned CPU tensor.  Returns the int32 result array."""
+        src = _host_u8(h_input)
+        n = _host_len(src) if size is None else size
+        if h_result is None:
+            h_result = np.zeros(n, dtype=np.int32)
+        _check(self._L.PFAC_matchFromHost(self._h, _ptr(src), n, _ptr(h_result)), "PFAC_matchFromHost")
+        return h_result
+
+    def matchFromHostReduce(self, h_input, h_result=None, h_pos=None, size=None):
+        """Returns (ids[:M], pos[:M]) as int32 arrays (views of the supplied buffers)."""
+        src = _host_u8(h_input)
+        n = _host_len(src) if size is None else size
+        if h_result is None:
+            h_result = np.zeros(n, dtype=np.int32)
+        if h_pos is None:
+            h_pos = np.zeros(n, dtype=np.int32)
+        m = ctypes.c_int(0)
+        _check(self._L.PFAC_matchFromHostReduce(self._h, _ptr(src), n, _ptr(h_result), _ptr(h_pos),
+                                                ctypes.byref(m)), "PFAC_matchFromHostReduce")
+        return h_result[:m.value], h_pos[:m.value]
+
+
+def _host_u8(x):
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    if isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x.view(np.uint8) if x.dtype != np.uint8 else x)
+    return x  # CPU tensor
+
+
+def _host_len(x):
+    if isinstance(x, np.ndarray):
+        return x.size
+    return x.numel()
+
+
+class TableCompiler:
+    """Host-only table compiler (no GPU needed): PFAC_tableCompile* in include/PFAC_ext.h."""
+
+    def __init__(self, pattern_file=None, image=None, hot_budget_bytes=24 * 1024):
+        self._L = load_library()
+        self._t = ctypes.c_void_p()
+        if pattern_file is not None:
+            st = self._L.PFAC_tableCompileFile(os.fsencode(pattern_file), hot_budget_bytes,
+                                               ctypes.byref(self._t))
+        else:
+            image = bytes(image)
+            st = self._L.PFAC_tableCompile(image, len(image), hot_budget_bytes, ctypes.byref(self._t))
+        _check(st, "PFAC_tableCompile")
+
+    def __del__(self):
+        if getattr(self, "_t", None):
+            self._L.PFAC_tableDestroy(self._t)
+            self._t = None
+
+    def info(self):
+        info = TableInfo()
+        _check(self._L.PFAC_tableGetInfo(self._t, ctypes.byref(info)), "PFAC_tableGetInfo")
+        return info.as_dict()
+
+    def dump(self, filename):
+        _check(self._L.PFAC_tableDumpToFile(self._t, os.fsencode(filename)), "PFAC_tableDumpToFile")
+
+    def layout(self):
+        """Copies of the device layout arrays: root[256] i32, pre2[2048] u32, hot/cold [n,4] u32."""
+        ptrs = [ctypes.c_void_p() for _ in range(4)]
+        _check(self._L.PFAC_tableGetLayout(self._t, *[ctypes.byref(p) for p in ptrs]),
+               "PFAC_tableGetLayout")
+        info = self.info()
+
+        def arr(p, n, dt):
+            if n == 0 or not p.value:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)),
+                                         shape=(n,)).view(dt).copy()
+        root = arr(ptrs[0], 256, np.int32)
+        pre2 = arr(ptrs[1], 2048, np.uint32)
+        hot = arr(ptrs[2], info["hot_buckets"] * 4, np.uint32).reshape(-1, 4)
+        cold = arr(ptrs[3], info["cold_buckets"] * 4, np.uint32).reshape(-1, 4)
+        return root, pre2, hot, cold

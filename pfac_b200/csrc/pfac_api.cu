@@ -1,0 +1,630 @@
+// pfac_api.cu -- the C ABI of libpfac.so (include/PFAC.h, include/PFAC_ext.h): handle
+// lifecycle, argument checking in the reference's order, table upload, host-buffer pipelines.
+//
+// Mirrors the behaviour of reference PFAC/src/PFAC.cpp (each entry point cites its lines);
+// the implementation is new.  There is no CPU matcher in this library.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "PFAC.h"
+#include "PFAC_ext.h"
+#include "pfac_kernels.h"
+#include "pfac_table.h"
+
+namespace {
+
+constexpr size_t kFilenameLen = 256;            // reference PFAC_P.h FILENAME_LEN
+constexpr size_t kDefaultHotBytes = 24 * 1024;  // shared-memory budget for hot hash rows
+constexpr size_t kInt32Limit = size_t(1) << 31;
+
+size_t envBytes(const char* name, size_t dflt, size_t unit) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr;
+    unsigned long long x = strtoull(v, &end, 10);
+    if (end == v) return dflt;
+    return size_t(x) * unit;
+}
+
+struct HostPipe {  // cached buffers of the matchFromHost* pipelines
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    unsigned char* d_in[2] = {nullptr, nullptr};
+    int* d_out[2] = {nullptr, nullptr};  // dense results, or ids (reduce)
+    int* d_pos[2] = {nullptr, nullptr};  // reduce positions
+    size_t chunk = 0;                    // owned bytes per chunk
+    size_t inCap = 0;
+    bool hasPos = false;
+};
+
+}  // namespace
+
+struct PFAC_context {
+    int device = 0;
+    pfac::LaunchConfig launch;
+    int platform = PFAC_PLATFORM_GPU;
+    int textureMode = PFAC_AUTOMATIC;
+    int perfMode = PFAC_TIME_DRIVEN;
+    bool patternsReady = false;
+    cudaStream_t stream = nullptr;  // legacy default stream, as the reference
+    char patternFile[kFilenameLen] = {0};
+
+    pfac::Machine machine;
+    pfac::DeviceLayout layout;
+    pfac::DeviceTable table;
+    void* d_root = nullptr;
+    void* d_pre2 = nullptr;
+    void* d_hot = nullptr;
+    void* d_cold = nullptr;
+
+    std::mutex pipeMu;  // held for a whole matchFromHost* call (host pipeline buffers)
+    std::mutex mu;      // guards the reduce workspace (several host threads may share a handle)
+    unsigned long long* d_ws = nullptr;
+    size_t wsWords = 0;
+    unsigned long long* d_total = nullptr;
+    unsigned long long* h_total = nullptr;  // pinned
+    HostPipe pipe;
+};
+
+namespace {
+
+void freeDeviceTable(PFAC_handle_t h) {
+    cudaFree(h->d_root); h->d_root = nullptr;
+    cudaFree(h->d_pre2); h->d_pre2 = nullptr;
+    cudaFree(h->d_hot); h->d_hot = nullptr;
+    cudaFree(h->d_cold); h->d_cold = nullptr;
+    h->table = pfac::DeviceTable();
+}
+
+void freePatterns(PFAC_handle_t h) {  // reference PFAC_freeResource, PFAC.cpp:221-296
+    freeDeviceTable(h);
+    h->machine = pfac::Machine();
+    h->layout = pfac::DeviceLayout();
+    h->patternsReady = false;
+}
+
+void freePipe(HostPipe& p) {
+    for (int i = 0; i < 2; i++) {
+        if (p.d_in[i]) cudaFree(p.d_in[i]);
+        if (p.d_out[i]) cudaFree(p.d_out[i]);
+        if (p.d_pos[i]) cudaFree(p.d_pos[i]);
+        if (p.done[i]) cudaEventDestroy(p.done[i]);
+        if (p.stream[i]) cudaStreamDestroy(p.stream[i]);
+    }
+    p = HostPipe();
+}
+
+PFAC_status_t uploadArray(void** dst, const void* src, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(dst, bytes) != cudaSuccess) { *dst = nullptr; return PFAC_STATUS_CUDA_ALLOC_FAILED; }
+    if (src && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+        return PFAC_STATUS_INTERNAL_ERROR;
+    return PFAC_STATUS_SUCCESS;
+}
+
+size_t hotBudget(PFAC_handle_t h) {
+    if (h->perfMode == PFAC_SPACE_DRIVEN) return 0;
+    return envBytes("PFAC_B200_HOT_KB", kDefaultHotBytes / 1024, 1024);
+}
+
+// compile the device layout for the current perf mode and upload it (reference PFAC_bindTable,
+// PFAC.cpp:321-343, which picks the dense 2-D table or the hash table)
+PFAC_status_t bindTable(PFAC_handle_t h) {
+    freeDeviceTable(h);
+    pfac::compileLayout(h->machine, hotBudget(h), h->layout);
+    const pfac::DeviceLayout& L = h->layout;
+    PFAC_status_t st;
+    if ((st = uploadArray(&h->d_root, L.root, sizeof(L.root))) != PFAC_STATUS_SUCCESS) return st;
+    if ((st = uploadArray(&h->d_pre2, L.pre2.data(), L.pre2.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+    if ((st = uploadArray(&h->d_hot, L.hot.data(), L.hot.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+    if ((st = uploadArray(&h->d_cold, L.cold.data(), L.cold.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+    pfac::DeviceTable& t = h->table;
+    t.root = static_cast<const int32_t*>(h->d_root);
+    t.pre2 = static_cast<const uint32_t*>(h->d_pre2);
+    t.hot = static_cast<const uint4*>(h->d_hot);
+    t.cold = static_cast<const uint4*>(h->d_cold);
+    t.hotBuckets = L.hotBuckets;
+    t.coldBuckets = L.coldBuckets;
+    t.mul = L.mul;
+    t.hotDepth = L.hotDepth;
+    t.numFinal = h->machine.numFinal;
+    t.maxPatternLen = h->machine.maxPatternLen;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t loadImage(PFAC_handle_t h, const char* image, size_t size) {
+    int st = pfac::buildMachine(image, size, h->machine);
+    if (st != PFAC_STATUS_SUCCESS) { freePatterns(h); return PFAC_status_t(st); }
+    h->patternsReady = true;
+    PFAC_status_t bs = bindTable(h);
+    if (bs != PFAC_STATUS_SUCCESS) { freePatterns(h); return bs; }
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t readWholeFile(const char* filename, std::string& out) {
+    FILE* fp = fopen(filename, "rb");
+    if (!fp) return PFAC_STATUS_FILE_OPEN_ERROR;
+    fseek(fp, 0, SEEK_END);
+    long sz = ftell(fp);
+    rewind(fp);
+    if (sz < 0) { fclose(fp); return PFAC_STATUS_FILE_OPEN_ERROR; }
+    out.resize(size_t(sz));
+    size_t got = sz ? fread(&out[0], 1, size_t(sz), fp) : 0;
+    fclose(fp);
+    out.resize(got);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t cudaToStatus(cudaError_t e) {
+    if (e == cudaSuccess) return PFAC_STATUS_SUCCESS;
+    if (e == cudaErrorMemoryAllocation) return PFAC_STATUS_CUDA_ALLOC_FAILED;
+    return PFAC_STATUS_INTERNAL_ERROR;
+}
+
+// workspace for one reduce launch; caller holds h->mu
+PFAC_status_t ensureReduceWorkspace(PFAC_handle_t h, size_t words) {
+    if (!h->d_total) {
+        if (cudaMalloc(reinterpret_cast<void**>(&h->d_total), 16) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
+        if (cudaMallocHost(reinterpret_cast<void**>(&h->h_total), 16) != cudaSuccess) return PFAC_STATUS_ALLOC_FAILED;
+    }
+    if (words > h->wsWords) {
+        cudaFree(h->d_ws);
+        h->d_ws = nullptr;
+        h->wsWords = 0;
+        size_t want = words + words / 4 + 1024;
+        if (cudaMalloc(reinterpret_cast<void**>(&h->d_ws), want * 8) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
+        h->wsWords = want;
+    }
+    return PFAC_STATUS_SUCCESS;
+}
+
+// one fused match+compaction over a device shard; synchronous (returns the count)
+PFAC_status_t reduceShard(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
+                          long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
+                          unsigned long long* count) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    const size_t words = pfac::reduceWorkspaceWords(n_owned);
+    PFAC_status_t st = ensureReduceWorkspace(h, words);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    if (cudaMemsetAsync(h->d_ws, 0, words * 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    if (cudaMemsetAsync(h->d_total, 0, 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    cudaError_t e = pfac::launchMatchReduce(h->table, h->launch, d_in, n_owned, n_total, pos_base, d_id,
+                                            d_pos, pos64, h->d_ws, h->d_total, stream);
+    if (e != cudaSuccess) return cudaToStatus(e);
+    if (cudaMemcpyAsync(h->h_total, h->d_total, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+        return PFAC_STATUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    *count = *h->h_total;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// host pipeline buffers; caller holds h->pipeMu
+PFAC_status_t ensurePipe(PFAC_handle_t h, bool needPos) {
+    HostPipe& p = h->pipe;
+    const size_t chunk = envBytes("PFAC_B200_HOST_CHUNK_MB", 32, size_t(1) << 20);
+    const size_t halo = size_t(h->machine.maxPatternLen > 1 ? h->machine.maxPatternLen - 1 : 0);
+    const size_t inCap = ((chunk + halo + 255) / 256) * 256;
+    if (p.chunk == chunk && p.inCap >= inCap && (!needPos || p.hasPos)) return PFAC_STATUS_SUCCESS;
+    freePipe(p);
+    for (int i = 0; i < 2; i++) {
+        if (cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        if (cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        if (cudaMalloc(reinterpret_cast<void**>(&p.d_in[i]), inCap) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
+        if (cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
+        if (needPos && cudaMalloc(reinterpret_cast<void**>(&p.d_pos[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
+    }
+    p.chunk = chunk;
+    p.inCap = inCap;
+    p.hasPos = needPos;
+    return PFAC_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* PFAC_versionString(void) { return "pfac-b200 sm_100a"; }
+
+// reference PFAC.cpp:133-204.  No per-arch module to dlopen: the sm_100a kernels are in this
+// library.  Without a usable device the raw CUDA error is returned, as the reference does.
+PFAC_status_t PFAC_create(PFAC_handle_t* handle) {
+    if (!handle) return PFAC_STATUS_INVALID_PARAMETER;
+    *handle = nullptr;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return PFAC_status_t(e);
+    int major = 0, sms = 0;
+    if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device)) != cudaSuccess) return PFAC_status_t(e);
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return PFAC_status_t(e);
+    if (major != 10) return PFAC_STATUS_ARCH_MISMATCH;  // kernels are built for sm_100a only
+    PFAC_context* h = new (std::nothrow) PFAC_context();
+    if (!h) return PFAC_STATUS_ALLOC_FAILED;
+    h->device = device;
+    h->launch.numSMs = sms;
+    h->launch.ctasPerSM = int(envBytes("PFAC_B200_CTAS_PER_SM", 0, 1));
+    *handle = h;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:207-218
+PFAC_status_t PFAC_destroy(PFAC_handle_t handle) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    freePatterns(handle);
+    freePipe(handle->pipe);
+    cudaFree(handle->d_ws);
+    cudaFree(handle->d_total);
+    if (handle->h_total) cudaFreeHost(handle->h_total);
+    delete handle;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:741-757
+PFAC_status_t PFAC_setPlatform(PFAC_handle_t handle, PFAC_platform_t platform) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (platform != PFAC_PLATFORM_GPU && platform != PFAC_PLATFORM_CPU && platform != PFAC_PLATFORM_CPU_OMP)
+        return PFAC_STATUS_INVALID_PARAMETER;
+    handle->platform = int(platform);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:764-780
+PFAC_status_t PFAC_setTextureMode(PFAC_handle_t handle, PFAC_textureMode_t mode) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (mode != PFAC_AUTOMATIC && mode != PFAC_TEXTURE_ON && mode != PFAC_TEXTURE_OFF)
+        return PFAC_STATUS_INVALID_PARAMETER;
+    handle->textureMode = int(mode);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:782-817: a mode change with patterns loaded rebuilds the device table
+PFAC_status_t PFAC_setPerfMode(PFAC_handle_t handle, PFAC_perfMode_t mode) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (mode != PFAC_TIME_DRIVEN && mode != PFAC_SPACE_DRIVEN) return PFAC_STATUS_INVALID_PARAMETER;
+    const bool rebuild = handle->patternsReady && (int(mode) != handle->perfMode);
+    handle->perfMode = int(mode);
+    if (rebuild) {
+        std::lock_guard<std::mutex> lock(handle->mu);
+        cudaDeviceSynchronize();  // no kernel may still be reading the old table
+        PFAC_status_t st = bindTable(handle);
+        if (st != PFAC_STATUS_SUCCESS) { freeDeviceTable(handle); return st; }
+    }
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:1131-1185 (same text: callers print these)
+const char* PFAC_getErrorString(PFAC_status_t status) {
+    if (status == PFAC_STATUS_SUCCESS) return "PFAC_STATUS_SUCCESS: operation is successful";
+    if (status < PFAC_STATUS_BASE) return cudaGetErrorString(cudaError_t(status));
+    static const char* const text[] = {
+        "PFAC_STATUS_ALLOC_FAILED: allocation fails on host memory",
+        "PFAC_STATUS_CUDA_ALLOC_FAILED: allocation fails on device memory",
+        "PFAC_STATUS_INVALID_HANDLE: handle is invalid (NULL)",
+        "PFAC_STATUS_INVALID_PARAMETER: parameter is invalid",
+        "PFAC_STATUS_PATTERNS_NOT_READY: please call PFAC_readPatternFromFile() first",
+        "PFAC_STATUS_FILE_OPEN_ERROR: pattern file does not exist",
+        "PFAC_STATUS_LIB_NOT_EXIST: cannot find PFAC library, please check LD_LIBRARY_PATH",
+        "PFAC_STATUS_ARCH_MISMATCH: sm1.0 is not supported",
+        "PFAC_STATUS_MUTEX_ERROR: please report bugs. Workaround: choose non-texture mode.",
+    };
+    const int idx = int(status) - int(PFAC_STATUS_ALLOC_FAILED);
+    if (idx >= 0 && idx < int(sizeof(text) / sizeof(text[0]))) return text[idx];
+    return "PFAC_STATUS_INTERNAL_ERROR: please report bugs";
+}
+
+// reference PFAC.cpp:1188-1246
+PFAC_status_t PFAC_dumpTransitionTable(PFAC_handle_t handle, FILE* fp) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!fp) fp = stdout;
+    pfac::dumpMachine(handle->machine, fp);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_dumpTransitionTableToFile(PFAC_handle_t handle, const char* filename) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!filename) return PFAC_STATUS_INVALID_PARAMETER;
+    FILE* fp = fopen(filename, "w");
+    if (!fp) return PFAC_STATUS_FILE_OPEN_ERROR;
+    pfac::dumpMachine(handle->machine, fp);
+    fclose(fp);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:653-735
+PFAC_status_t PFAC_readPatternFromFile(PFAC_handle_t handle, char* filename) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!filename) return PFAC_STATUS_INVALID_PARAMETER;
+    std::lock_guard<std::mutex> lock(handle->mu);
+    if (handle->patternsReady) {
+        cudaDeviceSynchronize();
+        freePatterns(handle);
+    }
+    if (strlen(filename) >= kFilenameLen) return PFAC_STATUS_INTERNAL_ERROR;  // as :668-672
+    strcpy(handle->patternFile, filename);
+    std::string image;
+    PFAC_status_t st = readWholeFile(filename, image);
+    if (st != PFAC_STATUS_SUCCESS) { freePatterns(handle); return st; }
+    return loadImage(handle, image.data(), image.size());
+}
+
+PFAC_status_t PFAC_readPatternFromMemory(PFAC_handle_t handle, const char* image, size_t size) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!image && size) return PFAC_STATUS_INVALID_PARAMETER;
+    std::lock_guard<std::mutex> lock(handle->mu);
+    if (handle->patternsReady) {
+        cudaDeviceSynchronize();
+        freePatterns(handle);
+    }
+    handle->patternFile[0] = 0;
+    return loadImage(handle, image, size);
+}
+
+PFAC_status_t PFAC_setStream(PFAC_handle_t handle, void* cuda_stream) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    handle->stream = static_cast<cudaStream_t>(cuda_stream);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_matchShardFromDevice(PFAC_handle_t handle, const char* d_in, size_t n_owned,
+                                        size_t n_total, int* d_out) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!d_in || !d_out) return PFAC_STATUS_INVALID_PARAMETER;
+    if (n_total < n_owned) return PFAC_STATUS_INVALID_PARAMETER;
+    if (n_owned == 0) return PFAC_STATUS_SUCCESS;
+    return cudaToStatus(pfac::launchMatchDense(handle->table, handle->launch,
+                                               reinterpret_cast<const unsigned char*>(d_in), n_owned,
+                                               n_total, d_out, handle->stream));
+}
+
+// reference PFAC.cpp:843-876: same checks in the same order; platform is immaterial
+PFAC_status_t PFAC_matchFromDevice(PFAC_handle_t handle, char* d_in, size_t size, int* d_out) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!d_in) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!d_out) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    return cudaToStatus(pfac::launchMatchDense(handle->table, handle->launch,
+                                               reinterpret_cast<const unsigned char*>(d_in), size, size,
+                                               d_out, handle->stream));
+}
+
+// reference PFAC.cpp:879-961.  Chunks of the host input (+ tail halo) go H2D on two private
+// streams, each followed by its kernel and the D2H of its 4-byte-per-position results, so
+// copy-in, match and copy-out of neighbouring chunks overlap.  Synchronous, like the reference.
+PFAC_status_t PFAC_matchFromHost(PFAC_handle_t handle, char* h_in, size_t size, int* h_out) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!h_in) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_out) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    std::lock_guard<std::mutex> lock(handle->pipeMu);
+    PFAC_status_t st = ensurePipe(handle, false);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    HostPipe& p = handle->pipe;
+    const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
+    cudaError_t e = cudaSuccess;
+    int slot = 0;
+    for (size_t off = 0; off < size && e == cudaSuccess; off += p.chunk, slot ^= 1) {
+        const size_t owned = (size - off < p.chunk) ? size - off : p.chunk;
+        const size_t total = (size - off < owned + halo) ? size - off : owned + halo;
+        cudaStream_t s = p.stream[slot];
+        e = cudaMemcpyAsync(p.d_in[slot], h_in + off, total, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) break;
+        e = pfac::launchMatchDense(handle->table, handle->launch, p.d_in[slot], owned, total, p.d_out[slot], s);
+        if (e != cudaSuccess) break;
+        e = cudaMemcpyAsync(h_out + off, p.d_out[slot], owned * sizeof(int), cudaMemcpyDeviceToHost, s);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(p.stream[0]);
+    cudaError_t e1 = cudaStreamSynchronize(p.stream[1]);
+    if (e != cudaSuccess) return cudaToStatus(e);
+    if (e0 != cudaSuccess) return cudaToStatus(e0);
+    return cudaToStatus(e1);
+}
+
+PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char* d_in, size_t n_owned,
+                                                size_t n_total, long long pos_base, int* d_id,
+                                                long long* d_pos, unsigned long long* h_num) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!d_in || !h_num || !d_pos || !d_id) return PFAC_STATUS_INVALID_PARAMETER;
+    if (n_total < n_owned) return PFAC_STATUS_INVALID_PARAMETER;
+    *h_num = 0;
+    if (n_owned == 0) return PFAC_STATUS_SUCCESS;
+    return reduceShard(handle, reinterpret_cast<const unsigned char*>(d_in), n_owned, n_total, pos_base,
+                       d_id, d_pos, true, handle->stream, h_num);
+}
+
+PFAC_status_t PFAC_matchFromDeviceReduce64(PFAC_handle_t handle, const char* d_in, size_t size, int* d_id,
+                                           long long* d_pos, unsigned long long* h_num) {
+    return PFAC_matchShardFromDeviceReduce64(handle, d_in, size, size, 0, d_id, d_pos, h_num);
+}
+
+// reference PFAC.cpp:964-1008.  NULL checks are the reference's, in its order: handle, input,
+// h_num_matched, d_pos (it checks neither isPatternsReady nor d_matched_result; with no
+// patterns the reference would dereference a NULL table -- here that is PATTERNS_NOT_READY).
+PFAC_status_t PFAC_matchFromDeviceReduce(PFAC_handle_t handle, char* d_in, size_t size, int* d_id,
+                                         int* d_pos, int* h_num) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!d_in) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_num) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!d_pos) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!d_id) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size >= kInt32Limit) return PFAC_STATUS_INVALID_PARAMETER;  // int positions; use the 64-bit call
+    unsigned long long count = 0;
+    PFAC_status_t st = reduceShard(handle, reinterpret_cast<const unsigned char*>(d_in), size, size, 0, d_id,
+                                   d_pos, false, handle->stream, &count);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    *h_num = int(count);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_reduceOnDevice(PFAC_handle_t handle, char* d_in, size_t size, int* d_id, int* d_pos,
+                                  int* h_num) {
+    return PFAC_matchFromDeviceReduce(handle, d_in, size, d_id, d_pos, h_num);
+}
+
+PFAC_status_t PFAC_reduceInplaceOnDevice(PFAC_handle_t handle, char* d_in, size_t size, int* d_id,
+                                         int* d_pos, int* h_num) {
+    return PFAC_matchFromDeviceReduce(handle, d_in, size, d_id, d_pos, h_num);
+}
+
+// reference PFAC.cpp:1010-1128.  Chunked: H2D of chunk c+1 overlaps the fused match+compaction
+// of chunk c; only 8 bytes per match come back.  Positions are global (chunk offset added on
+// the device), lists are appended in chunk order, so the result is ascending in position.
+PFAC_status_t PFAC_matchFromHostReduce(PFAC_handle_t handle, char* h_in, size_t size, int* h_id, int* h_pos,
+                                       int* h_num) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!h_in) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_id) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_pos) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_num) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    if (size >= kInt32Limit) return PFAC_STATUS_INVALID_PARAMETER;
+    std::lock_guard<std::mutex> lock(handle->pipeMu);
+    {
+        PFAC_status_t st = ensurePipe(handle, true);
+        if (st != PFAC_STATUS_SUCCESS) return st;
+    }
+    HostPipe& p = handle->pipe;
+    const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
+    size_t written = 0;
+    int slot = 0;
+    // prefetch the first chunk, then: [H2D next chunk on the other stream] || [reduce this chunk]
+    auto stageIn = [&](size_t off, int sl) -> cudaError_t {
+        const size_t owned = (size - off < p.chunk) ? size - off : p.chunk;
+        const size_t total = (size - off < owned + halo) ? size - off : owned + halo;
+        return cudaMemcpyAsync(p.d_in[sl], h_in + off, total, cudaMemcpyHostToDevice, p.stream[sl]);
+    };
+    if (stageIn(0, 0) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    for (size_t off = 0; off < size; off += p.chunk, slot ^= 1) {
+        const size_t owned = (size - off < p.chunk) ? size - off : p.chunk;
+        const size_t total = (size - off < owned + halo) ? size - off : owned + halo;
+        if (off + p.chunk < size && stageIn(off + p.chunk, slot ^ 1) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        unsigned long long count = 0;
+        PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, total, (long long)off, p.d_out[slot],
+                                       p.d_pos[slot], false, p.stream[slot], &count);
+        if (st != PFAC_STATUS_SUCCESS) { cudaDeviceSynchronize(); return st; }
+        if (count) {
+            if (cudaMemcpyAsync(h_id + written, p.d_out[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess ||
+                cudaMemcpyAsync(h_pos + written, p.d_pos[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess) {
+                cudaDeviceSynchronize();
+                return PFAC_STATUS_INTERNAL_ERROR;
+            }
+            written += count;
+        }
+        // the slot is reused two chunks later: its D2H must have drained before the next H2D into it
+        if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    }
+    if (cudaStreamSynchronize(p.stream[0]) != cudaSuccess || cudaStreamSynchronize(p.stream[1]) != cudaSuccess)
+        return PFAC_STATUS_INTERNAL_ERROR;
+    *h_num = int(written);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// ---- host-only table compiler --------------------------------------------------------------
+struct PFAC_table {
+    pfac::Machine machine;
+    pfac::DeviceLayout layout;
+};
+
+static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_tableInfo_t* info) {
+    info->num_patterns = m.numPatterns;
+    info->num_states = m.numStates;
+    info->initial_state = m.initialState;
+    info->max_pattern_len = m.maxPatternLen;
+    info->num_leaves = m.numLeaves;
+    info->num_edges = L.numEdges + L.rootFanout;
+    info->max_depth = L.maxDepth;
+    info->hot_depth = L.hotDepth;
+    info->hot_buckets = L.hotBuckets;
+    info->cold_buckets = L.coldBuckets;
+    info->hash_mul = L.mul;
+    info->hot_max_probe = L.hotMaxProbe;
+    info->cold_max_probe = L.coldMaxProbe;
+    info->pre2_bits_set = L.pre2BitsSet;
+    info->root_fanout = L.rootFanout;
+    info->device_bytes = L.deviceBytes();
+}
+
+PFAC_status_t PFAC_tableCompile(const char* image, size_t size, size_t hot_budget_bytes, PFAC_table_t* table) {
+    if (!table) return PFAC_STATUS_INVALID_PARAMETER;
+    *table = nullptr;
+    PFAC_table* t = new (std::nothrow) PFAC_table();
+    if (!t) return PFAC_STATUS_ALLOC_FAILED;
+    int st = pfac::buildMachine(image, size, t->machine);
+    if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
+    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout);
+    *table = t;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableCompileFile(const char* filename, size_t hot_budget_bytes, PFAC_table_t* table) {
+    if (!filename || !table) return PFAC_STATUS_INVALID_PARAMETER;
+    std::string image;
+    PFAC_status_t st = readWholeFile(filename, image);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    return PFAC_tableCompile(image.data(), image.size(), hot_budget_bytes, table);
+}
+
+PFAC_status_t PFAC_tableDestroy(PFAC_table_t table) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    delete table;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableDump(PFAC_table_t table, FILE* fp) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    pfac::dumpMachine(table->machine, fp ? fp : stdout);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableDumpToFile(PFAC_table_t table, const char* filename) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    if (!filename) return PFAC_STATUS_INVALID_PARAMETER;
+    FILE* fp = fopen(filename, "w");
+    if (!fp) return PFAC_STATUS_FILE_OPEN_ERROR;
+    pfac::dumpMachine(table->machine, fp);
+    fclose(fp);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableGetInfo(PFAC_table_t table, PFAC_tableInfo_t* info) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    if (!info) return PFAC_STATUS_INVALID_PARAMETER;
+    fillInfo(table->machine, table->layout, info);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int** root, const unsigned** pre2,
+                                  const unsigned** hot, const unsigned** cold) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    if (root) *root = table->layout.root;
+    if (pre2) *pre2 = table->layout.pre2.data();
+    if (hot) *hot = table->layout.hot.data();
+    if (cold) *cold = table->layout.cold.data();
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!info) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    fillInfo(handle->machine, handle->layout, info);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// bench.py reports how many of this library's kernels ran inside its timed region
+unsigned long long PFAC_kernelLaunchCount(void) { return pfac::kernelLaunchCount(); }
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,46 @@
+// pfac_kernels.h -- launch interface of the sm_100a matching kernels (pfac_kernels.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace pfac {
+
+// Device-resident compiled table (uploaded by the handle).
+struct DeviceTable {
+    const int32_t* root = nullptr;    // 256
+    const uint32_t* pre2 = nullptr;   // 2048
+    const uint4* hot = nullptr;       // hotBuckets (copied into shared memory by each CTA)
+    const uint4* cold = nullptr;      // coldBuckets (read through L1/L2)
+    uint32_t hotBuckets = 0;
+    uint32_t coldBuckets = 1;
+    uint32_t mul = 0;
+    int hotDepth = 1;
+    int numFinal = 0;
+    int maxPatternLen = 0;
+};
+
+struct LaunchConfig {
+    int numSMs = 148;
+    int ctasPerSM = 0;   // 0 = ask the occupancy API
+};
+
+// Look-back descriptor words needed by the reduce kernel for an n_owned-byte shard.
+size_t reduceWorkspaceWords(size_t n_owned);
+
+// Dense result: out[i] for i in [0,n_owned); walks may read in[0,n_total).
+cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
+                             size_t n_owned, size_t n_total, int* out, cudaStream_t stream);
+
+// Fused match + ordered compaction.  desc: reduceWorkspaceWords(n_owned) zeroed uint64 words.
+// d_total: one uint64 receiving the match count.  pos64 selects long long vs int positions.
+cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
+                              size_t n_owned, size_t n_total, long long pos_base, int* out_id,
+                              void* out_pos, bool pos64, unsigned long long* desc,
+                              unsigned long long* d_total, cudaStream_t stream);
+
+// Number of kernels launched by this library since load (bench.py reports it).
+unsigned long long kernelLaunchCount();
+
+}  // namespace pfac

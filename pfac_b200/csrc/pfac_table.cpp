@@ -1,0 +1,296 @@
+// pfac_table.cpp -- table compiler (host only).  See pfac_table.h.
+#include "pfac_table.h"
+
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+
+#include "PFAC.h"
+
+namespace pfac {
+
+namespace {
+
+struct Pat {
+    size_t off;
+    int id;
+};
+
+// Order of reference pattern_cmp_functor (PFAC_reorder_Table.cpp:37-72): '\n'-terminated,
+// plain char (signed on x86-64: 0x80..0xFF sort before 0x00..0x7F), proper prefix first.
+// The reference returns true for equal strings (not a strict weak order); here equal strings
+// compare "not less" and std::stable_sort keeps file order, so of two identical patterns the
+// later ID wins in the matching table.
+struct PatLess {
+    const char* base;
+    bool operator()(const Pat& a, const Pat& b) const {
+        const signed char* s = reinterpret_cast<const signed char*>(base + a.off);
+        const signed char* t = reinterpret_cast<const signed char*>(base + b.off);
+        for (;;) {
+            signed char sc = *s++, tc = *t++;
+            bool se = (sc == '\n'), te = (tc == '\n');
+            if (se || te) return se && !te;
+            if (sc < tc) return true;
+            if (sc > tc) return false;
+        }
+    }
+};
+
+inline uint32_t edgeKey(int state, int ch) { return (uint32_t(state) << 8) | uint32_t(ch); }
+
+inline uint32_t homeBucket(uint32_t key, uint32_t mul, uint32_t nb) {
+    return uint32_t((uint64_t(key * mul) * uint64_t(nb)) >> 32);
+}
+
+struct FlatEdge {
+    uint32_t key;
+    int next;
+    int depth;  // depth of the source state
+};
+
+// Fill a bucketed table; returns the longest probe sequence (in buckets) over all keys.
+int fillBuckets(const std::vector<FlatEdge>& edges, size_t begin, size_t end, uint32_t nb,
+                uint32_t mul, std::vector<uint32_t>& out) {
+    out.assign(size_t(nb) * 4, kEmptyKey);
+    int maxProbe = 0;
+    for (size_t i = begin; i < end; i++) {
+        uint32_t b = homeBucket(edges[i].key, mul, nb);
+        int probe = 1;
+        for (;;) {
+            uint32_t* e = &out[size_t(b) * 4];
+            if (e[0] == kEmptyKey) { e[0] = edges[i].key; e[1] = uint32_t(edges[i].next); break; }
+            if (e[2] == kEmptyKey) { e[2] = edges[i].key; e[3] = uint32_t(edges[i].next); break; }
+            b = (b + 1 == nb) ? 0 : b + 1;
+            probe++;
+        }
+        maxProbe = std::max(maxProbe, probe);
+    }
+    // a miss stops at the first bucket whose slot 1 is empty: its worst case is the longest
+    // run of full buckets + 1
+    int run = 0, longest = 0;
+    for (uint32_t pass = 0; pass < 2 * nb; pass++) {
+        uint32_t b = pass % nb;
+        if (out[size_t(b) * 4 + 2] != kEmptyKey) { run++; longest = std::max(longest, run); if (run >= int(nb)) break; }
+        else run = 0;
+    }
+    return std::max(maxProbe, longest + 1);
+}
+
+}  // namespace
+
+int buildMachine(const char* image, size_t size, Machine& m) {
+    m = Machine();
+    if (image == nullptr && size != 0) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size >= size_t(kMaxStates)) return PFAC_STATUS_INTERNAL_ERROR;  // states <= size+2
+    m.image.assign(image ? image : "", size);
+    m.image.push_back('\n');
+    const char* buf = m.image.data();
+
+    // Line split, reference PFAC_reorder_Table.cpp:176-193: only 0x0A separates; the '\n' at
+    // i closes a pattern iff i>0 && buf[i-1] != '\n'; an unterminated last line is dropped.
+    std::vector<Pat> pats;
+    std::vector<int> lens;
+    size_t lineStart = 0;
+    bool pendingBlank = false;
+    for (size_t i = 0; i < size; i++) {
+        if (buf[i] != '\n') continue;
+        if (i > 0 && buf[i - 1] != '\n') {
+            // the reference would hand the trie builder a pointer to the blank line here and
+            // abort on assert('\n' != ch) (:291); report it instead
+            if (pendingBlank) { m = Machine(); return PFAC_STATUS_INVALID_PARAMETER; }
+            pats.push_back(Pat{lineStart, int(pats.size()) + 1});
+            lens.push_back(int(i - lineStart));
+        } else {
+            pendingBlank = true;
+        }
+        lineStart = i + 1;
+    }
+    const int k = int(pats.size());
+    m.numPatterns = m.numFinal = k;
+    m.initialState = k + 1;
+    m.lenById.assign(size_t(k) + 1, 0);
+    m.offById.assign(size_t(k) + 1, 0);
+    for (int i = 0; i < k; i++) {
+        m.lenById[size_t(i) + 1] = lens[size_t(i)];
+        m.offById[size_t(i) + 1] = pats[size_t(i)].off;
+        m.maxPatternLen = std::max(m.maxPatternLen, lens[size_t(i)]);
+    }
+    std::stable_sort(pats.begin(), pats.end(), PatLess{buf});
+    m.sortedOff.resize(size_t(k));
+    m.sortedId.resize(size_t(k));
+    for (int i = 0; i < k; i++) {
+        m.sortedOff[size_t(i)] = pats[size_t(i)].off;
+        m.sortedId[size_t(i)] = pats[size_t(i)].id;
+    }
+
+    // Trie with the reference numbering (PFAC_reorder_Table.cpp:279-321): state 0 unused,
+    // finals 1..k = pattern ids, initial k+1, internal states from k+2 in first-visit order.
+    // The last byte of a pattern ALWAYS appends (state,ch)->id; traversal follows the FIRST
+    // edge for a byte (lookup(), :234-244).
+    m.rows.assign(size_t(k) + 2, std::vector<Edge>());
+    std::unordered_map<uint32_t, int> firstEdge;
+    firstEdge.reserve(size * 2 + 16);
+    int stateNum = m.initialState + 1;
+    for (int p = 0; p < k; p++) {
+        const unsigned char* pos = reinterpret_cast<const unsigned char*>(buf + m.sortedOff[size_t(p)]);
+        const int id = m.sortedId[size_t(p)];
+        const int len = m.lenById[size_t(id)];
+        int state = m.initialState;
+        for (int off = 0; off < len; off++) {
+            const int ch = pos[off];
+            const uint32_t key = edgeKey(state, ch);
+            if (off == len - 1) {
+                m.rows[size_t(state)].push_back(Edge{ch, id});
+                firstEdge.emplace(key, id);  // keeps an earlier edge if one exists
+            } else {
+                auto it = firstEdge.find(key);
+                if (it == firstEdge.end()) {
+                    m.rows[size_t(state)].push_back(Edge{ch, stateNum});
+                    firstEdge.emplace(key, stateNum);
+                    m.rows.emplace_back();
+                    state = stateNum++;
+                } else {
+                    state = it->second;
+                }
+            }
+        }
+    }
+    m.numStates = stateNum;
+    if (m.numStates > kMaxStates) { m = Machine(); return PFAC_STATUS_INTERNAL_ERROR; }
+    m.rows.resize(size_t(m.numStates));
+    for (int i = 1; i <= k; i++)
+        if (m.rows[size_t(i)].empty()) m.numLeaves++;  // reference PFAC.cpp:716-722
+    return PFAC_STATUS_SUCCESS;
+}
+
+void dumpMachine(const Machine& m, FILE* fp) {
+    fprintf(fp, "# Transition table: number of states = %d, initial state = %d\n", m.numStates,
+            m.initialState);
+    fprintf(fp, "# (current state, input character) -> next state \n");
+    for (int s = 0; s < m.numStates; s++) {
+        for (const Edge& e : m.rows[size_t(s)]) {
+            if (e.ch >= 32 && e.ch <= 126) fprintf(fp, "(%4d,%4c) -> %d \n", s, e.ch, e.next);
+            else fprintf(fp, "(%4d,%4.2x) -> %d \n", s, e.ch, e.next);
+        }
+    }
+    fprintf(fp, "# Output table: number of final states = %d\n", m.numFinal);
+    fprintf(fp, "# [final state] [matched pattern ID] [pattern length] [pattern(string literal)] \n");
+    for (int s = 1; s <= m.numFinal; s++) {
+        const int len = m.lenById[size_t(s)];
+        fprintf(fp, "%5d %5d %5d    ", s, s, len);
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(m.image.data() + m.offById[size_t(s)]);
+        fputc('"', fp);
+        for (int i = 0; i < len; i++) {
+            if (p[i] >= 32 && p[i] <= 126) fputc(p[i], fp);
+            else fprintf(fp, "%2.2x", p[i]);
+        }
+        fputc('"', fp);
+        fputc('\n', fp);
+    }
+}
+
+void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
+    L = DeviceLayout();
+    for (int c = 0; c < kCharSet; c++) L.root[c] = -1;
+    L.pre2.assign(65536 / 32, 0u);
+
+    // Matching edges: per (state,ch) the LAST edge in insertion order wins, as in the
+    // reference's dense table fill (PFAC.cpp:376-381).  BFS from the initial state gives the
+    // depth of every reachable source state.
+    std::vector<FlatEdge> edges;
+    std::vector<int> depth(size_t(std::max(m.numStates, 1)), -1);
+    std::vector<int> frontier;
+    if (m.numStates > m.initialState) {
+        depth[size_t(m.initialState)] = 0;
+        frontier.push_back(m.initialState);
+    }
+    int last[kCharSet];
+    std::fill(last, last + kCharSet, -1);
+    std::vector<int> touched;
+    for (size_t qi = 0; qi < frontier.size(); qi++) {
+        const int s = frontier[qi];
+        const std::vector<Edge>& row = m.rows[size_t(s)];
+        touched.clear();
+        for (size_t j = 0; j < row.size(); j++) {
+            if (last[row[j].ch] < 0) touched.push_back(row[j].ch);
+            last[row[j].ch] = int(j);
+        }
+        std::sort(touched.begin(), touched.end());
+        for (int ch : touched) {
+            const int nx = row[size_t(last[ch])].next;
+            last[ch] = -1;
+            if (depth[size_t(nx)] < 0) {
+                depth[size_t(nx)] = depth[size_t(s)] + 1;
+                frontier.push_back(nx);
+            }
+            if (s == m.initialState) L.root[ch] = nx;
+            else edges.push_back(FlatEdge{edgeKey(s, ch), nx, depth[size_t(s)]});
+            L.maxDepth = std::max(L.maxDepth, depth[size_t(s)] + 1);
+        }
+    }
+    L.numEdges = int(edges.size());
+    for (int c = 0; c < kCharSet; c++) if (L.root[c] >= 0) L.rootFanout++;
+
+    // Prefilter: bit (c0 | c1<<8) is set iff a walk starting with c0,c1 can produce a result:
+    // root[c0] is a final state (1-byte pattern: any c1), or (root[c0], c1) is an edge.
+    // Clear bit => result 0 with certainty; set bit => the walker decides.
+    for (int c0 = 0; c0 < kCharSet; c0++) {
+        if (L.root[c0] >= 0 && L.root[c0] <= m.numFinal)
+            for (int c1 = 0; c1 < kCharSet; c1++) {
+                uint32_t idx = uint32_t(c0) | (uint32_t(c1) << 8);
+                L.pre2[idx >> 5] |= 1u << (idx & 31);
+            }
+    }
+    {
+        std::unordered_map<int, int> c0OfState;  // depth-1 state -> the first byte leading to it
+        for (int c0 = 0; c0 < kCharSet; c0++)
+            if (L.root[c0] >= 0) c0OfState[L.root[c0]] = c0;
+        for (const FlatEdge& e : edges) {
+            if (e.depth != 1) continue;
+            const int src = int(e.key >> 8), c1 = int(e.key & 0xFF);
+            auto it = c0OfState.find(src);
+            if (it == c0OfState.end()) continue;
+            uint32_t idx = uint32_t(it->second) | (uint32_t(c1) << 8);
+            L.pre2[idx >> 5] |= 1u << (idx & 31);
+        }
+    }
+    for (uint32_t w : L.pre2) L.pre2BitsSet += __builtin_popcount(w);
+
+    // Hot/cold split by source depth.  The walker knows its depth (= bytes consumed), so
+    // which table to probe costs no lookup.  Load factor 0.5: buckets(2 slots) = #edges.
+    std::stable_sort(edges.begin(), edges.end(),
+                     [](const FlatEdge& a, const FlatEdge& b) { return a.depth < b.depth; });
+    std::vector<size_t> upto(size_t(L.maxDepth) + 2, 0);  // upto[d] = #edges with depth < d
+    for (const FlatEdge& e : edges) upto[size_t(e.depth) + 1]++;
+    for (size_t d = 1; d < upto.size(); d++) upto[d] += upto[d - 1];
+    const size_t hotSlots = hotBudgetBytes / 16;  // buckets affordable
+    int H = 1;  // upto[] is non-decreasing; upto[1] == 0 (root edges live in the root row)
+    for (int d = 2; d < int(upto.size()); d++) {
+        if (upto[size_t(d)] <= hotSlots) H = d;
+        else break;
+    }
+    L.hotDepth = H;
+    const size_t nHot = upto[size_t(H)];
+    const size_t nCold = edges.size() - nHot;
+    L.hotBuckets = uint32_t(nHot);         // 0 => kernels never probe the hot table
+    L.coldBuckets = uint32_t(std::max<size_t>(nCold, 1));
+
+    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu,
+                                    0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+    int bestHot = 1 << 30, bestCold = 1 << 30;
+    std::vector<uint32_t> hot, cold;
+    for (uint32_t mul : muls) {
+        int ph = 0, pc = 0;
+        if (L.hotBuckets) ph = fillBuckets(edges, 0, nHot, L.hotBuckets, mul, hot);
+        else hot.clear();
+        pc = fillBuckets(edges, nHot, edges.size(), L.coldBuckets, mul, cold);
+        if (ph < bestHot || (ph == bestHot && pc < bestCold)) {
+            bestHot = ph; bestCold = pc; L.mul = mul;
+            L.hot.swap(hot); L.cold.swap(cold);
+        }
+    }
+    L.hotMaxProbe = L.hotBuckets ? bestHot : 0;
+    L.coldMaxProbe = bestCold;
+}
+
+}  // namespace pfac

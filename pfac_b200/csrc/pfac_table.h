@@ -1,0 +1,71 @@
+// pfac_table.h -- host-side table compiler: pattern image -> reference-numbered automaton
+// -> B200 device layout.  No CUDA dependency.
+//
+// Reference behaviour restated (not copied) from PFAC/src/PFAC_reorder_Table.cpp:121-329
+// (parse, order, trie numbering) and PFAC/src/PFAC.cpp:345-402 (which edge wins in the
+// matching table).  The device layout is new: see DESIGN.md "Device layout".
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace pfac {
+
+constexpr int kCharSet = 256;
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;   // hash slot never holds (state<<8|ch) == this
+constexpr int kMaxStates = (1 << 24) - 2;     // state ids must fit 24 bits of the hash key
+
+struct Edge {
+    int ch;
+    int next;
+};
+
+// The automaton with the reference's state numbering (needed for a byte-identical dump and
+// because final-state ids ARE the pattern ids the kernels emit).
+struct Machine {
+    std::string image;               // pattern file bytes + '\n' sentinel
+    int numPatterns = 0;             // k
+    int numFinal = 0;                // k
+    int initialState = 0;            // k+1   (reference PFAC.cpp:693)
+    int numStates = 0;               // next unused id, counts the unused state 0
+    int maxPatternLen = 0;
+    int numLeaves = 0;
+    std::vector<size_t> sortedOff;   // pattern start offsets into image, sorted order
+    std::vector<int> sortedId;       // original 1-based id, sorted order
+    std::vector<int> lenById;        // [0..k], [0] = 0
+    std::vector<size_t> offById;     // [0..k]
+    std::vector<std::vector<Edge>> rows;  // per state, insertion order, duplicates kept
+};
+
+// Returns a PFAC_status_t value (0 = success).
+int buildMachine(const char* image, size_t size, Machine& m);
+
+// Text dump, byte-identical to reference PFAC_dumpTransitionTable (PFAC.cpp:1188-1246).
+void dumpMachine(const Machine& m, FILE* fp);
+
+// What gets uploaded.  Buckets are 4 x uint32 {key0, val0, key1, val1}, key = state<<8|ch,
+// slot 0 filled before slot 1, bucket = umulhi(key * mul, nbuckets), linear probing.
+struct DeviceLayout {
+    int32_t root[kCharSet];          // next state from the initial state, -1 = trap
+    std::vector<uint32_t> pre2;      // 65536-bit prefilter, index c0 | c1<<8
+    std::vector<uint32_t> hot;       // edges with source depth in [1,hotDepth)  -> smem
+    std::vector<uint32_t> cold;      // edges with source depth >= hotDepth      -> global/L2
+    uint32_t hotBuckets = 0, coldBuckets = 0;
+    uint32_t mul = 0x9E3779B1u;
+    int hotDepth = 1;
+    int maxDepth = 0;
+    int numEdges = 0;
+    int hotMaxProbe = 0, coldMaxProbe = 0;
+    int pre2BitsSet = 0;
+    int rootFanout = 0;
+    size_t deviceBytes() const {
+        return sizeof(root) + pre2.size() * 4 + hot.size() * 4 + cold.size() * 4;
+    }
+};
+
+// hotBudgetBytes: shared-memory bytes the kernels may spend on the hot hash rows.
+void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L);
+
+}  // namespace pfac

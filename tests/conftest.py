@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_libraries():
+    """Build the product library and the oracle once per session (no-ops when up to date)."""
+    from pfac_b200 import build as pbuild
+    import oracle
+    try:
+        pbuild.build()
+    except Exception as e:  # prebuilt .so may still be present (GPU box without nvcc is not expected)
+        if not os.path.exists(pbuild.LIB):
+            raise
+        print("warning: rebuild failed, using existing libpfac.so:", e)
+    if not os.path.exists(oracle.ORACLE_SO) or (
+            os.path.getmtime(os.path.join(oracle.HERE, "pfac_oracle.c")) > os.path.getmtime(oracle.ORACLE_SO)):
+        oracle.build()
+    yield
