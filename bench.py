@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE configs[1] = 1,000 synthetic patterns (len 4-32, 255-symbol
+alphabet) over 1 GiB of planted random text per GPU, PFAC_matchFromDevice (dense int32 result).
+One step = one pass of the hot path over the rank's resident 1 GiB shard (+ tail halo).  N > 1
+is weak scaling: rank r owns bytes [r GiB, (r+1) GiB) of an N GiB stream, no data-path
+collective.  value = total input GB (1e9 B) scanned by all ranks per second of the slowest rank.
+
+Extra objects on the JSON line: roofline (dominant kernel vs the measured HBM peak),
+cpu_baseline (reference CPU_OMP matcher on this box's host cores, rank 0, N=1), e2e (same
+metric through PFAC_matchFromHost with pinned host buffers, copies inside the timed region),
+reduce (the fused compaction path on the same shard, with the cross-GPU count scan at N>1).
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from pfac_b200 import synth  # noqa: E402
+
+GIB = 1 << 30
+METRIC = "input_GB_per_s_scanned"
+UNIT = "GB/s"
+TEXT_SEED = synth.SEED_BASE + 2
+N_PATTERNS = 1000
+
+
+def workload_config(bytes_per_gpu, n_gpus):
+    return {
+        "workload": "C2: %d synthetic patterns (len 4-32, 255-symbol alphabet, 50 prefix pairs) over "
+                    "%.3f GiB planted random text per GPU, PFAC_matchFromDevice dense int32 result"
+                    % (N_PATTERNS, bytes_per_gpu / GIB),
+        "patterns": N_PATTERNS,
+        "bytes_per_gpu": bytes_per_gpu,
+        "total_bytes": bytes_per_gpu * n_gpus,
+        "plant_every": 4096,
+        "sharding": "contiguous shards + (maxPatternLen-1)-byte tail halo, no data-path collective",
+        "l2": "5 B/position of traffic per step (>= 5 GiB) is far larger than the 126 MB L2: no flush",
+    }
+
+
+def make_shard(rank, world, bytes_per_gpu, patterns):
+    """Bytes [rank*B, (rank+1)*B + halo) of the world*B-byte stream, generated in 64 MiB pieces."""
+    total_len = bytes_per_gpu * world
+    halo = max(len(p) for p in patterns) - 1
+    start = rank * bytes_per_gpu
+    n = min(bytes_per_gpu + halo, total_len - start)
+    out = np.empty(n, dtype=np.uint8)
+    piece = 64 << 20
+    for off in range(0, n, piece):
+        m = min(piece, n - off)
+        out[off:off + m] = synth.random_bytes(TEXT_SEED, start + off, m)
+    synth.plant(out, start, total_len, patterns, TEXT_SEED, every=4096)
+    return out, min(bytes_per_gpu, n)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.period = period
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get("dense_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_reference(pfile, text, threads, reps, budget_s=None):
+    """Times the reference CPU_OMP matcher (oracle/_ref when built, else the oracle port)."""
+    import oracle
+    if oracle.ref_available():
+        cls, kind = oracle.RefOracle, "reference"
+    else:
+        cls, kind = oracle.Oracle, "port"
+    cls.set_threads(threads)
+    m = cls(pfile)
+    best = None
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        m.match(text, omp=True)
+        dt = time.perf_counter() - t0
+        times.append(dt)
+        best = dt if best is None else min(best, dt)
+        if budget_s is not None and sum(times) > budget_s:
+            break
+    return kind, cls.threads(), best, times
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on host cores."""
+    if rank != 0:
+        return
+    patterns = synth.patterns_c2(N_PATTERNS)
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as td:
+        pfile = synth.write_pattern_file(os.path.join(td, "c2.pat"), patterns)
+        # size the per-step sample so that (warmup + steps) passes end within ~2 minutes
+        probe_n = 32 << 20
+        probe, _ = make_shard(0, world, probe_n, patterns)
+        kind, threads, best, _ = cpu_reference(pfile, probe[:probe_n], cores, 1)
+        rate = probe_n / best  # B/s
+        want = int(rate * 120.0 / max(1, args.steps + args.warmup))
+        sample_n = max(16 << 20, min(args.bytes, want, GIB))
+        sample_n -= sample_n % 4096
+        text, _ = make_shard(0, world, sample_n, patterns)
+        text = text[:sample_n]
+        import oracle
+        cls = oracle.RefOracle if oracle.ref_available() else oracle.Oracle
+        cls.set_threads(cores)
+        m = cls(pfile)
+        for _ in range(args.warmup):
+            m.match(text, omp=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m.match(text, omp=True)
+        dt = time.perf_counter() - t0
+    value = sample_n * args.steps / dt / 1e9
+    sample = "first %.0f MiB of the rank-0 shard per step, PFAC_CPU_OMP_timeDriven, %d OpenMP threads" % (
+        sample_n / (1 << 20), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(args.bytes, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bytes", type=int, default=GIB, help="input bytes per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--reduce-steps", type=int, default=10)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-reduce", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pfac_b200 import PFAC
+    from pfac_b200.api import kernel_launch_count
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the library has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    patterns = synth.patterns_c2(N_PATTERNS)
+    tmpdir = tempfile.mkdtemp(prefix="pfac_bench_")
+    pfile = synth.write_pattern_file(os.path.join(tmpdir, "c2_rank%d.pat" % rank), patterns)
+    shard, owned = make_shard(rank, world, args.bytes, patterns)
+    total = shard.size
+
+    pf = PFAC()
+    pf.readPatternFromFile(pfile)
+    info = pf.tableInfo()
+    d_in = torch.from_numpy(shard).to(dev)
+    d_out = torch.empty(owned, dtype=torch.int32, device=dev)
+
+    def step():
+        pf.matchShardFromDevice(d_in, owned, total, d_out)
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = kernel_launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    launches = kernel_launch_count() - launches0
+    barrier()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    worst_ms = max_over_ranks(total_ms)
+    ms_per_step = worst_ms / args.steps
+    value = owned * world / (ms_per_step * 1e-3) / 1e9
+    sampler.join(timeout=1.0)
+    clocks = sampler.result()
+
+    # result digest (cheap proof that the timed kernel did the work)
+    n_matches = int((d_out != 0).sum().item())
+
+    # ---- roofline of the dominant kernel (this rank) -------------------------------------------
+    peak, peak_src = measured_peak()
+    avg_launch_ms = float(np.mean(per_launch_ms))
+    algo_bytes = 5 * owned  # 1 B read + 4 B written per position
+    achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pfac_match_kernel<dense>",
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_ms,
+                "median_launch_ms": float(np.median(per_launch_ms)), "best_launch_ms": float(np.min(per_launch_ms)),
+                "frac_of_8TBps_spec": achieved / 8000.0}
+
+    # ---- end to end through the host-buffer API ---------------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        h_in = torch.empty(owned, dtype=torch.uint8, pin_memory=True)
+        h_in.numpy()[:] = shard[:owned]
+        h_out = torch.empty(owned, dtype=torch.int32, pin_memory=True)
+        pf.matchFromHost(h_in, h_out, size=owned)  # warm-up: allocates the pipeline buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            pf.matchFromHost(h_in, h_out, size=owned)
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        e2e = {"value": owned * world * args.e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(owned), "d2h_bytes_per_step": int(owned) * 4,
+               "steps": args.e2e_steps, "api": "PFAC_matchFromHost (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
+        if world == 1:
+            # the shard ends at the end of the stream, so the host call and the shard call agree
+            assert bool((torch.from_numpy(h_out.numpy()).to(dev) == d_out).all().item()), "e2e result differs"
+        del h_in, h_out
+
+    # ---- fused reduce path on the same shard, with the cross-GPU count scan --------------------------
+    reduce_info = None
+    if not args.skip_reduce:
+        cap = max(owned // 16, 1 << 20)
+        d_id = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_pos = torch.empty(cap, dtype=torch.int64, device=dev)
+        base = rank * args.bytes
+        m = pf.matchShardFromDeviceReduce64(d_in, owned, total, base, d_id, d_pos)
+        barrier()
+        t0 = time.perf_counter()
+        coll_s = 0.0
+        for _ in range(args.reduce_steps):
+            m = pf.matchShardFromDeviceReduce64(d_in, owned, total, base, d_id, d_pos)
+            tc = time.perf_counter()
+            counts = torch.tensor([m], dtype=torch.int64, device=dev)
+            if world > 1:
+                allc = torch.empty(world, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allc, counts)  # NCCL: 8 bytes per rank
+            else:
+                allc = counts
+            offs = torch.cumsum(allc, 0) - allc          # exclusive scan: global output offsets
+            my_off = int(offs[rank].item())
+            coll_s += time.perf_counter() - tc
+        dt = max_over_ranks(time.perf_counter() - t0)
+        total_m = int(allc.sum().item())
+        assert m == n_matches, "reduce count %d != dense non-zeros %d" % (m, n_matches)
+        reduce_info = {"value": owned * world * args.reduce_steps / dt / 1e9, "unit": UNIT,
+                       "api": "PFAC_matchShardFromDeviceReduce64 + count all-gather/exclusive scan",
+                       "matches_total": total_m, "rank0_offset": my_off if rank == 0 else None,
+                       "count_scan_ms_per_step": coll_s / args.reduce_steps * 1e3,
+                       "algorithmic_bytes_per_step": int(owned + 12 * m), "steps": args.reduce_steps}
+
+    # ---- reference CPU path beside it (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if world == 1 and rank == 0 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        sample_n = min(owned, GIB)
+        kind, threads, best, times = cpu_reference(pfile, shard[:sample_n], cores, 3, budget_s=30.0)
+        cpu = {"value": sample_n / best / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "first %.0f MiB of the shard, best of %d passes of PFAC_CPU_OMP_timeDriven, %d threads"
+                         % (sample_n / (1 << 20), len(times), threads)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": dict(workload_config(args.bytes, world), states=info["num_states"],
+                           hot_depth=info["hot_depth"], hot_buckets=info["hot_buckets"],
+                           prefilter_pass_rate=info["pre2_bits_set"] / 65536.0, matches_per_gpu=n_matches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reduce": reduce_info,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "gbps_reference_unit": value * 8.0,
+        }
+        print(json.dumps(line), flush=True)
+    pf.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,8 @@ class Oracle:
             L.orc_reduce.restype = ctypes.c_int64
             L.orc_dump.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
             L.orc_omp_threads.restype = ctypes.c_int
+            L.orc_set_threads.argtypes = [ctypes.c_int]
+            L.orc_set_threads.restype = None
             cls._lib = L
         return cls._lib
 
@@ -108,6 +110,10 @@ class Oracle:
     @staticmethod
     def threads():
         return Oracle.lib().orc_omp_threads()
+
+    @staticmethod
+    def set_threads(n):
+        Oracle.lib().orc_set_threads(int(n))
 
     def dense_table(self):
         p = self.lib().orc_dense_table(self._h)
@@ -166,8 +172,19 @@ class RefOracle:
                 getattr(L, f).restype = ctypes.c_int
             L.ref_dense_table.argtypes = [ctypes.c_void_p]
             L.ref_dense_table.restype = ctypes.POINTER(ctypes.c_int)
+            L.ref_set_threads.argtypes = [ctypes.c_int]
+            L.ref_set_threads.restype = None
+            L.ref_get_threads.restype = ctypes.c_int
             cls._lib = L
         return cls._lib
+
+    @staticmethod
+    def threads():
+        return RefOracle.lib().ref_get_threads()
+
+    @staticmethod
+    def set_threads(n):
+        RefOracle.lib().ref_set_threads(int(n))
 
     def __init__(self, pattern_file):
         L = self.lib()

@@ -361,6 +361,16 @@ int orc_dump(const orc_machine_t *m, const char *path)
     return 0;
 }
 
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_omp_threads(void)
 {
 #ifdef _OPENMP

@@ -20,6 +20,8 @@
 #include <string.h>
 #include <vector>
 
+#include <omp.h>
+
 #include <PFAC.h>
 #include <PFAC_P.h>
 
@@ -100,6 +102,10 @@ int ref_dump(void *p, const char *path)
     fclose(fp);
     return st;
 }
+
+/* torchrun exports OMP_NUM_THREADS=1; the bench sets the count it reports explicitly */
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ref_get_threads(void) { return omp_get_max_threads(); }
 
 int ref_num_patterns(void *p) { return ((PFAC_handle_t)p)->numOfPatterns; }
 int ref_num_states(void *p) { return ((PFAC_handle_t)p)->numOfStates; }

@@ -1,0 +1,50 @@
+"""Host-side shard arithmetic for the multi-GPU path.
+
+Every start position is independent (reference PFAC_CPU.cpp:76), so an N-byte stream is cut
+into contiguous shards; rank g owns start positions [s_g, e_g) and additionally holds the
+next H = maxPatternLen-1 bytes (tail halo; real bytes, or fewer when the stream ends).  The
+only exchange is the per-rank match count: an all-gather of one int64 per rank followed by a
+local exclusive scan gives each rank's offset into the global (ID, position) list.
+This is what the reference's test/omp_PFAC.cpp:316-383 does by hand with host threads
+(there with maxPatternLen+1 bytes of overlap and no reduced output).
+"""
+from typing import List, Tuple
+
+
+def shard_bounds(total_len: int, world: int, rank: int, max_pattern_len: int,
+                 align: int = 4096) -> Tuple[int, int, int]:
+    """(start, n_owned, n_total) for `rank`: shard starts are multiples of `align` (keeps the
+    device pointers 16-byte aligned for the TMA path), n_total = owned + tail halo."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    per = -(-total_len // world)               # ceil
+    per = -(-per // align) * align if per else 0
+    start = min(rank * per, total_len)
+    end = min(start + per, total_len)
+    halo = max(max_pattern_len - 1, 0)
+    n_total = min(end + halo, total_len) - start
+    return start, end - start, n_total
+
+
+def exclusive_offsets(counts: List[int]) -> Tuple[List[int], int]:
+    """Exclusive scan of per-rank match counts -> (offsets, total)."""
+    offs, run = [], 0
+    for c in counts:
+        offs.append(run)
+        run += int(c)
+    return offs, run
+
+
+def allgather_count_offsets(count: int, device=None, group=None) -> Tuple[int, int, List[int]]:
+    """The cross-GPU step: all-gather of one int64 per rank (NCCL over NVLink on GPUs, gloo in
+    the CPU tests) + local exclusive scan.  Returns (my_offset, total, all_counts)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = torch.tensor([int(count)], dtype=torch.int64, device=device)
+    allc = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    counts = [int(x) for x in allc.cpu().tolist()]
+    offs, total = exclusive_offsets(counts)
+    return offs[rank], total, counts

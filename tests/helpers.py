@@ -1,0 +1,57 @@
+"""Shared test helpers (CPU side)."""
+import numpy as np
+
+
+def read_patterns(path):
+    """Patterns of a reference-grammar file, in ID order (ID = index + 1)."""
+    data = open(path, "rb").read()
+    parts = data.split(b"\n")
+    return [p for p in parts[:-1] if p]  # the unterminated tail is dropped by the parser
+
+
+def emulate_layout_walk(layout, num_final, text, start, n_total=None):
+    """Python restatement of the lookup sequence the CUDA kernels run on the compiled device
+    layout (pfac_b200/csrc/pfac_kernels.cu): prefilter bit -> root row -> bucketed hash rows,
+    hot for depth < hot_depth else cold.  Test-only; checks the table compiler without a GPU."""
+    root, pre2, hot, cold, hot_depth, mul = layout
+    n_total = len(text) if n_total is None else n_total
+    avail = n_total - start
+    if avail <= 0:
+        return 0
+    c0 = int(text[start])
+    c1 = int(text[start + 1]) if avail >= 2 else 0
+    idx = c0 | (c1 << 8)
+    if not (int(pre2[idx >> 5]) >> (idx & 31)) & 1:
+        return 0
+    s = int(root[c0])
+    assert s >= 0, "prefilter bit set but root row traps"
+    best = s if s <= num_final else 0
+    d = 1
+    while d < avail:
+        key = ((s << 8) | int(text[start + d])) & 0xFFFFFFFF
+        tab = hot if d < hot_depth else cold
+        nx = probe(tab, mul, key)
+        if nx < 0:
+            break
+        s = nx
+        if s <= num_final:
+            best = s
+        d += 1
+    return best
+
+
+def probe(tab, mul, key):
+    nb = tab.shape[0]
+    if nb == 0:
+        return -1
+    b = (((key * mul) & 0xFFFFFFFF) * nb) >> 32
+    for _ in range(nb + 1):
+        k0, v0, k1, v1 = (int(x) for x in tab[b])
+        if k0 == key:
+            return v0
+        if k1 == key:
+            return v1
+        if k1 == 0xFFFFFFFF:
+            return -1
+        b = 0 if b + 1 == nb else b + 1
+    raise AssertionError("probe did not terminate: table has no empty slot")

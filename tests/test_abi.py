@@ -1,0 +1,86 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares; status strings and
+argument checks that need no GPU behave like the reference (PFAC.cpp).  CPU only: no compute."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from pfac_b200 import PFAC, PFACError, Status, load_library, library_path
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(PFAC_[A-Za-z0-9]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = load_library()
+    names = _declared("PFAC.h") + _declared("PFAC_ext.h")
+    assert len(_declared("PFAC.h")) == 12  # the reference's 12 entry points (PFAC.h:87-215)
+    for n in names:
+        assert hasattr(L, n), "libpfac.so does not export " + n
+    out = subprocess.run(["nm", "-D", "--defined-only", library_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (PFAC_\w+)", out))
+    assert set(names) <= exported
+    # no CPU matcher and nothing from oracle/ in the product library
+    assert not any(s.startswith(("orc_", "ref_")) for s in re.findall(r" T (\w+)", out))
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", library_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_enum_values_match_reference_abi():
+    assert Status.SUCCESS == 0 and Status.BASE == 10000
+    assert [int(s) for s in (Status.ALLOC_FAILED, Status.CUDA_ALLOC_FAILED, Status.INVALID_HANDLE,
+                             Status.INVALID_PARAMETER, Status.PATTERNS_NOT_READY, Status.FILE_OPEN_ERROR,
+                             Status.LIB_NOT_EXIST, Status.ARCH_MISMATCH, Status.MUTEX_ERROR,
+                             Status.INTERNAL_ERROR)] == list(range(10001, 10011))
+    hdr = open(os.path.join(ROOT, "include", "PFAC.h")).read()
+    for frag in ["PFAC_PLATFORM_GPU = 0", "PFAC_PLATFORM_CPU = 1", "PFAC_PLATFORM_CPU_OMP = 2",
+                 "PFAC_AUTOMATIC = 0", "PFAC_TEXTURE_ON = 1", "PFAC_TEXTURE_OFF = 2",
+                 "PFAC_TIME_DRIVEN = 0", "PFAC_SPACE_DRIVEN = 1", "PFAC_STATUS_BASE = 10000"]:
+        assert frag in hdr
+
+
+def test_error_strings():
+    L = load_library()
+    assert L.PFAC_getErrorString(0) == b"PFAC_STATUS_SUCCESS: operation is successful"
+    assert L.PFAC_getErrorString(10003) == b"PFAC_STATUS_INVALID_HANDLE: handle is invalid (NULL)"
+    assert L.PFAC_getErrorString(10005).startswith(b"PFAC_STATUS_PATTERNS_NOT_READY")
+    assert L.PFAC_getErrorString(10010) == b"PFAC_STATUS_INTERNAL_ERROR: please report bugs"
+    assert L.PFAC_getErrorString(2) == b"out of memory"  # < BASE: forwarded to cudaGetErrorString
+
+
+def test_null_handle_is_invalid_handle_first():
+    """Reference order: NULL handle -> INVALID_HANDLE before anything else (PFAC.cpp:846,882,967)."""
+    L = load_library()
+    n = ctypes.c_int(0)
+    assert L.PFAC_destroy(None) == Status.INVALID_HANDLE
+    assert L.PFAC_setPlatform(None, 0) == Status.INVALID_HANDLE
+    assert L.PFAC_setTextureMode(None, 0) == Status.INVALID_HANDLE
+    assert L.PFAC_setPerfMode(None, 0) == Status.INVALID_HANDLE
+    assert L.PFAC_readPatternFromFile(None, b"x") == Status.INVALID_HANDLE
+    assert L.PFAC_matchFromDevice(None, None, 0, None) == Status.INVALID_HANDLE
+    assert L.PFAC_matchFromHost(None, None, 0, None) == Status.INVALID_HANDLE
+    assert L.PFAC_matchFromDeviceReduce(None, None, 0, None, None, ctypes.byref(n)) == Status.INVALID_HANDLE
+    assert L.PFAC_matchFromHostReduce(None, None, 0, None, None, ctypes.byref(n)) == Status.INVALID_HANDLE
+    assert L.PFAC_dumpTransitionTable(None, None) == Status.INVALID_HANDLE
+
+
+def test_create_fails_loudly_without_gpu():
+    """No CPU fallback: without a device PFAC_create returns the raw CUDA error (reference
+    PFAC.cpp:148-151 does the same)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(PFACError) as e:
+        PFAC()
+    assert 0 < e.value.status < Status.BASE

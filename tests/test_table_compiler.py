@@ -1,0 +1,132 @@
+"""Host logic of the product library, no GPU: the C++ table compiler (pfac_b200/csrc/
+pfac_table.cpp) reached through the C ABI (PFAC_tableCompile*, include/PFAC_ext.h).
+
+  * dump is byte-identical to the reference's PFAC_dumpTransitionTable (goldens),
+  * state numbering / counts equal the oracle's,
+  * the emitted device layout (root row, prefilter bitmap, hot/cold hash rows), walked by a
+    Python restatement of the kernels' lookup sequence, reproduces the oracle's dense result.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import Oracle
+from pfac_b200 import PFACError, Status, TableCompiler, synth
+from tests.helpers import emulate_layout_walk, read_patterns
+
+
+def _layout(tc):
+    root, pre2, hot, cold = tc.layout()
+    info = tc.info()
+    return (root, pre2, hot, cold, info["hot_depth"], info["hash_mul"])
+
+
+@pytest.mark.parametrize("fixture", ["example_pattern", "example_pattern2"])
+def test_dump_matches_reference_golden(golden_dir, tmp_path, fixture):
+    tc = TableCompiler(os.path.join(golden_dir, fixture))
+    out = tmp_path / "t.txt"
+    tc.dump(str(out))
+    assert out.read_bytes() == open(os.path.join(golden_dir, fixture + ".dump"), "rb").read()
+
+
+@pytest.mark.parametrize("case", ["c2", "snort", "dna"])
+def test_dump_digest_matches_reference(golden_dir, tmp_path, case):
+    g = np.load(os.path.join(golden_dir, "synth_%s.npz" % case))
+    tc = TableCompiler(os.path.join(golden_dir, "synth_%s.pat" % case))
+    out = tmp_path / "t.txt"
+    tc.dump(str(out))
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == str(g["dump_sha256"])
+    info = tc.info()
+    assert info["num_states"] == int(g["num_states"])
+    assert info["max_pattern_len"] == int(g["max_pattern_len"])
+
+
+def test_info_readme_example(golden_dir):
+    info = TableCompiler(os.path.join(golden_dir, "example_pattern")).info()
+    assert (info["num_patterns"], info["num_states"], info["initial_state"], info["max_pattern_len"]) == (4, 11, 5, 4)
+    assert info["num_leaves"] == 3 and info["num_edges"] == 9 and info["root_fanout"] == 3
+    assert info["pre2_bits_set"] == 3  # AB, BE, ED
+
+
+@pytest.mark.parametrize("hot_kb", [0, 1, 24, 512])
+@pytest.mark.parametrize("case", ["c2", "snort", "dna"])
+def test_layout_walk_equals_oracle(golden_dir, case, hot_kb):
+    """Every hot/cold split must give the oracle's result (PFAC_SPACE_DRIVEN == hot budget 0)."""
+    g = np.load(os.path.join(golden_dir, "synth_%s.npz" % case))
+    pfile = os.path.join(golden_dir, "synth_%s.pat" % case)
+    pats = read_patterns(pfile)
+    n = 6000
+    text = synth.make_text(str(g["kind"]), int(g["seed"]), 0, n, n, pats, 128)
+    o = Oracle(pfile)
+    want = o.match(text)
+    assert (want > 0).sum() > 10
+    tc = TableCompiler(pfile, hot_budget_bytes=hot_kb * 1024)
+    info = tc.info()
+    L = _layout(tc)
+    assert L[2].shape[0] * 16 <= max(hot_kb * 1024, 0)
+    if hot_kb == 0:
+        assert info["hot_depth"] == 1 and info["hot_buckets"] == 0
+    if hot_kb == 512:
+        assert info["hot_depth"] == info["max_depth"] + 1  # everything fits: all rows hot
+    got = np.array([emulate_layout_walk(L, o.num_patterns, text, i) for i in range(n)], dtype=np.int32)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "first mismatch at %d: got %d want %d" % (bad[0], got[bad[0]], want[bad[0]])
+
+
+def test_layout_root_and_prefilter_against_dense_table(golden_dir):
+    pfile = os.path.join(golden_dir, "synth_snort.pat")
+    o = Oracle(pfile)
+    T = o.dense_table()
+    tc = TableCompiler(pfile)
+    root, pre2, hot, cold = tc.layout()
+    init, k = o.initial_state, o.num_patterns
+    assert np.array_equal(root, T[init])
+    bits = np.unpackbits(pre2.view(np.uint8), bitorder="little").reshape(256, 256)  # [c1][c0]
+    for c0 in range(256):
+        s = T[init, c0]
+        for c1 in range(256):
+            expect = s >= 0 and (s <= k or T[s, c1] >= 0)
+            assert bool(bits[c1, c0]) == bool(expect), (c0, c1)
+    # every transition of every reachable non-root state is in exactly one hash table
+    info = tc.info()
+    keys = np.concatenate([hot[:, 0], hot[:, 2], cold[:, 0], cold[:, 2]])
+    keys = keys[keys != 0xFFFFFFFF]
+    assert keys.size == np.unique(keys).size == info["num_edges"] - info["root_fanout"]
+
+
+def test_duplicates_prefixes_and_one_byte_patterns():
+    """Last edge wins in the matching table (reference PFAC.cpp:376-381); a 1-byte pattern makes
+    its byte always a candidate; a final state can have out-edges."""
+    image = b"AB\nA\nABC\nB\n"
+    o = Oracle(image=image)
+    tc = TableCompiler(image=image)
+    L = _layout(tc)
+    text = np.frombuffer(b"ABCABXBA", dtype=np.uint8)
+    got = [emulate_layout_walk(L, o.num_patterns, text, i) for i in range(text.size)]
+    assert got == o.match(text).tolist() == [3, 4, 0, 1, 4, 0, 4, 2]
+
+
+def test_parser_errors_and_quirks(tmp_path):
+    with pytest.raises(PFACError) as e:
+        TableCompiler(image=b"AB\n\nCD\n")
+    assert e.value.status == Status.INVALID_PARAMETER
+    with pytest.raises(PFACError) as e:
+        TableCompiler(pattern_file=str(tmp_path / "does_not_exist"))
+    assert e.value.status == Status.FILE_OPEN_ERROR
+    assert TableCompiler(image=b"AB\nCD").info()["num_patterns"] == 1     # unterminated tail dropped
+    assert TableCompiler(image=b"AB\n\n\n").info()["num_patterns"] == 1   # trailing blank lines ok
+    info = TableCompiler(image=b"").info()
+    assert info["num_patterns"] == 0 and info["pre2_bits_set"] == 0
+
+
+def test_state_numbering_matches_oracle_on_binary_patterns(tmp_path):
+    pats = synth.patterns_c2(500, seed=77, min_len=1, max_len=12, prefix_pairs=100)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    o = Oracle(pfile)
+    tc = TableCompiler(pfile)
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    o.dump(str(a))
+    tc.dump(str(b))
+    assert a.read_bytes() == b.read_bytes()
