@@ -57,7 +57,7 @@ PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char
 
 /* ---- table compiler, host only (no CUDA calls): pattern image -> reference-numbered trie
  * -> B200 device layout (dense root row, 2-byte prefilter bitmap, hot/cold bucketed hash
- * rows). */
+ * rows, path-compressed chains). */
 typedef struct PFAC_table *PFAC_table_t;
 
 typedef struct {
@@ -66,7 +66,11 @@ typedef struct {
     int initial_state;     /* k+1 */
     int max_pattern_len;
     int num_leaves;        /* final states without out-edges */
-    int num_edges;         /* distinct (state,ch) transitions used for matching */
+    int num_edges;         /* distinct (state,ch) transitions of the matching automaton */
+    int hash_edges;        /* hash-row entries left after chain compression */
+    int num_chains;        /* compressed single-child runs (tail compared byte-wise) */
+    int tail_bytes;        /* bytes of chain tails (padded) */
+    int chains_hot;        /* 1: chain records and tails also live in shared memory */
     int max_depth;
     int hot_depth;         /* edges whose source state has depth in [1,hot_depth) are "hot" */
     unsigned hot_buckets;  /* 16-byte buckets (2 slots) of the shared-memory hash rows */
@@ -87,9 +91,12 @@ PFAC_status_t PFAC_tableDump(PFAC_table_t table, FILE *fp);
 PFAC_status_t PFAC_tableDumpToFile(PFAC_table_t table, const char *filename);
 PFAC_status_t PFAC_tableGetInfo(PFAC_table_t table, PFAC_tableInfo_t *info);
 /* read-only views of the layout arrays (valid until PFAC_tableDestroy):
- * root: 256 int; pre2: 2048 unsigned; hot/cold: 4 unsigned per bucket {key0,val0,key1,val1} */
+ * root: 256 int; pre2: 2048 unsigned; hot/cold: 4 unsigned per bucket {key0,val0,key1,val1}
+ * (val bit 31 set = chain index); chains: 4 unsigned per record {tail offset, len,
+ * end state | leaf bit 31, first 4 tail bytes}; tails: tail_bytes bytes */
 PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int **root, const unsigned **pre2,
-                                  const unsigned **hot, const unsigned **cold);
+                                  const unsigned **hot, const unsigned **cold,
+                                  const unsigned **chains, const unsigned char **tails);
 
 /* info / dump-to-path for a live handle */
 PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);

@@ -54,6 +54,8 @@ class TableInfo(ctypes.Structure):
     _fields_ = [("num_patterns", ctypes.c_int), ("num_states", ctypes.c_int),
                 ("initial_state", ctypes.c_int), ("max_pattern_len", ctypes.c_int),
                 ("num_leaves", ctypes.c_int), ("num_edges", ctypes.c_int),
+                ("hash_edges", ctypes.c_int), ("num_chains", ctypes.c_int),
+                ("tail_bytes", ctypes.c_int), ("chains_hot", ctypes.c_int),
                 ("max_depth", ctypes.c_int), ("hot_depth", ctypes.c_int),
                 ("hot_buckets", ctypes.c_uint), ("cold_buckets", ctypes.c_uint),
                 ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
@@ -118,7 +120,7 @@ def load_library():
         "PFAC_tableDumpToFile": [vp, cp],
         "PFAC_tableGetInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_tableGetLayout": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
-                                ctypes.POINTER(vp)],
+                                ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
     }
     for name, args in sig.items():
@@ -319,19 +321,24 @@ class TableCompiler:
         _check(self._L.PFAC_tableDumpToFile(self._t, os.fsencode(filename)), "PFAC_tableDumpToFile")
 
     def layout(self):
-        """Copies of the device layout arrays: root[256] i32, pre2[2048] u32, hot/cold [n,4] u32."""
-        ptrs = [ctypes.c_void_p() for _ in range(4)]
+        """Copies of the device layout arrays as a dict: root[256] i32, pre2[2048] u32, hot/cold
+        [n,4] u32 buckets, chains [n,4] u32 records, tails u8, plus hot_depth and mul."""
+        ptrs = [ctypes.c_void_p() for _ in range(6)]
         _check(self._L.PFAC_tableGetLayout(self._t, *[ctypes.byref(p) for p in ptrs]),
                "PFAC_tableGetLayout")
         info = self.info()
 
-        def arr(p, n, dt):
-            if n == 0 or not p.value:
+        def arr(p, nbytes, dt):
+            if nbytes == 0 or not p.value:
                 return np.zeros(0, dtype=dt)
-            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)),
-                                         shape=(n,)).view(dt).copy()
-        root = arr(ptrs[0], 256, np.int32)
-        pre2 = arr(ptrs[1], 2048, np.uint32)
-        hot = arr(ptrs[2], info["hot_buckets"] * 4, np.uint32).reshape(-1, 4)
-        cold = arr(ptrs[3], info["cold_buckets"] * 4, np.uint32).reshape(-1, 4)
-        return root, pre2, hot, cold
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)),
+                                         shape=(nbytes,)).copy().view(dt)
+        return {
+            "root": arr(ptrs[0], 1024, np.int32),
+            "pre2": arr(ptrs[1], 8192, np.uint32),
+            "hot": arr(ptrs[2], info["hot_buckets"] * 16, np.uint32).reshape(-1, 4),
+            "cold": arr(ptrs[3], info["cold_buckets"] * 16, np.uint32).reshape(-1, 4),
+            "chains": arr(ptrs[4], max(info["num_chains"], 1) * 16, np.uint32).reshape(-1, 4),
+            "tails": arr(ptrs[5], info["tail_bytes"], np.uint8),
+            "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
+        }

@@ -20,15 +20,14 @@
 namespace {
 
 constexpr size_t kFilenameLen = 256;            // reference PFAC_P.h FILENAME_LEN
-constexpr size_t kDefaultHotBytes = 24 * 1024;  // shared-memory budget for hot hash rows
 constexpr size_t kInt32Limit = size_t(1) << 31;
 
 size_t envBytes(const char* name, size_t dflt, size_t unit) {
     const char* v = getenv(name);
-    if (!v || !*v) return dflt;
+    if (!v || !*v) return dflt * unit;
     char* end = nullptr;
     unsigned long long x = strtoull(v, &end, 10);
-    if (end == v) return dflt;
+    if (end == v) return dflt * unit;
     return size_t(x) * unit;
 }
 
@@ -62,6 +61,8 @@ struct PFAC_context {
     void* d_pre2 = nullptr;
     void* d_hot = nullptr;
     void* d_cold = nullptr;
+    void* d_chains = nullptr;
+    void* d_tails = nullptr;
 
     std::mutex pipeMu;  // held for a whole matchFromHost* call (host pipeline buffers)
     std::mutex mu;      // guards the reduce workspace (several host threads may share a handle)
@@ -79,6 +80,8 @@ void freeDeviceTable(PFAC_handle_t h) {
     cudaFree(h->d_pre2); h->d_pre2 = nullptr;
     cudaFree(h->d_hot); h->d_hot = nullptr;
     cudaFree(h->d_cold); h->d_cold = nullptr;
+    cudaFree(h->d_chains); h->d_chains = nullptr;
+    cudaFree(h->d_tails); h->d_tails = nullptr;
     h->table = pfac::DeviceTable();
 }
 
@@ -108,9 +111,13 @@ PFAC_status_t uploadArray(void** dst, const void* src, size_t bytes) {
     return PFAC_STATUS_SUCCESS;
 }
 
+// shared-memory bytes the table compiler may fill: whatever the dense kernel's per-warp
+// pipelines leave free (PFAC_B200_HOT_KB caps it; PFAC_SPACE_DRIVEN = nothing in smem)
 size_t hotBudget(PFAC_handle_t h) {
     if (h->perfMode == PFAC_SPACE_DRIVEN) return 0;
-    return envBytes("PFAC_B200_HOT_KB", kDefaultHotBytes / 1024, 1024);
+    const size_t avail = pfac::tableSmemBudget(h->machine.maxPatternLen);
+    const size_t cap = envBytes("PFAC_B200_HOT_KB", avail / 1024 + 1, 1024);
+    return cap < avail ? cap : avail;
 }
 
 // compile the device layout for the current perf mode and upload it (reference PFAC_bindTable,
@@ -124,11 +131,18 @@ PFAC_status_t bindTable(PFAC_handle_t h) {
     if ((st = uploadArray(&h->d_pre2, L.pre2.data(), L.pre2.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
     if ((st = uploadArray(&h->d_hot, L.hot.data(), L.hot.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
     if ((st = uploadArray(&h->d_cold, L.cold.data(), L.cold.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+    if ((st = uploadArray(&h->d_chains, L.chains.data(), L.chains.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+    if ((st = uploadArray(&h->d_tails, L.tails.data(), L.tails.size())) != PFAC_STATUS_SUCCESS) return st;
     pfac::DeviceTable& t = h->table;
     t.root = static_cast<const int32_t*>(h->d_root);
     t.pre2 = static_cast<const uint32_t*>(h->d_pre2);
     t.hot = static_cast<const uint4*>(h->d_hot);
     t.cold = static_cast<const uint4*>(h->d_cold);
+    t.chains = static_cast<const uint4*>(h->d_chains);
+    t.tails = static_cast<const unsigned char*>(h->d_tails);
+    t.chainBytes = uint32_t(L.chains.size() * 4);
+    t.tailBytes = uint32_t(L.tails.size());
+    t.chainsHot = L.chainsHot;
     t.hotBuckets = L.hotBuckets;
     t.coldBuckets = L.coldBuckets;
     t.mul = L.mul;
@@ -543,7 +557,11 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->initial_state = m.initialState;
     info->max_pattern_len = m.maxPatternLen;
     info->num_leaves = m.numLeaves;
-    info->num_edges = L.numEdges + L.rootFanout;
+    info->num_edges = L.numEdges;
+    info->hash_edges = L.hashEdges;
+    info->num_chains = L.numChains;
+    info->tail_bytes = int(L.tails.size());
+    info->chains_hot = L.chainsHot ? 1 : 0;
     info->max_depth = L.maxDepth;
     info->hot_depth = L.hotDepth;
     info->hot_buckets = L.hotBuckets;
@@ -606,12 +624,15 @@ PFAC_status_t PFAC_tableGetInfo(PFAC_table_t table, PFAC_tableInfo_t* info) {
 }
 
 PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int** root, const unsigned** pre2,
-                                  const unsigned** hot, const unsigned** cold) {
+                                  const unsigned** hot, const unsigned** cold, const unsigned** chains,
+                                  const unsigned char** tails) {
     if (!table) return PFAC_STATUS_INVALID_HANDLE;
     if (root) *root = table->layout.root;
     if (pre2) *pre2 = table->layout.pre2.data();
     if (hot) *hot = table->layout.hot.data();
     if (cold) *cold = table->layout.cold.data();
+    if (chains) *chains = table->layout.chains.data();
+    if (tails) *tails = table->layout.tails.data();
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -4,15 +4,17 @@
 // (reference PFAC/src/PFAC_CPU.cpp:60-100 is the spec; PFAC_kernel.cu:377-458 and
 // PFAC_reduce_kernel.cu:639-867 are the 2012 GPU forms being replaced).  How it is computed
 // is new -- see DESIGN.md:
-//   * persistent CTAs, one 4096-byte input tile (+ halo) per iteration, staged global->shared
-//     by one 1-D TMA bulk copy (cp.async.bulk + mbarrier), double buffered;
 //   * a 64-Kbit two-byte prefilter in shared memory rejects most start positions with one
 //     LDS; survivors are compacted into a per-warp queue;
-//   * lanes pull survivors from the queue and walk them (refill on early exit), root row and
-//     shallow ("hot") hash rows in shared memory, deep ("cold") rows through L1/L2;
-//   * dense mode: results staged in shared memory, each warp ships its 2 KB with a TMA bulk
-//     store; reduce mode: ordered warp/CTA compaction + decoupled look-back across tiles
-//     writes (id, position) pairs in one pass.
+//   * lanes pull survivors from the queue and walk them (refill on early exit): root row and
+//     shallow ("hot") hash rows in shared memory, deep ("cold") rows through L1/L2, and
+//     path-compressed chains whose tail bytes are compared directly against the text;
+//   * dense kernel: one persistent 32-warp CTA per SM, every warp runs its own pipeline --
+//     512-byte input tiles (+halo) arrive by 1-D TMA bulk copies on per-warp mbarriers, the
+//     warp's 2 KB of results leave by a TMA bulk store; no CTA-wide barrier in the loop, so
+//     one long walk delays one warp, not a block;
+//   * reduce kernel: ordered warp/CTA compaction + decoupled look-back across tiles writes
+//     (id, position) pairs in one pass.
 #include "pfac_kernels.h"
 
 #include <atomic>
@@ -21,39 +23,33 @@ namespace pfac {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kPosPerThread = 16;
-constexpr int kWarpTile = 32 * kPosPerThread;    // 512 positions per warp per iteration
-constexpr int kTile = kThreads * kPosPerThread;  // 4096 positions per CTA per iteration
-constexpr int kMaxHalo = 1024;                   // staged halo cap; longer walks read global
-constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kWarpTile = 32 * kPosPerThread;  // 512 start positions per warp per iteration
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;       // empty hash slot / trap
+constexpr uint32_t kChainBit = 0x80000000u;
+constexpr int kMaxSmem = 232448;               // 227 KB opt-in dynamic shared memory per CTA
 
-constexpr int kModeDense = 0;
-constexpr int kModeReduce = 1;
+// ---- dense kernel geometry -------------------------------------------------------------------
+constexpr int kDenseWarps = 32;
+constexpr int kDenseThreads = kDenseWarps * 32;
+constexpr int kDenseMaxHalo = 512;             // staged halo cap; longer walks read global
+
+// ---- reduce kernel geometry ------------------------------------------------------------------
+constexpr int kRedThreads = 256;
+constexpr int kRedWarps = kRedThreads / 32;
+constexpr int kRedTile = kRedThreads * kPosPerThread;  // 4096
+constexpr int kRedMaxHalo = 1024;
 
 // look-back descriptor: [63:62] status, [61:0] value
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kStatusIncl = 2ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
-// shared memory map (bytes)
-constexpr int kOffBar = 0;                         // 2 x uint64 mbarrier
-constexpr int kOffBase = 16;                       // uint64 tile base (reduce)
-constexpr int kOffWcount = 32;                     // int[8]
-constexpr int kOffTicket = 96;                     // long long[2]
-constexpr int kOffWoff = 64;                       // int[8]
-constexpr int kOffRoot = 128;                      // int[256]
-constexpr int kOffPre2 = kOffRoot + 1024;          // uint32[2048]
-constexpr int kOffQueue = kOffPre2 + 8192;         // uint16[kWarps][512]
-constexpr int kOffRes = kOffQueue + kWarps * kWarpTile * 2;  // int[kTile]: dense results / reduce ids
-constexpr int kOffIn = kOffRes + kTile * 4;        // 2 x stage bytes, then hot buckets
-
 struct KParams {
     const unsigned char* in;
     long long n_owned;
     long long n_total;
-    long long num_tiles;
+    long long num_tiles;        // dense: 512-position warp tiles; reduce: 4096-position CTA tiles
     int* out;                   // dense
     int* out_id;                // reduce
     void* out_pos;              // reduce
@@ -65,14 +61,31 @@ struct KParams {
     const uint32_t* pre2;
     const uint4* hot;
     const uint4* cold;
+    const uint4* chains;
+    const unsigned char* tails;
     uint32_t hot_buckets;
     uint32_t cold_buckets;
+    uint32_t chain_bytes;       // bytes of chain records (copied to smem when chains_hot)
+    uint32_t tail_bytes;
     uint32_t mul;
     int hot_depth;
+    int chains_hot;
     int num_final;
-    int halo;                   // multiple of 16, >= 16
+    int halo;                   // staged halo, multiple of 16, >= 16
     int in_aligned;             // in is 16-byte aligned
     int out_aligned;            // out is 16-byte aligned
+};
+
+// tables as the walker sees them (shared-memory copies where available)
+struct Tables {
+    const int* root;            // smem
+    const uint32_t* pre2;       // smem
+    const uint4* hot;           // smem
+    const uint4* cold;          // global
+    const uint4* chains;        // smem or global
+    const unsigned char* tails; // smem or global
+    uint32_t hot_buckets, cold_buckets, mul;
+    int hot_depth, num_final;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -130,56 +143,331 @@ __device__ __forceinline__ uint32_t home_bucket(uint32_t key, uint32_t mul, uint
     return __umulhi(key * mul, nb);
 }
 
-// hot rows: shared memory
-__device__ __forceinline__ int probe_hot(const uint4* tab, uint32_t nb, uint32_t mul, uint32_t key) {
+// hot rows: shared memory.  Returns next state, kChainBit|index, or kEmpty (trap).
+__device__ __forceinline__ uint32_t probe_hot(const uint4* tab, uint32_t nb, uint32_t mul, uint32_t key) {
     uint32_t b = home_bucket(key, mul, nb);
     for (;;) {
         const uint4 e = tab[b];
-        if (e.x == key) return static_cast<int>(e.y);
-        if (e.z == key) return static_cast<int>(e.w);
-        if (e.z == kEmpty) return -1;
+        if (e.x == key) return e.y;
+        if (e.z == key) return e.w;
+        if (e.z == kEmpty) return kEmpty;
         b = (b + 1 == nb) ? 0 : b + 1;
     }
 }
 // cold rows: global memory through the read-only path (L1/L2 resident)
-__device__ __forceinline__ int probe_cold(const uint4* __restrict__ tab, uint32_t nb, uint32_t mul, uint32_t key) {
+__device__ __forceinline__ uint32_t probe_cold(const uint4* __restrict__ tab, uint32_t nb, uint32_t mul,
+                                               uint32_t key) {
     uint32_t b = home_bucket(key, mul, nb);
     for (;;) {
         const uint4 e = __ldg(tab + b);
-        if (e.x == key) return static_cast<int>(e.y);
-        if (e.z == key) return static_cast<int>(e.w);
-        if (e.z == kEmpty) return -1;
+        if (e.x == key) return e.y;
+        if (e.z == key) return e.w;
+        if (e.z == kEmpty) return kEmpty;
         b = (b + 1 == nb) ? 0 : b + 1;
     }
 }
 
-template <int MODE, bool POS64>
-__global__ void __launch_bounds__(kThreads) pfac_match_kernel(const KParams p) {
+// copy the compiled tables into shared memory (whole CTA), returns the walker's view
+__device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* s_root, unsigned char* s_pre2,
+                                               unsigned char* s_var, int tid, int nthreads) {
+    int* root = reinterpret_cast<int*>(s_root);
+    uint4* pre2 = reinterpret_cast<uint4*>(s_pre2);
+    uint4* hot = reinterpret_cast<uint4*>(s_var);
+    for (int i = tid; i < 256; i += nthreads) root[i] = p.root[i];
+    for (int i = tid; i < 2048 / 4; i += nthreads) pre2[i] = reinterpret_cast<const uint4*>(p.pre2)[i];
+    for (uint32_t i = tid; i < p.hot_buckets; i += nthreads) hot[i] = p.hot[i];
+    Tables t;
+    t.root = root;
+    t.pre2 = reinterpret_cast<const uint32_t*>(s_pre2);
+    t.hot = hot;
+    t.cold = p.cold;
+    t.chains = p.chains;
+    t.tails = p.tails;
+    if (p.chains_hot) {
+        uint4* sc = hot + p.hot_buckets;
+        uint4* st = sc + p.chain_bytes / 16;
+        for (uint32_t i = tid; i < p.chain_bytes / 16; i += nthreads) sc[i] = p.chains[i];
+        for (uint32_t i = tid; i < p.tail_bytes / 16; i += nthreads)
+            st[i] = reinterpret_cast<const uint4*>(p.tails)[i];
+        t.chains = sc;
+        t.tails = reinterpret_cast<const unsigned char*>(st);
+    }
+    t.hot_buckets = p.hot_buckets;
+    t.cold_buckets = p.cold_buckets;
+    t.mul = p.mul;
+    t.hot_depth = p.hot_depth;
+    t.num_final = p.num_final;
+    return t;
+}
+
+// 16 consecutive start positions at inb[lb..]: one LDS.128 + one LDS.32 of text, one prefilter
+// LDS per position.  Bit q of the result = position lb+q survives.
+__device__ __forceinline__ uint32_t prefilter16(const unsigned char* inb, int lb, const uint32_t* s_pre2) {
+    uint32_t w[5];
+    const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    w[4] = *reinterpret_cast<const uint32_t*>(inb + lb + 16);
+    uint32_t cand = 0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+#pragma unroll
+        for (int j = 3; j >= 0; j--) {
+            const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
+            const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
+            // wanted bit (x & 31) -> bit 31, then shift it into cand from the right
+            const uint32_t t = word << ((~x) & 31u);
+            cand = __funnelshift_l(t, cand, 1);
+        }
+    }
+    return cand;
+}
+
+// exclusive offset of this lane's survivors in the warp queue + warp total; pushes positions
+__device__ __forceinline__ int push_survivors(uint32_t cand, int lb, unsigned short* q16, int lane) {
+    const int cnt = __popc(cand);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+    int off = incl - cnt;
+    while (cand) {
+        const int b = __ffs(cand) - 1;
+        cand &= cand - 1;
+        q16[off++] = static_cast<unsigned short>(lb + b);
+    }
+    return wtotal;
+}
+
+// Walk the queued survivors of one warp.  inb: staged text of the tile (stage_bytes bytes,
+// local position 0 = first byte), gin: the same bytes in global memory (for walks that run past
+// the staged halo), tile_rem: real input bytes from local position 0 to the end of the input.
+// DENSE: wres[local position - res_base] = id (non-zero only); else wres[queue slot] = id.
+template <bool DENSE>
+__device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
+                                           const unsigned char* __restrict__ gin, int tile_rem,
+                                           const unsigned short* q16, int wtotal, int* wres, int res_base,
+                                           int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int head = 0;
+    bool active = false;
+    int pl = 0, d = 0, limit = 0, best = 0, slot = 0;
+    uint32_t s = 0;
+    auto text_byte = [&](int at) -> uint32_t { return (at < stage_bytes) ? inb[at] : gin[at]; };
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (need) {
+            const int my = head + __popc(need & lt_mask);
+            if (!active && my < wtotal) {
+                slot = my;
+                pl = q16[my];
+                s = static_cast<uint32_t>(T.root[inb[pl]]);
+                best = (static_cast<int>(s) <= T.num_final) ? static_cast<int>(s) : 0;
+                d = 1;
+                limit = tile_rem - pl;  // bytes of real input from this position
+                active = true;
+            }
+            head += __popc(need);
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            bool done = (d >= limit) || (static_cast<int>(s) < 0);
+            if (!done) {
+                const uint32_t key = (s << 8) | text_byte(pl + d);
+                const uint32_t v = (d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
+                                                     : probe_cold(T.cold, T.cold_buckets, T.mul, key);
+                if (v == kEmpty) {
+                    done = true;
+                } else if (v & kChainBit) {
+                    // compressed run: rec = {tail offset, len, end state | leaf, first 4 bytes}
+                    const uint4 rec = T.chains[v & ~kChainBit];
+                    const int len = static_cast<int>(rec.y);
+                    if (d + 1 + len > limit) {
+                        done = true;  // cut off by the end of the input: nothing more to report
+                    } else {
+                        const int at0 = pl + d + 1;
+                        uint32_t tw = rec.w;
+                        bool ok = true;
+                        for (int i = 0; i < len; i++) {
+                            if (i >= 4 && (i & 3) == 0) tw = *reinterpret_cast<const uint32_t*>(T.tails + rec.x + i);
+                            if (text_byte(at0 + i) != ((tw >> (8 * (i & 3))) & 0xFFu)) { ok = false; break; }
+                        }
+                        if (!ok) {
+                            done = true;
+                        } else {
+                            s = rec.z & ~kChainBit;
+                            d += 1 + len;
+                            if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                            if (rec.z & kChainBit) done = true;  // leaf: no out-edges
+                        }
+                    }
+                } else {
+                    s = v;
+                    if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                    d++;
+                }
+            }
+            if (done) {
+                if (DENSE) {
+                    if (best) wres[pl - res_base] = best;
+                } else {
+                    wres[slot] = best;
+                }
+                active = false;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// Dense kernel: one persistent CTA of 32 autonomous warps per SM.
+// shared memory: [mbarriers 32*NSTAGE*8][root 1K][pre2 8K][per warp: queue 1K | res 2K | NSTAGE
+// input stages][hot buckets][chains][tails]
+// =================================================================================================
+template <int NSTAGE>
+__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
-    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(smem + kOffBase);
-    int* s_wcount = reinterpret_cast<int*>(smem + kOffWcount);
-    int* s_woff = reinterpret_cast<int*>(smem + kOffWoff);
-    long long* s_ticket = reinterpret_cast<long long*>(smem + kOffTicket);
-    int* s_root = reinterpret_cast<int*>(smem + kOffRoot);
-    uint32_t* s_pre2 = reinterpret_cast<uint32_t*>(smem + kOffPre2);
-    unsigned short* s_queue = reinterpret_cast<unsigned short*>(smem + kOffQueue);
-    int* s_res = reinterpret_cast<int*>(smem + kOffRes);
-    const int stage = kTile + p.halo;
-    unsigned char* s_in = smem + kOffIn;
-    const uint4* s_hot = reinterpret_cast<const uint4*>(smem + kOffIn + 2 * stage);
+    const int stage = kWarpTile + p.halo;
+    const int per_warp = kWarpTile * 2 + kWarpTile * 4 + NSTAGE * stage;
+    constexpr int kBarBytes = ((kDenseWarps * NSTAGE * 8 + 127) / 128) * 128;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
+    unsigned char* s_root = smem + kBarBytes;
+    unsigned char* s_pre2 = s_root + 1024;
+    unsigned char* s_warp = s_pre2 + 8192;
+    unsigned char* s_var = s_warp + kDenseWarps * per_warp;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    const Tables T = stage_tables(p, s_root, s_pre2, s_var, tid, kDenseThreads);
+    unsigned long long* bar = s_bar + warp * NSTAGE;
+    if (lane == 0) {
+        for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide barrier
+
+    unsigned char* mine = s_warp + warp * per_warp;
+    unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
+    int* wres = reinterpret_cast<int*>(mine + kWarpTile * 2);
+    unsigned char* s_in = mine + kWarpTile * 2 + kWarpTile * 4;
+
+    // warp tile of iteration `it`: consecutive warps of a CTA take consecutive 512-byte tiles
+    auto tile_of = [&](long long it) -> long long {
+        return (it * gridDim.x + blockIdx.x) * kDenseWarps + warp;
+    };
+    auto tile_is_bulk = [&](long long t) -> bool {
+        return p.in_aligned && (t * kWarpTile + stage <= p.n_total);
+    };
+    auto issue_load = [&](long long t, int st) {  // lane 0 only
+        if (t < p.num_tiles && tile_is_bulk(t)) {
+            mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
+            tma_load_1d(s_in + st * stage, p.in + t * kWarpTile, static_cast<uint32_t>(stage), &bar[st]);
+        }
+    };
+
+    if (lane == 0)
+        for (int i = 0; i < NSTAGE; i++) issue_load(tile_of(i), i);
+
+    uint32_t parity = 0u;  // bit s = phase of bar[s]
+    int st = 0;
+    for (long long it = 0;; ++it) {
+        const long long tile = tile_of(it);
+        if (tile >= p.num_tiles) break;
+        unsigned char* inb = s_in + st * stage;
+        const long long start = tile * kWarpTile;
+        if (tile_is_bulk(tile)) {
+            mbar_wait(&bar[st], (parity >> st) & 1u);
+            parity ^= 1u << st;
+        } else {
+            // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
+            for (int i = lane; i < stage; i += 32) {
+                const long long g = start + i;
+                inb[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
+            }
+            __syncwarp();
+        }
+        const long long owned_left = p.n_owned - start;  // > 0
+        const int valid = owned_left < kWarpTile ? static_cast<int>(owned_left) : kWarpTile;
+        const long long total_left = p.n_total - start;
+        const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
+
+        const int lb = lane * kPosPerThread;
+        uint32_t cand = prefilter16(inb, lb, T.pre2);
+        if (valid < kWarpTile) {  // tail tile: drop positions we do not own
+            int nv = valid - lb;
+            nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
+            cand &= (1u << nv) - 1u;
+        }
+        const int wtotal = push_survivors(cand, lb, q16, lane);
+
+        // the previous bulk store of this warp must have finished reading wres
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(wres)[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+
+        walk_queue<true>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, 0, lane);
+
+        int* gout = p.out + start;
+        if (p.out_aligned && valid == kWarpTile) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_1d(gout, wres, kWarpTile * 4);
+                tma_store_commit();
+                issue_load(tile_of(it + NSTAGE), st);  // every lane is done with this stage
+            }
+        } else {
+            __syncwarp();
+            for (int i = lane; i < valid; i += 32) gout[i] = wres[i];
+            __syncwarp();
+            if (lane == 0) issue_load(tile_of(it + NSTAGE), st);
+        }
+        st = (st + 1 == NSTAGE) ? 0 : st + 1;
+    }
+    if (lane == 0) tma_store_wait_all();  // shared memory must outlive the bulk stores
+}
+
+// =================================================================================================
+// Reduce kernel: 256-thread CTAs, 4096-position tiles handed out by a global ticket counter.
+// shared memory: [bars 16][base 8][misc][root 1K][pre2 8K][queue 8K][ids 16K][2 input stages]
+// [hot][chains][tails]
+// =================================================================================================
+constexpr int kROffBar = 0;        // 2 x uint64 mbarrier
+constexpr int kROffBase = 16;      // uint64 tile base
+constexpr int kROffWcount = 32;    // int[8]
+constexpr int kROffWoff = 64;      // int[8]
+constexpr int kROffTicket = 96;    // long long[2]
+constexpr int kROffRoot = 128;
+constexpr int kROffPre2 = kROffRoot + 1024;
+constexpr int kROffQueue = kROffPre2 + 8192;
+constexpr int kROffIds = kROffQueue + kRedWarps * kWarpTile * 2;
+constexpr int kROffIn = kROffIds + kRedTile * 4;
+
+template <bool POS64>
+__global__ void __launch_bounds__(kRedThreads) pfac_reduce_kernel(const KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + kROffBar);
+    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(smem + kROffBase);
+    int* s_wcount = reinterpret_cast<int*>(smem + kROffWcount);
+    int* s_woff = reinterpret_cast<int*>(smem + kROffWoff);
+    long long* s_ticket = reinterpret_cast<long long*>(smem + kROffTicket);
+    unsigned short* s_queue = reinterpret_cast<unsigned short*>(smem + kROffQueue);
+    int* s_ids = reinterpret_cast<int*>(smem + kROffIds);
+    const int stage = kRedTile + p.halo;
+    unsigned char* s_in = smem + kROffIn;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // ---- one-time setup: tables -> shared memory, mbarriers ---------------------------------
-    for (int i = tid; i < 256; i += kThreads) s_root[i] = p.root[i];
-    for (int i = tid; i < 2048 / 4; i += kThreads)
-        reinterpret_cast<uint4*>(s_pre2)[i] = reinterpret_cast<const uint4*>(p.pre2)[i];
-    for (uint32_t i = tid; i < p.hot_buckets; i += kThreads)
-        const_cast<uint4*>(s_hot)[i] = p.hot[i];
+    const Tables T = stage_tables(p, smem + kROffRoot, smem + kROffPre2, smem + kROffIn + 2 * stage, tid, kRedThreads);
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -187,311 +475,183 @@ __global__ void __launch_bounds__(kThreads) pfac_match_kernel(const KParams p) {
     }
     __syncthreads();
 
-    // stage one tile (+halo) into s_in[buf]; TMA when aligned and fully inside the input,
-    // else a guarded cooperative copy that zero-fills past n_total (tail tiles, odd pointers)
     auto tile_is_bulk = [&](long long t) -> bool {
-        return p.in_aligned && (t * kTile + stage <= p.n_total);
+        return p.in_aligned && (t * kRedTile + stage <= p.n_total);
     };
     auto load_tile = [&](long long t, int buf) {
         if (t >= p.num_tiles) return;
         unsigned char* dst = s_in + buf * stage;
-        const long long start = t * kTile;
+        const long long start = t * kRedTile;
         if (tile_is_bulk(t)) {
             if (tid == 0) {
                 mbar_arrive_expect_tx(&s_bar[buf], static_cast<uint32_t>(stage));
                 tma_load_1d(dst, p.in + start, static_cast<uint32_t>(stage), &s_bar[buf]);
             }
         } else {
-            for (int i = tid; i < stage; i += kThreads) {
+            for (int i = tid; i < stage; i += kRedThreads) {
                 const long long g = start + i;
                 dst[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
             }
         }
     };
 
-    // Tile assignment.  Dense: static striding (tiles are independent).  Reduce: tickets from a
-    // global counter, so a tile index is only ever held by a running CTA and the look-back
-    // below can never wait on a CTA that is not resident (two concurrent reduce launches on
-    // one GPU would otherwise be able to deadlock each other).
+    // Tiles are tickets from a global counter, so a tile index is only ever held by a running
+    // CTA and the look-back below can never wait on a CTA that is not resident.
     long long tile, next_tile;
-    if (MODE == kModeReduce) {
-        if (tid == 0) {
-            s_ticket[0] = static_cast<long long>(atomicAdd(p.ticket, 1ull));
-            s_ticket[1] = static_cast<long long>(atomicAdd(p.ticket, 1ull));
-        }
-        __syncthreads();
-        tile = s_ticket[0];
-        next_tile = s_ticket[1];
-        __syncthreads();
-    } else {
-        tile = blockIdx.x;
-        next_tile = tile + gridDim.x;
+    if (tid == 0) {
+        s_ticket[0] = static_cast<long long>(atomicAdd(p.ticket, 1ull));
+        s_ticket[1] = static_cast<long long>(atomicAdd(p.ticket, 1ull));
     }
+    __syncthreads();
+    tile = s_ticket[0];
+    next_tile = s_ticket[1];
+    __syncthreads();
     load_tile(tile, 0);
     load_tile(next_tile, 1);
     __syncthreads();
 
-    uint32_t parity = 0u;  // bit b = phase of s_bar[b]
+    uint32_t parity = 0u;
     unsigned short* q16 = s_queue + warp * kWarpTile;
-    int* wres = s_res + warp * kWarpTile;  // dense: this warp's 512 results; reduce: ids by queue slot
+    int* wids = s_ids + warp * kWarpTile;  // ids by queue slot
 
     for (int it = 0; tile < p.num_tiles; ++it) {
-        long long future_tile = next_tile + gridDim.x;  // dense; reduce overwrites below
         unsigned long long my_ticket = 0;
-        if (MODE == kModeReduce) {
-            if (tid == 0) my_ticket = atomicAdd(p.ticket, 1ull);  // consumed just before (A)
-        }
+        if (tid == 0) my_ticket = atomicAdd(p.ticket, 1ull);  // consumed just before (A)
         const int buf = it & 1;
         const unsigned char* inb = s_in + buf * stage;
-        const long long start = tile * kTile;
+        const long long start = tile * kRedTile;
         if (tile_is_bulk(tile)) {
             mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
             parity ^= 1u << buf;
         }
-        const long long owned_left = p.n_owned - start;             // > 0
-        const int valid = owned_left < kTile ? static_cast<int>(owned_left) : kTile;
-        const long long total_left = p.n_total - start;             // >= owned_left
+        const long long owned_left = p.n_owned - start;
+        const int valid = owned_left < kRedTile ? static_cast<int>(owned_left) : kRedTile;
+        const long long total_left = p.n_total - start;
         const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
 
-        // ---- prefilter: 16 consecutive start positions per thread ---------------------------
         const int lb = tid * kPosPerThread;
-        uint32_t w[5];
-        {
-            const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            w[4] = *reinterpret_cast<const uint32_t*>(inb + lb + 16);
-        }
-        uint32_t cand = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
-                const uint32_t idx = x & 0xFFFFu;  // c0 | c1<<8
-                const uint32_t word = s_pre2[idx >> 5];
-                cand |= ((word >> (idx & 31u)) & 1u) << (4 * k + j);
-            }
-        }
-        if (valid < kTile) {  // tail tile: drop positions we do not own
+        uint32_t cand = prefilter16(inb, lb, T.pre2);
+        if (valid < kRedTile) {
             int nv = valid - lb;
             nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
             cand &= (1u << nv) - 1u;
         }
-
-        // ---- ordered push of survivors into the warp queue -----------------------------------
-        const int cnt = __popc(cand);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
-        {
-            int off = incl - cnt;
-            while (cand) {
-                const int b = __ffs(cand) - 1;
-                cand &= cand - 1;
-                q16[off++] = static_cast<unsigned short>(lb + b);
-            }
-        }
-
-        if (MODE == kModeDense) {
-            // this warp's previous bulk store must have finished reading wres
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                reinterpret_cast<uint4*>(wres)[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
-        }
+        const int wtotal = push_survivors(cand, lb, q16, lane);
+        __syncwarp();
+        walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, 0, lane);
         __syncwarp();
 
-        // ---- walk the survivors; a lane that finishes pulls the next queue entry -------------
-        {
-            int head = 0;
-            bool active = false;
-            int pl = 0, d = 0, limit = 0, s = 0, best = 0, slot = 0;
-            for (;;) {
-                const unsigned need = __ballot_sync(0xffffffffu, !active);
-                if (need) {
-                    const int my = head + __popc(need & lt_mask);
-                    if (!active && my < wtotal) {
-                        slot = my;
-                        pl = q16[my];
-                        s = s_root[inb[pl]];
-                        best = (s <= p.num_final) ? s : 0;
-                        d = 1;
-                        limit = tile_rem - pl;  // bytes of real input from this position
-                        active = true;
+        // ---- ordered compaction: warp count -> CTA scan -> look-back -> write pairs -----------
+        int nmatch = 0;
+        for (int base = 0; base < wtotal; base += 32) {
+            const int i = base + lane;
+            const int id = (i < wtotal) ? wids[i] : 0;
+            nmatch += __popc(__ballot_sync(0xffffffffu, id != 0));
+        }
+        if (lane == 0) s_wcount[warp] = nmatch;
+        if (tid == 0) s_ticket[0] = static_cast<long long>(my_ticket);
+        __syncthreads();  // (A) all walks done: s_in[buf] is free, counts are published
+        const long long future_tile = s_ticket[0];
+        load_tile(future_tile, buf);
+        if (warp == 0) {
+            const int c = (lane < kRedWarps) ? s_wcount[lane] : 0;
+            int inc = c;
+#pragma unroll
+            for (int dd = 1; dd < kRedWarps; dd <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, dd);
+                if (lane >= dd) inc += o;
+            }
+            if (lane < kRedWarps) s_woff[lane] = inc - c;
+            const unsigned long long ttotal =
+                static_cast<unsigned long long>(__shfl_sync(0xffffffffu, inc, kRedWarps - 1));
+            unsigned long long base = 0;
+            if (tile > 0) {
+                if (lane == 0) st_relaxed_u64(p.desc + tile, kStatusAgg | ttotal);
+                long long t = tile - 1;
+                for (;;) {
+                    const long long idx = t - lane;
+                    unsigned long long v = (idx >= 0) ? ld_relaxed_u64(p.desc + idx) : kStatusIncl;
+                    while (__any_sync(0xffffffffu, (v >> 62) == 0)) {
+                        if ((v >> 62) == 0) v = ld_relaxed_u64(p.desc + idx);
                     }
-                    head += __popc(need);
+                    const unsigned incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+                    unsigned long long part = (lane <= first) ? (v & kValueMask) : 0ull;
+#pragma unroll
+                    for (int dd = 16; dd > 0; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+                    base += part;
+                    if (incl_mask) break;
+                    t -= 32;
                 }
-                if (!__any_sync(0xffffffffu, active)) break;
-                if (active) {
-                    bool done = (d >= limit) || (s < 0);
-                    if (!done) {
-                        const int at = pl + d;
-                        const uint32_t c = (at < stage) ? inb[at] : p.in[start + at];
-                        const uint32_t key = (static_cast<uint32_t>(s) << 8) | c;
-                        const int nx = (d < p.hot_depth) ? probe_hot(s_hot, p.hot_buckets, p.mul, key)
-                                                         : probe_cold(p.cold, p.cold_buckets, p.mul, key);
-                        if (nx < 0) {
-                            done = true;
-                        } else {
-                            s = nx;
-                            if (s <= p.num_final) best = s;
-                            d++;
-                        }
-                    }
-                    if (done) {
-                        if (MODE == kModeDense) {
-                            if (best) wres[pl - warp * kWarpTile] = best;
-                        } else {
-                            wres[slot] = best;
-                        }
-                        active = false;
-                    }
-                }
+            }
+            if (lane == 0) {
+                st_relaxed_u64(p.desc + tile, kStatusIncl | (base + ttotal));
+                *s_base = base;
+                if (tile == p.num_tiles - 1) *p.total = base + ttotal;
             }
         }
-
-        if (MODE == kModeDense) {
-            // ---- ship this warp's 512 results -------------------------------------------------
-            int vw = valid - warp * kWarpTile;
-            vw = vw < 0 ? 0 : (vw > kWarpTile ? kWarpTile : vw);
-            int* gout = p.out + start + warp * kWarpTile;
-            if (p.out_aligned && vw == kWarpTile) {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_1d(gout, wres, kWarpTile * 4);
-                    tma_store_commit();
-                }
-            } else {
-                __syncwarp();
-                for (int i = lane; i < vw; i += 32) gout[i] = wres[i];
+        __syncthreads();  // (B)
+        unsigned long long obase = *s_base + static_cast<unsigned long long>(s_woff[warp]);
+        for (int base = 0; base < wtotal; base += 32) {
+            const int i = base + lane;
+            const int id = (i < wtotal) ? wids[i] : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, id != 0);
+            if (id != 0) {
+                const unsigned long long o = obase + __popc(m & lt_mask);
+                const long long gpos = p.pos_base + start + q16[i];
+                p.out_id[o] = id;
+                if (POS64) reinterpret_cast<long long*>(p.out_pos)[o] = gpos;
+                else reinterpret_cast<int*>(p.out_pos)[o] = static_cast<int>(gpos);
             }
-            __syncthreads();  // every warp is done reading s_in[buf]
-            load_tile(future_tile, buf);
-        } else {
-            // ---- ordered compaction: warp count -> CTA scan -> look-back -> write pairs -------
-            __syncwarp();
-            int nmatch = 0;
-            for (int base = 0; base < wtotal; base += 32) {
-                const int i = base + lane;
-                const int id = (i < wtotal) ? wres[i] : 0;
-                nmatch += __popc(__ballot_sync(0xffffffffu, id != 0));
-            }
-            if (lane == 0) s_wcount[warp] = nmatch;
-            if (tid == 0) s_ticket[0] = static_cast<long long>(my_ticket);
-            __syncthreads();  // (A) all walks done: s_in[buf] is free, counts are published
-            future_tile = s_ticket[0];
-            load_tile(future_tile, buf);
-            if (warp == 0) {
-                const int c = (lane < kWarps) ? s_wcount[lane] : 0;
-                int inc = c;
-#pragma unroll
-                for (int dd = 1; dd < kWarps; dd <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, inc, dd);
-                    if (lane >= dd) inc += o;
-                }
-                if (lane < kWarps) s_woff[lane] = inc - c;
-                const unsigned long long ttotal =
-                    static_cast<unsigned long long>(__shfl_sync(0xffffffffu, inc, kWarps - 1));
-                unsigned long long base = 0;
-                if (tile > 0) {
-                    if (lane == 0) st_relaxed_u64(p.desc + tile, kStatusAgg | ttotal);
-                    long long t = tile - 1;
-                    for (;;) {
-                        const long long idx = t - lane;
-                        unsigned long long v = (idx >= 0) ? ld_relaxed_u64(p.desc + idx) : kStatusIncl;
-                        while (__any_sync(0xffffffffu, (v >> 62) == 0)) {
-                            if ((v >> 62) == 0) v = ld_relaxed_u64(p.desc + idx);
-                        }
-                        const unsigned incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                        const int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
-                        unsigned long long part = (lane <= first) ? (v & kValueMask) : 0ull;
-#pragma unroll
-                        for (int dd = 16; dd > 0; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
-                        base += part;
-                        if (incl_mask) break;
-                        t -= 32;
-                    }
-                }
-                if (lane == 0) {
-                    st_relaxed_u64(p.desc + tile, kStatusIncl | (base + ttotal));
-                    *s_base = base;
-                    if (tile == p.num_tiles - 1) *p.total = base + ttotal;
-                }
-            }
-            __syncthreads();  // (B)
-            unsigned long long obase = *s_base + static_cast<unsigned long long>(s_woff[warp]);
-            for (int base = 0; base < wtotal; base += 32) {
-                const int i = base + lane;
-                const int id = (i < wtotal) ? wres[i] : 0;
-                const unsigned m = __ballot_sync(0xffffffffu, id != 0);
-                if (id != 0) {
-                    const unsigned long long o = obase + __popc(m & lt_mask);
-                    const long long gpos = p.pos_base + start + q16[i];
-                    p.out_id[o] = id;
-                    if (POS64) reinterpret_cast<long long*>(p.out_pos)[o] = gpos;
-                    else reinterpret_cast<int*>(p.out_pos)[o] = static_cast<int>(gpos);
-                }
-                obase += __popc(m);
-            }
+            obase += __popc(m);
         }
         tile = next_tile;
         next_tile = future_tile;
-    }
-    if (MODE == kModeDense) {
-        if (lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
     }
 }
 
 std::atomic<unsigned long long> g_launches{0};
 
-int haloFor(int maxPatternLen) {
+int roundHalo(int maxPatternLen, int cap) {
     int h = maxPatternLen - 1;
-    if (h < 4) h = 4;                 // the prefilter reads one word past the tile
+    if (h < 4) h = 4;  // the prefilter reads one word past the tile
     h = (h + 15) & ~15;
-    if (h > kMaxHalo) h = kMaxHalo;
+    if (h > cap) h = cap;
     return h;
 }
 
-size_t smemBytes(const DeviceTable& t, int halo) {
-    return size_t(kOffIn) + 2 * size_t(kTile + halo) + size_t(t.hotBuckets) * 16;
+int denseStages(int halo) { return halo > 256 ? 2 : 3; }
+
+size_t denseFixedBytes(int halo) {
+    const int nst = denseStages(halo);
+    const size_t bar = size_t((kDenseWarps * nst * 8 + 127) / 128) * 128;
+    return bar + 1024 + 8192 + size_t(kDenseWarps) * (kWarpTile * 2 + kWarpTile * 4 + nst * (kWarpTile + halo));
 }
 
-template <typename K>
-cudaError_t prepare(K kernel, size_t smem, const LaunchConfig& cfg, long long numTiles, int* gridOut) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    int perSM = cfg.ctasPerSM;
-    if (perSM <= 0) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kThreads, smem);
-        if (e != cudaSuccess) return e;
-        if (perSM < 1) return cudaErrorLaunchOutOfResources;
-    }
-    long long g = static_cast<long long>(cfg.numSMs) * perSM;
-    if (g > numTiles) g = numTiles;
-    *gridOut = int(g);
-    return cudaSuccess;
+size_t tableSmemBytes(const DeviceTable& t) {
+    return size_t(t.hotBuckets) * 16 + (t.chainsHot ? size_t(t.chainBytes) + t.tailBytes : 0);
 }
 
-KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned, size_t n_total, int halo) {
+KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned, size_t n_total, int halo,
+                   int tileSize) {
     KParams p{};
     p.in = in;
     p.n_owned = (long long)n_owned;
     p.n_total = (long long)n_total;
-    p.num_tiles = ((long long)n_owned + kTile - 1) / kTile;
+    p.num_tiles = ((long long)n_owned + tileSize - 1) / tileSize;
     p.root = t.root;
     p.pre2 = t.pre2;
     p.hot = t.hot;
     p.cold = t.cold;
+    p.chains = t.chains;
+    p.tails = t.tails;
     p.hot_buckets = t.hotBuckets;
     p.cold_buckets = t.coldBuckets;
+    p.chain_bytes = t.chainBytes;
+    p.tail_bytes = t.tailBytes;
     p.mul = t.mul;
     p.hot_depth = t.hotDepth;
+    p.chains_hot = t.chainsHot ? 1 : 0;
     p.num_final = t.numFinal;
     p.halo = halo;
     p.in_aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
@@ -500,23 +660,32 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
 
 }  // namespace
 
-size_t reduceWorkspaceWords(size_t n_owned) { return (n_owned + kTile - 1) / kTile + 1; }
+size_t tableSmemBudget(int maxPatternLen) {
+    const size_t fixed = denseFixedBytes(roundHalo(maxPatternLen, kDenseMaxHalo));
+    return fixed < size_t(kMaxSmem) ? size_t(kMaxSmem) - fixed : 0;
+}
+
+size_t reduceWorkspaceWords(size_t n_owned) { return (n_owned + kRedTile - 1) / kRedTile + 1; }
 
 unsigned long long kernelLaunchCount() { return g_launches.load(); }
 
 cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                              size_t n_owned, size_t n_total, int* out, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
-    const int halo = haloFor(t.maxPatternLen);
-    KParams p = baseParams(t, in, n_owned, n_total, halo);
+    const int halo = roundHalo(t.maxPatternLen, kDenseMaxHalo);
+    KParams p = baseParams(t, in, n_owned, n_total, halo, kWarpTile);
     p.out = out;
     p.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    const size_t smem = smemBytes(t, halo);
-    auto kernel = pfac_match_kernel<kModeDense, false>;
-    int grid = 0;
-    cudaError_t e = prepare(kernel, smem, cfg, p.num_tiles, &grid);
+    const size_t smem = denseFixedBytes(halo) + tableSmemBytes(t);
+    if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
+    const int nst = denseStages(halo);
+    auto kernel = (nst == 3) ? pfac_dense_kernel<3> : pfac_dense_kernel<2>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kThreads, smem, stream>>>(p);
+    const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
+    long long grid = cfg.numSMs;
+    if (grid > ctaTiles) grid = ctaTiles;
+    kernel<<<int(grid), kDenseThreads, smem, stream>>>(p);
     g_launches++;
     return cudaGetLastError();
 }
@@ -526,28 +695,28 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
                               void* out_pos, bool pos64, unsigned long long* desc,
                               unsigned long long* d_total, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
-    const int halo = haloFor(t.maxPatternLen);
-    KParams p = baseParams(t, in, n_owned, n_total, halo);
+    const int halo = roundHalo(t.maxPatternLen, kRedMaxHalo);
+    KParams p = baseParams(t, in, n_owned, n_total, halo, kRedTile);
     p.out_id = out_id;
     p.out_pos = out_pos;
     p.pos_base = pos_base;
     p.desc = desc;
     p.ticket = desc + p.num_tiles;  // last workspace word
     p.total = d_total;
-    const size_t smem = smemBytes(t, halo);
-    int grid = 0;
-    cudaError_t e;
-    if (pos64) {
-        auto kernel = pfac_match_kernel<kModeReduce, true>;
-        e = prepare(kernel, smem, cfg, p.num_tiles, &grid);
+    const size_t smem = size_t(kROffIn) + 2 * size_t(kRedTile + halo) + tableSmemBytes(t);
+    if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
+    auto kernel = pos64 ? pfac_reduce_kernel<true> : pfac_reduce_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    int perSM = cfg.ctasPerSM;
+    if (perSM <= 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kRedThreads, smem);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, kThreads, smem, stream>>>(p);
-    } else {
-        auto kernel = pfac_match_kernel<kModeReduce, false>;
-        e = prepare(kernel, smem, cfg, p.num_tiles, &grid);
-        if (e != cudaSuccess) return e;
-        kernel<<<grid, kThreads, smem, stream>>>(p);
+        if (perSM < 1) return cudaErrorLaunchOutOfResources;
     }
+    long long grid = static_cast<long long>(cfg.numSMs) * perSM;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    kernel<<<int(grid), kRedThreads, smem, stream>>>(p);
     g_launches++;
     return cudaGetLastError();
 }

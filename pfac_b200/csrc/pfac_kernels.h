@@ -13,8 +13,13 @@ struct DeviceTable {
     const uint32_t* pre2 = nullptr;   // 2048
     const uint4* hot = nullptr;       // hotBuckets (copied into shared memory by each CTA)
     const uint4* cold = nullptr;      // coldBuckets (read through L1/L2)
+    const uint4* chains = nullptr;    // chain records (16 B each)
+    const unsigned char* tails = nullptr;
     uint32_t hotBuckets = 0;
     uint32_t coldBuckets = 1;
+    uint32_t chainBytes = 0;          // multiple of 16
+    uint32_t tailBytes = 0;           // multiple of 16
+    bool chainsHot = false;           // kernels also copy chains + tails into shared memory
     uint32_t mul = 0;
     int hotDepth = 1;
     int numFinal = 0;
@@ -25,6 +30,10 @@ struct LaunchConfig {
     int numSMs = 148;
     int ctasPerSM = 0;   // 0 = ask the occupancy API
 };
+
+// Shared-memory bytes the dense kernel can spare for hash rows / chains / tails, given the
+// longest pattern (which fixes the staged halo).  The table compiler is run with this budget.
+size_t tableSmemBudget(int maxPatternLen);
 
 // Look-back descriptor words needed by the reduce kernel for an n_owned-byte shard.
 size_t reduceWorkspaceWords(size_t n_owned);

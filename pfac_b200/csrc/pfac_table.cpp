@@ -194,11 +194,12 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     for (int c = 0; c < kCharSet; c++) L.root[c] = -1;
     L.pre2.assign(65536 / 32, 0u);
 
-    // Matching edges: per (state,ch) the LAST edge in insertion order wins, as in the
-    // reference's dense table fill (PFAC.cpp:376-381).  BFS from the initial state gives the
-    // depth of every reachable source state.
-    std::vector<FlatEdge> edges;
-    std::vector<int> depth(size_t(std::max(m.numStates, 1)), -1);
+    // ---- matching automaton: per (state,ch) the LAST edge in insertion order wins, as in the
+    // reference's dense table fill (PFAC.cpp:376-381).  BFS from the initial state gives every
+    // reachable state's depth and its (sorted) out-edges.
+    const size_t S = size_t(std::max(m.numStates, 1));
+    std::vector<int> depth(S, -1);
+    std::vector<std::vector<Edge>> out(S);
     std::vector<int> frontier;
     if (m.numStates > m.initialState) {
         depth[size_t(m.initialState)] = 0;
@@ -223,51 +224,107 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
                 depth[size_t(nx)] = depth[size_t(s)] + 1;
                 frontier.push_back(nx);
             }
-            if (s == m.initialState) L.root[ch] = nx;
-            else edges.push_back(FlatEdge{edgeKey(s, ch), nx, depth[size_t(s)]});
+            out[size_t(s)].push_back(Edge{ch, nx});
+            L.numEdges++;
             L.maxDepth = std::max(L.maxDepth, depth[size_t(s)] + 1);
         }
     }
-    L.numEdges = int(edges.size());
-    for (int c = 0; c < kCharSet; c++) if (L.root[c] >= 0) L.rootFanout++;
+    auto isFinal = [&](int s) { return s >= 1 && s <= m.numFinal; };
 
-    // Prefilter: bit (c0 | c1<<8) is set iff a walk starting with c0,c1 can produce a result:
-    // root[c0] is a final state (1-byte pattern: any c1), or (root[c0], c1) is an edge.
-    // Clear bit => result 0 with certainty; set bit => the walker decides.
-    for (int c0 = 0; c0 < kCharSet; c0++) {
-        if (L.root[c0] >= 0 && L.root[c0] <= m.numFinal)
-            for (int c1 = 0; c1 < kCharSet; c1++) {
-                uint32_t idx = uint32_t(c0) | (uint32_t(c1) << 8);
+    // ---- root row + prefilter.  Bit (c0 | c1<<8) is set iff a walk starting with c0,c1 can
+    // produce a result: root[c0] is a final state (1-byte pattern: any c1), or (root[c0], c1) is
+    // an edge.  Clear bit => result 0 with certainty; set bit => the walker decides.
+    if (!frontier.empty()) {
+        for (const Edge& e : out[size_t(m.initialState)]) {
+            L.root[e.ch] = e.next;
+            L.rootFanout++;
+            const uint32_t c0 = uint32_t(e.ch);
+            if (isFinal(e.next)) {
+                for (uint32_t c1 = 0; c1 < 256; c1++) {
+                    const uint32_t idx = c0 | (c1 << 8);
+                    L.pre2[idx >> 5] |= 1u << (idx & 31);
+                }
+            }
+            for (const Edge& e2 : out[size_t(e.next)]) {
+                const uint32_t idx = c0 | (uint32_t(e2.ch) << 8);
                 L.pre2[idx >> 5] |= 1u << (idx & 31);
             }
-    }
-    {
-        std::unordered_map<int, int> c0OfState;  // depth-1 state -> the first byte leading to it
-        for (int c0 = 0; c0 < kCharSet; c0++)
-            if (L.root[c0] >= 0) c0OfState[L.root[c0]] = c0;
-        for (const FlatEdge& e : edges) {
-            if (e.depth != 1) continue;
-            const int src = int(e.key >> 8), c1 = int(e.key & 0xFF);
-            auto it = c0OfState.find(src);
-            if (it == c0OfState.end()) continue;
-            uint32_t idx = uint32_t(it->second) | (uint32_t(c1) << 8);
-            L.pre2[idx >> 5] |= 1u << (idx & 31);
         }
     }
     for (uint32_t w : L.pre2) L.pre2BitsSet += __builtin_popcount(w);
 
-    // Hot/cold split by source depth.  The walker knows its depth (= bytes consumed), so
+    // ---- hash edges with chain compression.  From every lookup source (root children, plain
+    // edge targets, chain ends) follow each out-edge; a run of >= kMinChain non-final
+    // single-child states behind it becomes one chain record whose tail bytes are compared
+    // directly against the text (independent loads) instead of one dependent lookup per byte.
+    std::vector<FlatEdge> edges;
+    std::vector<char> queued(S, 0);
+    std::vector<int> sources;
+    if (!frontier.empty())
+        for (const Edge& e : out[size_t(m.initialState)])
+            if (!queued[size_t(e.next)]) { queued[size_t(e.next)] = 1; sources.push_back(e.next); }
+    std::vector<uint8_t> tail;
+    for (size_t qi = 0; qi < sources.size(); qi++) {
+        const int s = sources[qi];
+        for (const Edge& e : out[size_t(s)]) {
+            int cur = e.next;
+            tail.clear();
+            while (!isFinal(cur) && out[size_t(cur)].size() == 1) {
+                tail.push_back(uint8_t(out[size_t(cur)][0].ch));
+                cur = out[size_t(cur)][0].next;
+            }
+            uint32_t val;
+            int target;
+            if (int(tail.size()) >= kMinChain) {
+                const uint32_t idx = uint32_t(L.numChains++);
+                const uint32_t off = uint32_t(L.tails.size());
+                uint32_t inline4 = 0;
+                for (size_t b = 0; b < tail.size(); b++) {
+                    L.tails.push_back(tail[b]);
+                    if (b < 4) inline4 |= uint32_t(tail[b]) << (8 * b);
+                }
+                while (L.tails.size() & 3) L.tails.push_back(0);
+                const bool leaf = out[size_t(cur)].empty();
+                L.chains.push_back(off);
+                L.chains.push_back(uint32_t(tail.size()));
+                L.chains.push_back(uint32_t(cur) | (leaf ? kLeafFlag : 0u));
+                L.chains.push_back(inline4);
+                val = kChainFlag | idx;
+                target = cur;
+            } else {
+                val = uint32_t(e.next);
+                target = e.next;
+            }
+            edges.push_back(FlatEdge{edgeKey(s, e.ch), int(val), depth[size_t(s)]});
+            if (!out[size_t(target)].empty() && !queued[size_t(target)]) {
+                queued[size_t(target)] = 1;
+                sources.push_back(target);
+            }
+        }
+    }
+    L.hashEdges = int(edges.size());
+    while (L.tails.size() & 15) L.tails.push_back(0);
+    if (L.chains.empty()) L.chains.assign(4, 0u);  // keep device pointers valid
+
+    // ---- hot/cold split by source depth.  The walker knows its depth (= bytes consumed), so
     // which table to probe costs no lookup.  Load factor 0.5: buckets(2 slots) = #edges.
     std::stable_sort(edges.begin(), edges.end(),
                      [](const FlatEdge& a, const FlatEdge& b) { return a.depth < b.depth; });
     std::vector<size_t> upto(size_t(L.maxDepth) + 2, 0);  // upto[d] = #edges with depth < d
     for (const FlatEdge& e : edges) upto[size_t(e.depth) + 1]++;
     for (size_t d = 1; d < upto.size(); d++) upto[d] += upto[d - 1];
-    const size_t hotSlots = hotBudgetBytes / 16;  // buckets affordable
-    int H = 1;  // upto[] is non-decreasing; upto[1] == 0 (root edges live in the root row)
-    for (int d = 2; d < int(upto.size()); d++) {
-        if (upto[size_t(d)] <= hotSlots) H = d;
-        else break;
+    const size_t chainBytes = L.chains.size() * 4 + L.tails.size();
+    int H = 1;
+    if (!edges.empty() && edges.size() * 16 + chainBytes <= hotBudgetBytes) {
+        H = int(upto.size()) - 1;      // everything in shared memory, chains and tails too
+        L.chainsHot = true;
+    } else {
+        const size_t hotSlots = hotBudgetBytes / 16;
+        for (int d = 2; d < int(upto.size()); d++) {  // upto[] is non-decreasing, upto[1] == 0
+            if (upto[size_t(d)] <= hotSlots) H = d;
+            else break;
+        }
+        if (upto[size_t(H)] == 0) H = 1;
     }
     L.hotDepth = H;
     const size_t nHot = upto[size_t(H)];

@@ -45,27 +45,44 @@ int buildMachine(const char* image, size_t size, Machine& m);
 // Text dump, byte-identical to reference PFAC_dumpTransitionTable (PFAC.cpp:1188-1246).
 void dumpMachine(const Machine& m, FILE* fp);
 
-// What gets uploaded.  Buckets are 4 x uint32 {key0, val0, key1, val1}, key = state<<8|ch,
-// slot 0 filled before slot 1, bucket = umulhi(key * mul, nbuckets), linear probing.
+// What gets uploaded.
+//   hash rows: buckets of 4 x uint32 {key0, val0, key1, val1}; key = state<<8|ch; slot 0 is
+//     filled before slot 1; bucket = umulhi(key * mul, nbuckets); linear probing.
+//     val = next state, or kChainFlag | chain index when the edge starts a compressed chain.
+//   chains: 4 x uint32 {tail offset (bytes, multiple of 4), len, end state | kLeafFlag,
+//     first 4 tail bytes}: after the edge's own byte, `len` more bytes must equal the tail; the
+//     walk then stands in the end state.  Chain interiors are non-final single-child states, so
+//     skipping them cannot change any result; kLeafFlag = the end state has no out-edges.
+constexpr uint32_t kChainFlag = 0x80000000u;
+constexpr uint32_t kLeafFlag = 0x80000000u;
+constexpr int kMinChain = 2;          // compress runs of at least this many single-child states
+
 struct DeviceLayout {
     int32_t root[kCharSet];          // next state from the initial state, -1 = trap
     std::vector<uint32_t> pre2;      // 65536-bit prefilter, index c0 | c1<<8
     std::vector<uint32_t> hot;       // edges with source depth in [1,hotDepth)  -> smem
     std::vector<uint32_t> cold;      // edges with source depth >= hotDepth      -> global/L2
+    std::vector<uint32_t> chains;    // 4 words per chain record
+    std::vector<uint8_t> tails;      // chain tail bytes, each tail padded to 4
     uint32_t hotBuckets = 0, coldBuckets = 0;
     uint32_t mul = 0x9E3779B1u;
     int hotDepth = 1;
+    bool chainsHot = false;          // chain records + tails fit the shared-memory budget too
     int maxDepth = 0;
-    int numEdges = 0;
+    int numEdges = 0;                // transitions of the (uncompressed) automaton, root included
+    int hashEdges = 0;               // entries in hot + cold after chain compression
+    int numChains = 0;
     int hotMaxProbe = 0, coldMaxProbe = 0;
     int pre2BitsSet = 0;
     int rootFanout = 0;
     size_t deviceBytes() const {
-        return sizeof(root) + pre2.size() * 4 + hot.size() * 4 + cold.size() * 4;
+        return sizeof(root) + pre2.size() * 4 + hot.size() * 4 + cold.size() * 4 + chains.size() * 4 +
+               tails.size();
     }
 };
 
-// hotBudgetBytes: shared-memory bytes the kernels may spend on the hot hash rows.
+// hotBudgetBytes: shared-memory bytes the kernels may spend on hash rows (+ chains and tails
+// when everything fits).
 void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L);
 
 }  // namespace pfac

@@ -9,11 +9,11 @@ def read_patterns(path):
     return [p for p in parts[:-1] if p]  # the unterminated tail is dropped by the parser
 
 
-def emulate_layout_walk(layout, num_final, text, start, n_total=None):
+def emulate_layout_walk(L, num_final, text, start, n_total=None):
     """Python restatement of the lookup sequence the CUDA kernels run on the compiled device
-    layout (pfac_b200/csrc/pfac_kernels.cu): prefilter bit -> root row -> bucketed hash rows,
-    hot for depth < hot_depth else cold.  Test-only; checks the table compiler without a GPU."""
-    root, pre2, hot, cold, hot_depth, mul = layout
+    layout (pfac_b200/csrc/pfac_kernels.cu): prefilter bit -> root row -> bucketed hash rows
+    (hot for depth < hot_depth else cold) -> chain records with byte-wise tail compare.
+    Test-only; checks the table compiler without a GPU.  L = TableCompiler.layout()."""
     n_total = len(text) if n_total is None else n_total
     avail = n_total - start
     if avail <= 0:
@@ -21,22 +21,37 @@ def emulate_layout_walk(layout, num_final, text, start, n_total=None):
     c0 = int(text[start])
     c1 = int(text[start + 1]) if avail >= 2 else 0
     idx = c0 | (c1 << 8)
-    if not (int(pre2[idx >> 5]) >> (idx & 31)) & 1:
+    if not (int(L["pre2"][idx >> 5]) >> (idx & 31)) & 1:
         return 0
-    s = int(root[c0])
+    s = int(L["root"][c0])
     assert s >= 0, "prefilter bit set but root row traps"
     best = s if s <= num_final else 0
     d = 1
     while d < avail:
         key = ((s << 8) | int(text[start + d])) & 0xFFFFFFFF
-        tab = hot if d < hot_depth else cold
-        nx = probe(tab, mul, key)
-        if nx < 0:
+        tab = L["hot"] if d < L["hot_depth"] else L["cold"]
+        v = probe(tab, L["mul"], key)
+        if v < 0:
             break
-        s = nx
-        if s <= num_final:
-            best = s
-        d += 1
+        if v & 0x80000000:
+            off, ln, end, inline4 = (int(x) for x in L["chains"][v & 0x7FFFFFFF])
+            if d + 1 + ln > avail:
+                break  # cut off by the end of the input: nothing more can be reported
+            tail = bytes(L["tails"][off:off + ln])
+            assert inline4 == int.from_bytes(tail[:4].ljust(4, b"\0"), "little")
+            if bytes(text[start + d + 1:start + d + 1 + ln]) != tail:
+                break
+            s = end & 0x7FFFFFFF
+            d += 1 + ln
+            if s <= num_final:
+                best = s
+            if end & 0x80000000:
+                break
+        else:
+            s = v
+            if s <= num_final:
+                best = s
+            d += 1
     return best
 
 
@@ -52,6 +67,6 @@ def probe(tab, mul, key):
         if k1 == key:
             return v1
         if k1 == 0xFFFFFFFF:
-            return -1
+            return -1  # trap
         b = 0 if b + 1 == nb else b + 1
     raise AssertionError("probe did not terminate: table has no empty slot")

@@ -18,9 +18,7 @@ from tests.helpers import emulate_layout_walk, read_patterns
 
 
 def _layout(tc):
-    root, pre2, hot, cold = tc.layout()
-    info = tc.info()
-    return (root, pre2, hot, cold, info["hot_depth"], info["hash_mul"])
+    return tc.layout()
 
 
 @pytest.mark.parametrize("fixture", ["example_pattern", "example_pattern2"])
@@ -47,6 +45,7 @@ def test_info_readme_example(golden_dir):
     info = TableCompiler(os.path.join(golden_dir, "example_pattern")).info()
     assert (info["num_patterns"], info["num_states"], info["initial_state"], info["max_pattern_len"]) == (4, 11, 5, 4)
     assert info["num_leaves"] == 3 and info["num_edges"] == 9 and info["root_fanout"] == 3
+    assert info["num_chains"] == 1 and info["hash_edges"] == 4  # B-E-(D-E) is the only run >= 2
     assert info["pre2_bits_set"] == 3  # AB, BE, ED
 
 
@@ -65,11 +64,13 @@ def test_layout_walk_equals_oracle(golden_dir, case, hot_kb):
     tc = TableCompiler(pfile, hot_budget_bytes=hot_kb * 1024)
     info = tc.info()
     L = _layout(tc)
-    assert L[2].shape[0] * 16 <= max(hot_kb * 1024, 0)
+    assert L["hot"].shape[0] * 16 <= max(hot_kb * 1024, 0)
     if hot_kb == 0:
-        assert info["hot_depth"] == 1 and info["hot_buckets"] == 0
+        assert info["hot_depth"] == 1 and info["hot_buckets"] == 0 and not info["chains_hot"]
     if hot_kb == 512:
-        assert info["hot_depth"] == info["max_depth"] + 1  # everything fits: all rows hot
+        assert info["hot_depth"] == info["max_depth"] + 1 and info["chains_hot"]  # everything fits
+        assert info["hot_buckets"] == info["hash_edges"]
+    assert info["num_chains"] > 0 and info["hash_edges"] < info["num_edges"]
     got = np.array([emulate_layout_walk(L, o.num_patterns, text, i) for i in range(n)], dtype=np.int32)
     bad = np.flatnonzero(got != want)
     assert bad.size == 0, "first mismatch at %d: got %d want %d" % (bad[0], got[bad[0]], want[bad[0]])
@@ -80,7 +81,8 @@ def test_layout_root_and_prefilter_against_dense_table(golden_dir):
     o = Oracle(pfile)
     T = o.dense_table()
     tc = TableCompiler(pfile)
-    root, pre2, hot, cold = tc.layout()
+    L = tc.layout()
+    root, pre2, hot, cold = L["root"], L["pre2"], L["hot"], L["cold"]
     init, k = o.initial_state, o.num_patterns
     assert np.array_equal(root, T[init])
     bits = np.unpackbits(pre2.view(np.uint8), bitorder="little").reshape(256, 256)  # [c1][c0]
@@ -89,11 +91,13 @@ def test_layout_root_and_prefilter_against_dense_table(golden_dir):
         for c1 in range(256):
             expect = s >= 0 and (s <= k or T[s, c1] >= 0)
             assert bool(bits[c1, c0]) == bool(expect), (c0, c1)
-    # every transition of every reachable non-root state is in exactly one hash table
+    # every hash entry is unique; chain compression accounts for the missing transitions
     info = tc.info()
     keys = np.concatenate([hot[:, 0], hot[:, 2], cold[:, 0], cold[:, 2]])
     keys = keys[keys != 0xFFFFFFFF]
-    assert keys.size == np.unique(keys).size == info["num_edges"] - info["root_fanout"]
+    assert keys.size == np.unique(keys).size == info["hash_edges"]
+    chain_len = int(L["chains"][:info["num_chains"], 1].sum())
+    assert info["num_edges"] == info["root_fanout"] + info["hash_edges"] + chain_len
 
 
 def test_duplicates_prefixes_and_one_byte_patterns():
