@@ -56,6 +56,7 @@ class TableInfo(ctypes.Structure):
                 ("num_leaves", ctypes.c_int), ("num_edges", ctypes.c_int),
                 ("hash_edges", ctypes.c_int), ("num_chains", ctypes.c_int),
                 ("tail_bytes", ctypes.c_int), ("chains_hot", ctypes.c_int),
+                ("next2_hot", ctypes.c_int),
                 ("max_depth", ctypes.c_int), ("hot_depth", ctypes.c_int),
                 ("hot_buckets", ctypes.c_uint), ("cold_buckets", ctypes.c_uint),
                 ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
@@ -119,8 +120,7 @@ def load_library():
         "PFAC_tableDump": [vp, vp],
         "PFAC_tableDumpToFile": [vp, cp],
         "PFAC_tableGetInfo": [vp, ctypes.POINTER(TableInfo)],
-        "PFAC_tableGetLayout": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
-                                ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
+        "PFAC_tableGetLayout": [vp] + [ctypes.POINTER(vp)] * 8,
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
     }
     for name, args in sig.items():
@@ -321,9 +321,9 @@ class TableCompiler:
         _check(self._L.PFAC_tableDumpToFile(self._t, os.fsencode(filename)), "PFAC_tableDumpToFile")
 
     def layout(self):
-        """Copies of the device layout arrays as a dict: root[256] i32, pre2[2048] u32, hot/cold
+        """Copies of the device layout arrays as a dict: root[256] i32, pre2[2048] u32 (bit-reversed words), rank2[2048] u16, next2 u32, hot/cold
         [n,4] u32 buckets, chains [n,4] u32 records, tails u8, plus hot_depth and mul."""
-        ptrs = [ctypes.c_void_p() for _ in range(6)]
+        ptrs = [ctypes.c_void_p() for _ in range(8)]
         _check(self._L.PFAC_tableGetLayout(self._t, *[ctypes.byref(p) for p in ptrs]),
                "PFAC_tableGetLayout")
         info = self.info()
@@ -336,9 +336,11 @@ class TableCompiler:
         return {
             "root": arr(ptrs[0], 1024, np.int32),
             "pre2": arr(ptrs[1], 8192, np.uint32),
-            "hot": arr(ptrs[2], info["hot_buckets"] * 16, np.uint32).reshape(-1, 4),
-            "cold": arr(ptrs[3], info["cold_buckets"] * 16, np.uint32).reshape(-1, 4),
-            "chains": arr(ptrs[4], max(info["num_chains"], 1) * 16, np.uint32).reshape(-1, 4),
-            "tails": arr(ptrs[5], info["tail_bytes"], np.uint8),
+            "rank2": arr(ptrs[2], 4096, np.uint16),
+            "next2": arr(ptrs[3], max(info["pre2_bits_set"], 1) * 4, np.uint32),
+            "hot": arr(ptrs[4], info["hot_buckets"] * 16, np.uint32).reshape(-1, 4),
+            "cold": arr(ptrs[5], info["cold_buckets"] * 16, np.uint32).reshape(-1, 4),
+            "chains": arr(ptrs[6], max(info["num_chains"], 1) * 16, np.uint32).reshape(-1, 4),
+            "tails": arr(ptrs[7], info["tail_bytes"], np.uint8),
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
         }

@@ -59,6 +59,8 @@ struct PFAC_context {
     pfac::DeviceTable table;
     void* d_root = nullptr;
     void* d_pre2 = nullptr;
+    void* d_rank2 = nullptr;
+    void* d_next2 = nullptr;
     void* d_hot = nullptr;
     void* d_cold = nullptr;
     void* d_chains = nullptr;
@@ -78,6 +80,8 @@ namespace {
 void freeDeviceTable(PFAC_handle_t h) {
     cudaFree(h->d_root); h->d_root = nullptr;
     cudaFree(h->d_pre2); h->d_pre2 = nullptr;
+    cudaFree(h->d_rank2); h->d_rank2 = nullptr;
+    cudaFree(h->d_next2); h->d_next2 = nullptr;
     cudaFree(h->d_hot); h->d_hot = nullptr;
     cudaFree(h->d_cold); h->d_cold = nullptr;
     cudaFree(h->d_chains); h->d_chains = nullptr;
@@ -129,6 +133,13 @@ PFAC_status_t bindTable(PFAC_handle_t h) {
     PFAC_status_t st;
     if ((st = uploadArray(&h->d_root, L.root, sizeof(L.root))) != PFAC_STATUS_SUCCESS) return st;
     if ((st = uploadArray(&h->d_pre2, L.pre2.data(), L.pre2.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+    if ((st = uploadArray(&h->d_rank2, L.rank2.data(), L.rank2.size() * 2)) != PFAC_STATUS_SUCCESS) return st;
+    {   // next2 is copied to shared memory in 16-byte pieces: pad the upload
+        std::vector<uint32_t> padded(L.next2);
+        while (padded.size() & 3) padded.push_back(0xFFFFFFFFu);
+        if ((st = uploadArray(&h->d_next2, padded.data(), padded.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
+        h->table.next2Bytes = uint32_t(padded.size() * 4);
+    }
     if ((st = uploadArray(&h->d_hot, L.hot.data(), L.hot.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
     if ((st = uploadArray(&h->d_cold, L.cold.data(), L.cold.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
     if ((st = uploadArray(&h->d_chains, L.chains.data(), L.chains.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
@@ -138,6 +149,9 @@ PFAC_status_t bindTable(PFAC_handle_t h) {
     t.pre2 = static_cast<const uint32_t*>(h->d_pre2);
     t.hot = static_cast<const uint4*>(h->d_hot);
     t.cold = static_cast<const uint4*>(h->d_cold);
+    t.rank2 = static_cast<const unsigned short*>(h->d_rank2);
+    t.next2 = static_cast<const uint32_t*>(h->d_next2);
+    t.next2Hot = L.next2Hot;
     t.chains = static_cast<const uint4*>(h->d_chains);
     t.tails = static_cast<const unsigned char*>(h->d_tails);
     t.chainBytes = uint32_t(L.chains.size() * 4);
@@ -562,6 +576,7 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->num_chains = L.numChains;
     info->tail_bytes = int(L.tails.size());
     info->chains_hot = L.chainsHot ? 1 : 0;
+    info->next2_hot = L.next2Hot ? 1 : 0;
     info->max_depth = L.maxDepth;
     info->hot_depth = L.hotDepth;
     info->hot_buckets = L.hotBuckets;
@@ -624,11 +639,14 @@ PFAC_status_t PFAC_tableGetInfo(PFAC_table_t table, PFAC_tableInfo_t* info) {
 }
 
 PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int** root, const unsigned** pre2,
+                                  const unsigned short** rank2, const unsigned** next2,
                                   const unsigned** hot, const unsigned** cold, const unsigned** chains,
                                   const unsigned char** tails) {
     if (!table) return PFAC_STATUS_INVALID_HANDLE;
     if (root) *root = table->layout.root;
     if (pre2) *pre2 = table->layout.pre2.data();
+    if (rank2) *rank2 = table->layout.rank2.data();
+    if (next2) *next2 = table->layout.next2.data();
     if (hot) *hot = table->layout.hot.data();
     if (cold) *cold = table->layout.cold.data();
     if (chains) *chains = table->layout.chains.data();

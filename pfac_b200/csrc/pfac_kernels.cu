@@ -59,16 +59,21 @@ struct KParams {
     unsigned long long* total;
     const int32_t* root;
     const uint32_t* pre2;
+    const unsigned short* rank2;
+    const uint32_t* next2;
     const uint4* hot;
     const uint4* cold;
     const uint4* chains;
     const unsigned char* tails;
+    uint32_t next2_bytes;       // multiple of 16 (copied to smem when next2_hot)
     uint32_t hot_buckets;
     uint32_t cold_buckets;
     uint32_t chain_bytes;       // bytes of chain records (copied to smem when chains_hot)
     uint32_t tail_bytes;
     uint32_t mul;
+    uint32_t bulk_tiles;        // dense: tiles [0,bulk_tiles) are staged by TMA
     int hot_depth;
+    int next2_hot;
     int chains_hot;
     int num_final;
     int halo;                   // staged halo, multiple of 16, >= 16
@@ -80,6 +85,8 @@ struct KParams {
 struct Tables {
     const int* root;            // smem
     const uint32_t* pre2;       // smem
+    const unsigned short* rank2;  // smem
+    const uint32_t* next2;      // smem or global
     const uint4* hot;           // smem
     const uint4* cold;          // global
     const uint4* chains;        // smem or global
@@ -167,29 +174,41 @@ __device__ __forceinline__ uint32_t probe_cold(const uint4* __restrict__ tab, ui
     }
 }
 
-// copy the compiled tables into shared memory (whole CTA), returns the walker's view
-__device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* s_root, unsigned char* s_pre2,
-                                               unsigned char* s_var, int tid, int nthreads) {
-    int* root = reinterpret_cast<int*>(s_root);
-    uint4* pre2 = reinterpret_cast<uint4*>(s_pre2);
-    uint4* hot = reinterpret_cast<uint4*>(s_var);
+// copy the compiled tables into shared memory (whole CTA), returns the walker's view.
+// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB;  s_var: [next2][hot buckets][chains][tails]
+constexpr int kFixedTableBytes = 1024 + 8192 + 4096;
+__device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* s_fixed, unsigned char* s_var,
+                                               int tid, int nthreads) {
+    int* root = reinterpret_cast<int*>(s_fixed);
+    uint4* pre2 = reinterpret_cast<uint4*>(s_fixed + 1024);
+    uint4* rank2 = reinterpret_cast<uint4*>(s_fixed + 1024 + 8192);
     for (int i = tid; i < 256; i += nthreads) root[i] = p.root[i];
-    for (int i = tid; i < 2048 / 4; i += nthreads) pre2[i] = reinterpret_cast<const uint4*>(p.pre2)[i];
-    for (uint32_t i = tid; i < p.hot_buckets; i += nthreads) hot[i] = p.hot[i];
+    for (int i = tid; i < 8192 / 16; i += nthreads) pre2[i] = reinterpret_cast<const uint4*>(p.pre2)[i];
+    for (int i = tid; i < 4096 / 16; i += nthreads) rank2[i] = reinterpret_cast<const uint4*>(p.rank2)[i];
     Tables t;
     t.root = root;
-    t.pre2 = reinterpret_cast<const uint32_t*>(s_pre2);
-    t.hot = hot;
+    t.pre2 = reinterpret_cast<const uint32_t*>(pre2);
+    t.rank2 = reinterpret_cast<const unsigned short*>(rank2);
+    t.next2 = p.next2;
+    uint4* var = reinterpret_cast<uint4*>(s_var);
+    if (p.next2_hot) {
+        for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
+            var[i] = reinterpret_cast<const uint4*>(p.next2)[i];
+        t.next2 = reinterpret_cast<const uint32_t*>(var);
+        var += p.next2_bytes / 16;
+    }
+    for (uint32_t i = tid; i < p.hot_buckets; i += nthreads) var[i] = p.hot[i];
+    t.hot = var;
+    var += p.hot_buckets;
     t.cold = p.cold;
     t.chains = p.chains;
     t.tails = p.tails;
     if (p.chains_hot) {
-        uint4* sc = hot + p.hot_buckets;
-        uint4* st = sc + p.chain_bytes / 16;
-        for (uint32_t i = tid; i < p.chain_bytes / 16; i += nthreads) sc[i] = p.chains[i];
+        uint4* st = var + p.chain_bytes / 16;
+        for (uint32_t i = tid; i < p.chain_bytes / 16; i += nthreads) var[i] = p.chains[i];
         for (uint32_t i = tid; i < p.tail_bytes / 16; i += nthreads)
             st[i] = reinterpret_cast<const uint4*>(p.tails)[i];
-        t.chains = sc;
+        t.chains = var;
         t.tails = reinterpret_cast<const unsigned char*>(st);
     }
     t.hot_buckets = p.hot_buckets;
@@ -214,8 +233,9 @@ __device__ __forceinline__ uint32_t prefilter16(const unsigned char* inb, int lb
         for (int j = 3; j >= 0; j--) {
             const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
             const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
-            // wanted bit (x & 31) -> bit 31, then shift it into cand from the right
-            const uint32_t t = word << ((~x) & 31u);
+            // the table stores bit idx at position 31-(idx&31): one shift brings it to bit 31,
+            // one funnel shift moves it into cand from the right
+            const uint32_t t = word << (x & 31u);
             cand = __funnelshift_l(t, cand, 1);
         }
     }
@@ -244,18 +264,31 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, int lb, unsigned sh
 // Walk the queued survivors of one warp.  inb: staged text of the tile (stage_bytes bytes,
 // local position 0 = first byte), gin: the same bytes in global memory (for walks that run past
 // the staged halo), tile_rem: real input bytes from local position 0 to the end of the input.
-// DENSE: wres[local position - res_base] = id (non-zero only); else wres[queue slot] = id.
+// DENSE: wres[local position] = id (non-zero only); else wres[queue slot] = id.
+//
+// Per survivor: root row (is c0 alone a match?) -> next2[rank of (c0,c1)] (the walk after two
+// bytes, no hashing) -> then per step either a chain (tail compared 4 bytes at a time) or a
+// hash probe (hot rows in shared memory below hot_depth, cold rows through L1/L2).
 template <bool DENSE>
 __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
                                            const unsigned char* __restrict__ gin, int tile_rem,
-                                           const unsigned short* q16, int wtotal, int* wres, int res_base,
-                                           int lane) {
+                                           const unsigned short* q16, int wtotal, int* wres, int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
     int head = 0;
     bool active = false;
     int pl = 0, d = 0, limit = 0, best = 0, slot = 0;
-    uint32_t s = 0;
+    uint32_t v = kEmpty;
     auto text_byte = [&](int at) -> uint32_t { return (at < stage_bytes) ? inb[at] : gin[at]; };
+    // n (1..4) text bytes from `at`, little-endian, possibly with junk above byte n-1
+    auto text_word = [&](int at, int n) -> uint32_t {
+        if (at + 4 <= stage_bytes) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(inb + (at & ~3));
+            return __funnelshift_r(w[0], w[1], (at & 3) * 8);
+        }
+        uint32_t x = 0;
+        for (int k = 0; k < n; k++) x |= text_byte(at + k) << (8 * k);
+        return x;
+    };
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !active);
         if (need) {
@@ -263,55 +296,71 @@ __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char*
             if (!active && my < wtotal) {
                 slot = my;
                 pl = q16[my];
-                s = static_cast<uint32_t>(T.root[inb[pl]]);
-                best = (static_cast<int>(s) <= T.num_final) ? static_cast<int>(s) : 0;
+                const uint32_t c0 = inb[pl], c1 = inb[pl + 1];  // pl+1 is always staged (halo >= 16)
+                const int r = T.root[c0];                        // valid: the prefilter bit is set
+                best = (r <= T.num_final) ? r : 0;
+                limit = tile_rem - pl;                           // real input bytes from this position
+                v = kEmpty;
+                if (limit >= 2) {
+                    const uint32_t idx = c0 | (c1 << 8);
+                    const uint32_t word = T.pre2[idx >> 5];
+                    const uint32_t before = __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
+                    v = T.next2[T.rank2[idx >> 5] + before];
+                }
                 d = 1;
-                limit = tile_rem - pl;  // bytes of real input from this position
                 active = true;
             }
             head += __popc(need);
         }
         if (!__any_sync(0xffffffffu, active)) break;
         if (active) {
-            bool done = (d >= limit) || (static_cast<int>(s) < 0);
-            if (!done) {
-                const uint32_t key = (s << 8) | text_byte(pl + d);
-                const uint32_t v = (d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
-                                                     : probe_cold(T.cold, T.cold_buckets, T.mul, key);
-                if (v == kEmpty) {
-                    done = true;
-                } else if (v & kChainBit) {
-                    // compressed run: rec = {tail offset, len, end state | leaf, first 4 bytes}
-                    const uint4 rec = T.chains[v & ~kChainBit];
-                    const int len = static_cast<int>(rec.y);
-                    if (d + 1 + len > limit) {
-                        done = true;  // cut off by the end of the input: nothing more to report
-                    } else {
-                        const int at0 = pl + d + 1;
-                        uint32_t tw = rec.w;
-                        bool ok = true;
-                        for (int i = 0; i < len; i++) {
-                            if (i >= 4 && (i & 3) == 0) tw = *reinterpret_cast<const uint32_t*>(T.tails + rec.x + i);
-                            if (text_byte(at0 + i) != ((tw >> (8 * (i & 3))) & 0xFFu)) { ok = false; break; }
-                        }
-                        if (!ok) {
-                            done = true;
-                        } else {
-                            s = rec.z & ~kChainBit;
-                            d += 1 + len;
-                            if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
-                            if (rec.z & kChainBit) done = true;  // leaf: no out-edges
-                        }
-                    }
+            // v = the transition out of depth d (d bytes consumed): trap, chain or plain state
+            bool done = false;
+            uint32_t s = 0;
+            if (v == kEmpty) {
+                done = true;
+            } else if (v & kChainBit) {
+                const uint4 rec = T.chains[v & ~kChainBit];  // {tail offset, len, end|leaf, first 4 bytes}
+                const int len = static_cast<int>(rec.y);
+                if (d + 1 + len > limit) {
+                    done = true;  // cut off by the end of the input: nothing more to report
                 } else {
-                    s = v;
-                    if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
-                    d++;
+                    const int at0 = pl + d + 1;
+                    uint32_t tw = rec.w;
+                    int i = 0;
+                    for (;;) {
+                        const int n = len - i;
+                        const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
+                        if ((text_word(at0 + i, n) ^ tw) & mask) { done = true; break; }
+                        i += 4;
+                        if (i >= len) break;
+                        tw = *reinterpret_cast<const uint32_t*>(T.tails + rec.x + i);
+                    }
+                    if (!done) {
+                        s = rec.z & ~kChainBit;
+                        d += 1 + len;
+                        if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                        if (rec.z & kChainBit) done = true;  // leaf: no out-edges
+                    }
+                }
+            } else {
+                s = v;
+                if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                d++;
+            }
+            if (!done) {
+                if (d >= limit) {
+                    done = true;
+                } else {
+                    const uint32_t key = (s << 8) | text_byte(pl + d);
+                    v = (d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
+                                          : probe_cold(T.cold, T.cold_buckets, T.mul, key);
+                    if (v == kEmpty) done = true;
                 }
             }
             if (done) {
                 if (DENSE) {
-                    if (best) wres[pl - res_base] = best;
+                    if (best) wres[pl] = best;
                 } else {
                     wres[slot] = best;
                 }
@@ -323,9 +372,21 @@ __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char*
 
 // =================================================================================================
 // Dense kernel: one persistent CTA of 32 autonomous warps per SM.
-// shared memory: [mbarriers 32*NSTAGE*8][root 1K][pre2 8K][per warp: queue 1K | res 2K | NSTAGE
-// input stages][hot buckets][chains][tails]
+// shared memory: [mbarriers 32*NSTAGE*8][root 1K | pre2 8K | rank2 4K][per warp: queue 1K | res 2K |
+// NSTAGE input stages][next2][hot buckets][chains][tails]
 // =================================================================================================
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 template <int NSTAGE>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -333,16 +394,16 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
     const int per_warp = kWarpTile * 2 + kWarpTile * 4 + NSTAGE * stage;
     constexpr int kBarBytes = ((kDenseWarps * NSTAGE * 8 + 127) / 128) * 128;
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
-    unsigned char* s_root = smem + kBarBytes;
-    unsigned char* s_pre2 = s_root + 1024;
-    unsigned char* s_warp = s_pre2 + 8192;
+    unsigned char* s_fixed = smem + kBarBytes;
+    unsigned char* s_warp = s_fixed + kFixedTableBytes;
     unsigned char* s_var = s_warp + kDenseWarps * per_warp;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
+    // warp-uniform by construction, so addresses derived from it can live in uniform registers
+    const uint32_t warp = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tid) >> 5, 0);
 
-    const Tables T = stage_tables(p, s_root, s_pre2, s_var, tid, kDenseThreads);
+    const Tables T = stage_tables(p, s_fixed, s_var, tid, kDenseThreads);
     unsigned long long* bar = s_bar + warp * NSTAGE;
     if (lane == 0) {
         for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
@@ -355,49 +416,50 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
     int* wres = reinterpret_cast<int*>(mine + kWarpTile * 2);
     unsigned char* s_in = mine + kWarpTile * 2 + kWarpTile * 4;
 
-    // warp tile of iteration `it`: consecutive warps of a CTA take consecutive 512-byte tiles
-    auto tile_of = [&](long long it) -> long long {
-        return (it * gridDim.x + blockIdx.x) * kDenseWarps + warp;
-    };
-    auto tile_is_bulk = [&](long long t) -> bool {
-        return p.in_aligned && (t * kWarpTile + stage <= p.n_total);
-    };
-    auto issue_load = [&](long long t, int st) {  // lane 0 only
-        if (t < p.num_tiles && tile_is_bulk(t)) {
+    // consecutive warps of a CTA take consecutive 512-byte tiles; tiles advance by the grid
+    const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
+    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kWarpTile);  // tiles with 512 owned positions
+    const uint32_t tstride = gridDim.x * kDenseWarps;
+    uint32_t tile = blockIdx.x * kDenseWarps + warp;
+
+    auto issue_load = [&](uint32_t t, int st) {  // one elected lane; tiles beyond bulk_tiles are copied at use
+        if (t < p.bulk_tiles) {
             mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
-            tma_load_1d(s_in + st * stage, p.in + t * kWarpTile, static_cast<uint32_t>(stage), &bar[st]);
+            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kWarpTile, static_cast<uint32_t>(stage),
+                        &bar[st]);
         }
     };
 
-    if (lane == 0)
-        for (int i = 0; i < NSTAGE; i++) issue_load(tile_of(i), i);
+    if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < NSTAGE; i++) issue_load(tile + i * tstride, i);
+    }
 
     uint32_t parity = 0u;  // bit s = phase of bar[s]
     int st = 0;
-    for (long long it = 0;; ++it) {
-        const long long tile = tile_of(it);
-        if (tile >= p.num_tiles) break;
+    for (; tile < num_tiles; tile += tstride) {
         unsigned char* inb = s_in + st * stage;
-        const long long start = tile * kWarpTile;
-        if (tile_is_bulk(tile)) {
+        const size_t start = static_cast<size_t>(tile) * kWarpTile;
+        if (tile < p.bulk_tiles) {
             mbar_wait(&bar[st], (parity >> st) & 1u);
             parity ^= 1u << st;
         } else {
             // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
             for (int i = lane; i < stage; i += 32) {
-                const long long g = start + i;
+                const long long g = static_cast<long long>(start) + i;
                 inb[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
             }
             __syncwarp();
         }
-        const long long owned_left = p.n_owned - start;  // > 0
-        const int valid = owned_left < kWarpTile ? static_cast<int>(owned_left) : kWarpTile;
-        const long long total_left = p.n_total - start;
+        const long long total_left = p.n_total - static_cast<long long>(start);
         const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
+        const bool full = tile < full_tiles;
 
         const int lb = lane * kPosPerThread;
         uint32_t cand = prefilter16(inb, lb, T.pre2);
-        if (valid < kWarpTile) {  // tail tile: drop positions we do not own
+        int valid = kWarpTile;
+        if (!full) {  // tail tile: drop positions we do not own
+            valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
             int nv = valid - lb;
             nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
             cand &= (1u << nv) - 1u;
@@ -405,47 +467,46 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
         const int wtotal = push_survivors(cand, lb, q16, lane);
 
         // the previous bulk store of this warp must have finished reading wres
-        if (lane == 0) tma_store_wait_read();
+        if (elect_one()) tma_store_wait_read();
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(wres)[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
 
-        walk_queue<true>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, 0, lane);
+        walk_queue<true>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane);
 
         int* gout = p.out + start;
-        if (p.out_aligned && valid == kWarpTile) {
+        if (p.out_aligned && full) {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
                 tma_store_1d(gout, wres, kWarpTile * 4);
                 tma_store_commit();
-                issue_load(tile_of(it + NSTAGE), st);  // every lane is done with this stage
+                issue_load(tile + NSTAGE * tstride, st);  // every lane is done with this stage
             }
         } else {
             __syncwarp();
             for (int i = lane; i < valid; i += 32) gout[i] = wres[i];
             __syncwarp();
-            if (lane == 0) issue_load(tile_of(it + NSTAGE), st);
+            if (elect_one()) issue_load(tile + NSTAGE * tstride, st);
         }
         st = (st + 1 == NSTAGE) ? 0 : st + 1;
     }
-    if (lane == 0) tma_store_wait_all();  // shared memory must outlive the bulk stores
+    if (elect_one()) tma_store_wait_all();  // shared memory must outlive the bulk stores
 }
 
 // =================================================================================================
 // Reduce kernel: 256-thread CTAs, 4096-position tiles handed out by a global ticket counter.
-// shared memory: [bars 16][base 8][misc][root 1K][pre2 8K][queue 8K][ids 16K][2 input stages]
-// [hot][chains][tails]
+// shared memory: [bars 16][base 8][misc][root 1K | pre2 8K | rank2 4K][queue 8K][ids 16K]
+// [2 input stages][next2][hot][chains][tails]
 // =================================================================================================
 constexpr int kROffBar = 0;        // 2 x uint64 mbarrier
 constexpr int kROffBase = 16;      // uint64 tile base
 constexpr int kROffWcount = 32;    // int[8]
 constexpr int kROffWoff = 64;      // int[8]
 constexpr int kROffTicket = 96;    // long long[2]
-constexpr int kROffRoot = 128;
-constexpr int kROffPre2 = kROffRoot + 1024;
-constexpr int kROffQueue = kROffPre2 + 8192;
+constexpr int kROffFixed = 128;    // root | pre2 | rank2
+constexpr int kROffQueue = kROffFixed + kFixedTableBytes;
 constexpr int kROffIds = kROffQueue + kRedWarps * kWarpTile * 2;
 constexpr int kROffIn = kROffIds + kRedTile * 4;
 
@@ -467,7 +528,7 @@ __global__ void __launch_bounds__(kRedThreads) pfac_reduce_kernel(const KParams 
     const int warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    const Tables T = stage_tables(p, smem + kROffRoot, smem + kROffPre2, smem + kROffIn + 2 * stage, tid, kRedThreads);
+    const Tables T = stage_tables(p, smem + kROffFixed, smem + kROffIn + 2 * stage, tid, kRedThreads);
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -538,7 +599,7 @@ __global__ void __launch_bounds__(kRedThreads) pfac_reduce_kernel(const KParams 
         }
         const int wtotal = push_survivors(cand, lb, q16, lane);
         __syncwarp();
-        walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, 0, lane);
+        walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane);
         __syncwarp();
 
         // ---- ordered compaction: warp count -> CTA scan -> look-back -> write pairs -----------
@@ -625,11 +686,13 @@ int denseStages(int halo) { return halo > 256 ? 2 : 3; }
 size_t denseFixedBytes(int halo) {
     const int nst = denseStages(halo);
     const size_t bar = size_t((kDenseWarps * nst * 8 + 127) / 128) * 128;
-    return bar + 1024 + 8192 + size_t(kDenseWarps) * (kWarpTile * 2 + kWarpTile * 4 + nst * (kWarpTile + halo));
+    return bar + kFixedTableBytes +
+           size_t(kDenseWarps) * (kWarpTile * 2 + kWarpTile * 4 + nst * (kWarpTile + halo));
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
-    return size_t(t.hotBuckets) * 16 + (t.chainsHot ? size_t(t.chainBytes) + t.tailBytes : 0);
+    return (t.next2Hot ? size_t(t.next2Bytes) : 0) + size_t(t.hotBuckets) * 16 +
+           (t.chainsHot ? size_t(t.chainBytes) + t.tailBytes : 0);
 }
 
 KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned, size_t n_total, int halo,
@@ -641,6 +704,10 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
     p.num_tiles = ((long long)n_owned + tileSize - 1) / tileSize;
     p.root = t.root;
     p.pre2 = t.pre2;
+    p.rank2 = t.rank2;
+    p.next2 = t.next2;
+    p.next2_bytes = t.next2Bytes;
+    p.next2_hot = t.next2Hot ? 1 : 0;
     p.hot = t.hot;
     p.cold = t.cold;
     p.chains = t.chains;
@@ -674,8 +741,16 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
     if (n_owned == 0) return cudaSuccess;
     const int halo = roundHalo(t.maxPatternLen, kDenseMaxHalo);
     KParams p = baseParams(t, in, n_owned, n_total, halo, kWarpTile);
+    if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;  // 1 TiB per launch
     p.out = out;
     p.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    {   // tile t is staged by TMA iff the pointer is 16-byte aligned and t*512 + stage <= n_total
+        const long long stage = kWarpTile + halo;
+        long long bulk = 0;
+        if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kWarpTile + 1;
+        if (bulk > p.num_tiles) bulk = p.num_tiles;
+        p.bulk_tiles = static_cast<uint32_t>(bulk);
+    }
     const size_t smem = denseFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const int nst = denseStages(halo);

@@ -11,6 +11,10 @@ namespace pfac {
 struct DeviceTable {
     const int32_t* root = nullptr;    // 256
     const uint32_t* pre2 = nullptr;   // 2048
+    const unsigned short* rank2 = nullptr;  // 2048
+    const uint32_t* next2 = nullptr;  // next2Bytes / 4 (padded to 16 bytes)
+    uint32_t next2Bytes = 0;
+    bool next2Hot = false;            // kernels copy next2 into shared memory
     const uint4* hot = nullptr;       // hotBuckets (copied into shared memory by each CTA)
     const uint4* cold = nullptr;      // coldBuckets (read through L1/L2)
     const uint4* chains = nullptr;    // chain records (16 B each)

@@ -231,27 +231,26 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     }
     auto isFinal = [&](int s) { return s >= 1 && s <= m.numFinal; };
 
-    // ---- root row + prefilter.  Bit (c0 | c1<<8) is set iff a walk starting with c0,c1 can
+    // ---- root row + prefilter.  Bit idx = c0 | c1<<8 is set iff a walk starting with c0,c1 can
     // produce a result: root[c0] is a final state (1-byte pattern: any c1), or (root[c0], c1) is
     // an edge.  Clear bit => result 0 with certainty; set bit => the walker decides.
+    auto setBit = [&](uint32_t idx) { L.pre2[idx >> 5] |= 0x80000000u >> (idx & 31); };
+    auto getBit = [&](uint32_t idx) { return (L.pre2[idx >> 5] << (idx & 31)) >> 31; };
     if (!frontier.empty()) {
         for (const Edge& e : out[size_t(m.initialState)]) {
             L.root[e.ch] = e.next;
             L.rootFanout++;
             const uint32_t c0 = uint32_t(e.ch);
-            if (isFinal(e.next)) {
-                for (uint32_t c1 = 0; c1 < 256; c1++) {
-                    const uint32_t idx = c0 | (c1 << 8);
-                    L.pre2[idx >> 5] |= 1u << (idx & 31);
-                }
-            }
-            for (const Edge& e2 : out[size_t(e.next)]) {
-                const uint32_t idx = c0 | (uint32_t(e2.ch) << 8);
-                L.pre2[idx >> 5] |= 1u << (idx & 31);
-            }
+            if (isFinal(e.next))
+                for (uint32_t c1 = 0; c1 < 256; c1++) setBit(c0 | (c1 << 8));
+            for (const Edge& e2 : out[size_t(e.next)]) setBit(c0 | (uint32_t(e2.ch) << 8));
         }
     }
-    for (uint32_t w : L.pre2) L.pre2BitsSet += __builtin_popcount(w);
+    L.rank2.assign(2048, 0);
+    for (size_t w = 0; w < 2048; w++) {
+        L.rank2[w] = uint16_t(L.pre2BitsSet);  // <= 65504 for every word but the sum itself
+        L.pre2BitsSet += __builtin_popcount(L.pre2[w]);
+    }
 
     // ---- hash edges with chain compression.  From every lookup source (root children, plain
     // edge targets, chain ends) follow each out-edge; a run of >= kMinChain non-final
@@ -260,47 +259,62 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     std::vector<FlatEdge> edges;
     std::vector<char> queued(S, 0);
     std::vector<int> sources;
-    if (!frontier.empty())
-        for (const Edge& e : out[size_t(m.initialState)])
-            if (!queued[size_t(e.next)]) { queued[size_t(e.next)] = 1; sources.push_back(e.next); }
     std::vector<uint8_t> tail;
-    for (size_t qi = 0; qi < sources.size(); qi++) {
-        const int s = sources[qi];
-        for (const Edge& e : out[size_t(s)]) {
-            int cur = e.next;
-            tail.clear();
-            while (!isFinal(cur) && out[size_t(cur)].size() == 1) {
-                tail.push_back(uint8_t(out[size_t(cur)][0].ch));
-                cur = out[size_t(cur)][0].next;
+    // follow the edge s -ch-> e.next: returns the value to store (state or chain reference) and
+    // queues the state the walk stands in afterwards when it has out-edges of its own
+    auto compress = [&](const Edge& e) -> uint32_t {
+        int cur = e.next;
+        tail.clear();
+        while (!isFinal(cur) && out[size_t(cur)].size() == 1) {
+            tail.push_back(uint8_t(out[size_t(cur)][0].ch));
+            cur = out[size_t(cur)][0].next;
+        }
+        uint32_t val;
+        int target;
+        if (int(tail.size()) >= kMinChain) {
+            const uint32_t idx = uint32_t(L.numChains++);
+            const uint32_t off = uint32_t(L.tails.size());
+            uint32_t inline4 = 0;
+            for (size_t b = 0; b < tail.size(); b++) {
+                L.tails.push_back(tail[b]);
+                if (b < 4) inline4 |= uint32_t(tail[b]) << (8 * b);
             }
-            uint32_t val;
-            int target;
-            if (int(tail.size()) >= kMinChain) {
-                const uint32_t idx = uint32_t(L.numChains++);
-                const uint32_t off = uint32_t(L.tails.size());
-                uint32_t inline4 = 0;
-                for (size_t b = 0; b < tail.size(); b++) {
-                    L.tails.push_back(tail[b]);
-                    if (b < 4) inline4 |= uint32_t(tail[b]) << (8 * b);
-                }
-                while (L.tails.size() & 3) L.tails.push_back(0);
-                const bool leaf = out[size_t(cur)].empty();
-                L.chains.push_back(off);
-                L.chains.push_back(uint32_t(tail.size()));
-                L.chains.push_back(uint32_t(cur) | (leaf ? kLeafFlag : 0u));
-                L.chains.push_back(inline4);
-                val = kChainFlag | idx;
-                target = cur;
-            } else {
-                val = uint32_t(e.next);
-                target = e.next;
-            }
-            edges.push_back(FlatEdge{edgeKey(s, e.ch), int(val), depth[size_t(s)]});
-            if (!out[size_t(target)].empty() && !queued[size_t(target)]) {
-                queued[size_t(target)] = 1;
-                sources.push_back(target);
+            while (L.tails.size() & 3) L.tails.push_back(0);
+            const bool leaf = out[size_t(cur)].empty();
+            L.chains.push_back(off);
+            L.chains.push_back(uint32_t(tail.size()));
+            L.chains.push_back(uint32_t(cur) | (leaf ? kLeafFlag : 0u));
+            L.chains.push_back(inline4);
+            val = kChainFlag | idx;
+            target = cur;
+        } else {
+            val = uint32_t(e.next);
+            target = e.next;
+        }
+        if (!out[size_t(target)].empty() && !queued[size_t(target)]) {
+            queued[size_t(target)] = 1;
+            sources.push_back(target);
+        }
+        return val;
+    };
+    // depth-1 transitions: direct-indexed through the prefilter's rank (no hashing)
+    L.next2.assign(size_t(std::max(L.pre2BitsSet, 1)), kTrap);
+    if (!frontier.empty()) {
+        for (const Edge& e : out[size_t(m.initialState)]) {
+            for (const Edge& e2 : out[size_t(e.next)]) {
+                const uint32_t idx = uint32_t(e.ch) | (uint32_t(e2.ch) << 8);
+                const uint32_t w = idx >> 5, b = idx & 31;
+                const uint32_t before = b ? uint32_t(__builtin_popcount(L.pre2[w] >> (32 - b))) : 0u;
+                L.next2[size_t(L.rank2[w]) + before] = compress(e2);
             }
         }
+    }
+    (void)getBit;
+    // deeper transitions: hash rows
+    for (size_t qi = 0; qi < sources.size(); qi++) {
+        const int s = sources[qi];
+        for (const Edge& e : out[size_t(s)])
+            edges.push_back(FlatEdge{edgeKey(s, e.ch), int(compress(e)), depth[size_t(s)]});
     }
     L.hashEdges = int(edges.size());
     while (L.tails.size() & 15) L.tails.push_back(0);
@@ -313,14 +327,23 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     std::vector<size_t> upto(size_t(L.maxDepth) + 2, 0);  // upto[d] = #edges with depth < d
     for (const FlatEdge& e : edges) upto[size_t(e.depth) + 1]++;
     for (size_t d = 1; d < upto.size(); d++) upto[d] += upto[d - 1];
+    // shared-memory budget: next2 first (touched by every survivor), then hash rows by depth,
+    // and chains + tails too when everything fits
+    const size_t next2Bytes = ((L.next2.size() * 4 + 15) / 16) * 16;
+    if (next2Bytes <= hotBudgetBytes) {
+        L.next2Hot = true;
+        hotBudgetBytes -= next2Bytes;
+    } else {
+        hotBudgetBytes = 0;  // deeper rows are colder than next2: keep them all in L2 as well
+    }
     const size_t chainBytes = L.chains.size() * 4 + L.tails.size();
     int H = 1;
-    if (!edges.empty() && edges.size() * 16 + chainBytes <= hotBudgetBytes) {
+    if (L.next2Hot && edges.size() * 16 + chainBytes <= hotBudgetBytes) {
         H = int(upto.size()) - 1;      // everything in shared memory, chains and tails too
         L.chainsHot = true;
     } else {
         const size_t hotSlots = hotBudgetBytes / 16;
-        for (int d = 2; d < int(upto.size()); d++) {  // upto[] is non-decreasing, upto[1] == 0
+        for (int d = 2; d < int(upto.size()); d++) {  // upto[] is non-decreasing
             if (upto[size_t(d)] <= hotSlots) H = d;
             else break;
         }

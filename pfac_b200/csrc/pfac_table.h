@@ -57,10 +57,21 @@ constexpr uint32_t kChainFlag = 0x80000000u;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr int kMinChain = 2;          // compress runs of at least this many single-child states
 
+//   pre2 / rank2 / next2: the first two bytes need no hashing.  pre2 is a 65536-bit set over
+//     idx = c0 | c1<<8, stored bit-reversed inside each 32-bit word (idx -> word idx>>5, bit
+//     31-(idx&31)) so that `word << (idx&31)` moves the wanted bit to the sign position.
+//     rank2[w] = number of set bits in words [0,w); next2[rank] = what the walk holds after
+//     consuming c0,c1: a state, kChainFlag|chain index, or kTrap when the bit is only set
+//     because root[c0] is final (1-byte pattern) and (root[c0],c1) is not an edge.
+constexpr uint32_t kTrap = 0xFFFFFFFFu;
+
 struct DeviceLayout {
     int32_t root[kCharSet];          // next state from the initial state, -1 = trap
-    std::vector<uint32_t> pre2;      // 65536-bit prefilter, index c0 | c1<<8
-    std::vector<uint32_t> hot;       // edges with source depth in [1,hotDepth)  -> smem
+    std::vector<uint32_t> pre2;      // 2048 words, bit-reversed within each word
+    std::vector<uint16_t> rank2;     // 2048 prefix popcounts
+    std::vector<uint32_t> next2;     // one entry per set bit, in idx order
+    bool next2Hot = false;           // next2 fits the shared-memory budget
+    std::vector<uint32_t> hot;       // edges with source depth in [2,hotDepth)  -> smem
     std::vector<uint32_t> cold;      // edges with source depth >= hotDepth      -> global/L2
     std::vector<uint32_t> chains;    // 4 words per chain record
     std::vector<uint8_t> tails;      // chain tail bytes, each tail padded to 4
@@ -76,8 +87,8 @@ struct DeviceLayout {
     int pre2BitsSet = 0;
     int rootFanout = 0;
     size_t deviceBytes() const {
-        return sizeof(root) + pre2.size() * 4 + hot.size() * 4 + cold.size() * 4 + chains.size() * 4 +
-               tails.size();
+        return sizeof(root) + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 + hot.size() * 4 +
+               cold.size() * 4 + chains.size() * 4 + tails.size();
     }
 };
 

@@ -21,17 +21,20 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None):
     c0 = int(text[start])
     c1 = int(text[start + 1]) if avail >= 2 else 0
     idx = c0 | (c1 << 8)
-    if not (int(L["pre2"][idx >> 5]) >> (idx & 31)) & 1:
+    word = int(L["pre2"][idx >> 5])
+    b = idx & 31
+    if not ((word << b) >> 31) & 1:           # bit 31-(idx&31) of the word
         return 0
     s = int(L["root"][c0])
     assert s >= 0, "prefilter bit set but root row traps"
     best = s if s <= num_final else 0
+    if avail < 2:
+        return best                            # c1 was padding: only the 1-byte result counts
+    rank = int(L["rank2"][idx >> 5]) + (bin(word >> (32 - b)).count("1") if b else 0)
+    v = int(L["next2"][rank])                  # the walk after consuming c0, c1
     d = 1
-    while d < avail:
-        key = ((s << 8) | int(text[start + d])) & 0xFFFFFFFF
-        tab = L["hot"] if d < L["hot_depth"] else L["cold"]
-        v = probe(tab, L["mul"], key)
-        if v < 0:
+    while True:
+        if v == 0xFFFFFFFF:
             break
         if v & 0x80000000:
             off, ln, end, inline4 = (int(x) for x in L["chains"][v & 0x7FFFFFFF])
@@ -52,6 +55,13 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None):
             if s <= num_final:
                 best = s
             d += 1
+        if d >= avail:
+            break
+        key = ((s << 8) | int(text[start + d])) & 0xFFFFFFFF
+        tab = L["hot"] if d < L["hot_depth"] else L["cold"]
+        v = probe(tab, L["mul"], key)
+        if v < 0:
+            break
     return best
 
 

@@ -45,7 +45,7 @@ def test_info_readme_example(golden_dir):
     info = TableCompiler(os.path.join(golden_dir, "example_pattern")).info()
     assert (info["num_patterns"], info["num_states"], info["initial_state"], info["max_pattern_len"]) == (4, 11, 5, 4)
     assert info["num_leaves"] == 3 and info["num_edges"] == 9 and info["root_fanout"] == 3
-    assert info["num_chains"] == 1 and info["hash_edges"] == 4  # B-E-(D-E) is the only run >= 2
+    assert info["num_chains"] == 1 and info["hash_edges"] == 1  # B-E-(D-E) is the only run >= 2; (1,G)->2 hashed
     assert info["pre2_bits_set"] == 3  # AB, BE, ED
 
 
@@ -69,7 +69,9 @@ def test_layout_walk_equals_oracle(golden_dir, case, hot_kb):
         assert info["hot_depth"] == 1 and info["hot_buckets"] == 0 and not info["chains_hot"]
     if hot_kb == 512:
         assert info["hot_depth"] == info["max_depth"] + 1 and info["chains_hot"]  # everything fits
-        assert info["hot_buckets"] == info["hash_edges"]
+        assert info["hot_buckets"] == info["hash_edges"] and info["next2_hot"]
+    if hot_kb == 0:
+        assert not info["next2_hot"]
     assert info["num_chains"] > 0 and info["hash_edges"] < info["num_edges"]
     got = np.array([emulate_layout_walk(L, o.num_patterns, text, i) for i in range(n)], dtype=np.int32)
     bad = np.flatnonzero(got != want)
@@ -85,19 +87,32 @@ def test_layout_root_and_prefilter_against_dense_table(golden_dir):
     root, pre2, hot, cold = L["root"], L["pre2"], L["hot"], L["cold"]
     init, k = o.initial_state, o.num_patterns
     assert np.array_equal(root, T[init])
-    bits = np.unpackbits(pre2.view(np.uint8), bitorder="little").reshape(256, 256)  # [c1][c0]
-    for c0 in range(256):
-        s = T[init, c0]
-        for c1 in range(256):
+    nset = 0
+    for c1 in range(256):
+        for c0 in range(256):
+            s = T[init, c0]
+            idx = c0 | (c1 << 8)
+            bit = (int(pre2[idx >> 5]) << (idx & 31) >> 31) & 1
             expect = s >= 0 and (s <= k or T[s, c1] >= 0)
-            assert bool(bits[c1, c0]) == bool(expect), (c0, c1)
+            assert bool(bit) == bool(expect), (c0, c1)
+            if bit:  # next2 is indexed by the rank of the bit, in idx order
+                if (idx & 31) == 0:
+                    assert int(L["rank2"][idx >> 5]) == nset
+                v = int(L["next2"][nset])
+                if T[s, c1] < 0:
+                    assert v == 0xFFFFFFFF
+                elif not (v & 0x80000000):
+                    assert v == T[s, c1]
+                nset += 1
+    assert nset == tc.info()["pre2_bits_set"]
     # every hash entry is unique; chain compression accounts for the missing transitions
     info = tc.info()
     keys = np.concatenate([hot[:, 0], hot[:, 2], cold[:, 0], cold[:, 2]])
     keys = keys[keys != 0xFFFFFFFF]
     assert keys.size == np.unique(keys).size == info["hash_edges"]
     chain_len = int(L["chains"][:info["num_chains"], 1].sum())
-    assert info["num_edges"] == info["root_fanout"] + info["hash_edges"] + chain_len
+    depth1 = int((L["next2"] != 0xFFFFFFFF).sum())  # (root child, c1) edges live in next2
+    assert info["num_edges"] == info["root_fanout"] + depth1 + info["hash_edges"] + chain_len
 
 
 def test_duplicates_prefixes_and_one_byte_patterns():
