@@ -55,16 +55,12 @@ struct PFAC_context {
     char patternFile[kFilenameLen] = {0};
 
     pfac::Machine machine;
-    pfac::DeviceLayout layout;
+    // one compiled layout per kernel: they differ only in the hot/cold split (smem budgets differ)
+    pfac::DeviceLayout layout;        // dense kernel
+    pfac::DeviceLayout layoutReduce;  // reduce kernel
     pfac::DeviceTable table;
-    void* d_root = nullptr;
-    void* d_pre2 = nullptr;
-    void* d_rank2 = nullptr;
-    void* d_next2 = nullptr;
-    void* d_hot = nullptr;
-    void* d_cold = nullptr;
-    void* d_chains = nullptr;
-    void* d_tails = nullptr;
+    pfac::DeviceTable tableReduce;
+    std::vector<void*> d_arrays;      // every device array of both tables
 
     std::mutex pipeMu;  // held for a whole matchFromHost* call (host pipeline buffers)
     std::mutex mu;      // guards the reduce workspace (several host threads may share a handle)
@@ -78,21 +74,17 @@ struct PFAC_context {
 namespace {
 
 void freeDeviceTable(PFAC_handle_t h) {
-    cudaFree(h->d_root); h->d_root = nullptr;
-    cudaFree(h->d_pre2); h->d_pre2 = nullptr;
-    cudaFree(h->d_rank2); h->d_rank2 = nullptr;
-    cudaFree(h->d_next2); h->d_next2 = nullptr;
-    cudaFree(h->d_hot); h->d_hot = nullptr;
-    cudaFree(h->d_cold); h->d_cold = nullptr;
-    cudaFree(h->d_chains); h->d_chains = nullptr;
-    cudaFree(h->d_tails); h->d_tails = nullptr;
+    for (void* p : h->d_arrays) cudaFree(p);
+    h->d_arrays.clear();
     h->table = pfac::DeviceTable();
+    h->tableReduce = pfac::DeviceTable();
 }
 
 void freePatterns(PFAC_handle_t h) {  // reference PFAC_freeResource, PFAC.cpp:221-296
     freeDeviceTable(h);
     h->machine = pfac::Machine();
     h->layout = pfac::DeviceLayout();
+    h->layoutReduce = pfac::DeviceLayout();
     h->patternsReady = false;
 }
 
@@ -107,53 +99,44 @@ void freePipe(HostPipe& p) {
     p = HostPipe();
 }
 
-PFAC_status_t uploadArray(void** dst, const void* src, size_t bytes) {
-    if (bytes == 0) bytes = 16;
-    if (cudaMalloc(dst, bytes) != cudaSuccess) { *dst = nullptr; return PFAC_STATUS_CUDA_ALLOC_FAILED; }
-    if (src && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+PFAC_status_t uploadArray(PFAC_handle_t h, const void** dst, const void* src, size_t bytes) {
+    void* d = nullptr;
+    const size_t padded = ((bytes + 15) / 16) * 16 + 16;  // kernels copy tables in 16-byte pieces
+    if (cudaMalloc(&d, padded) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
+    h->d_arrays.push_back(d);
+    if (cudaMemset(d, 0xFF, padded) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    if (bytes && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
+    *dst = d;
     return PFAC_STATUS_SUCCESS;
 }
 
-// shared-memory bytes the table compiler may fill: whatever the dense kernel's per-warp
-// pipelines leave free (PFAC_B200_HOT_KB caps it; PFAC_SPACE_DRIVEN = nothing in smem)
-size_t hotBudget(PFAC_handle_t h) {
+// shared-memory bytes the table compiler may fill: whatever the kernel's per-warp pipelines
+// leave free (PFAC_B200_HOT_KB caps it; PFAC_SPACE_DRIVEN = nothing in smem)
+size_t hotBudget(PFAC_handle_t h, bool reduceKernel) {
     if (h->perfMode == PFAC_SPACE_DRIVEN) return 0;
-    const size_t avail = pfac::tableSmemBudget(h->machine.maxPatternLen);
+    const size_t avail = pfac::tableSmemBudget(h->machine.maxPatternLen, reduceKernel);
     const size_t cap = envBytes("PFAC_B200_HOT_KB", avail / 1024 + 1, 1024);
     return cap < avail ? cap : avail;
 }
 
-// compile the device layout for the current perf mode and upload it (reference PFAC_bindTable,
-// PFAC.cpp:321-343, which picks the dense 2-D table or the hash table)
-PFAC_status_t bindTable(PFAC_handle_t h) {
-    freeDeviceTable(h);
-    pfac::compileLayout(h->machine, hotBudget(h), h->layout);
-    const pfac::DeviceLayout& L = h->layout;
+PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::DeviceTable& t) {
     PFAC_status_t st;
-    if ((st = uploadArray(&h->d_root, L.root, sizeof(L.root))) != PFAC_STATUS_SUCCESS) return st;
-    if ((st = uploadArray(&h->d_pre2, L.pre2.data(), L.pre2.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
-    if ((st = uploadArray(&h->d_rank2, L.rank2.data(), L.rank2.size() * 2)) != PFAC_STATUS_SUCCESS) return st;
-    {   // next2 is copied to shared memory in 16-byte pieces: pad the upload
-        std::vector<uint32_t> padded(L.next2);
-        while (padded.size() & 3) padded.push_back(0xFFFFFFFFu);
-        if ((st = uploadArray(&h->d_next2, padded.data(), padded.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
-        h->table.next2Bytes = uint32_t(padded.size() * 4);
-    }
-    if ((st = uploadArray(&h->d_hot, L.hot.data(), L.hot.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
-    if ((st = uploadArray(&h->d_cold, L.cold.data(), L.cold.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
-    if ((st = uploadArray(&h->d_chains, L.chains.data(), L.chains.size() * 4)) != PFAC_STATUS_SUCCESS) return st;
-    if ((st = uploadArray(&h->d_tails, L.tails.data(), L.tails.size())) != PFAC_STATUS_SUCCESS) return st;
-    pfac::DeviceTable& t = h->table;
-    t.root = static_cast<const int32_t*>(h->d_root);
-    t.pre2 = static_cast<const uint32_t*>(h->d_pre2);
-    t.hot = static_cast<const uint4*>(h->d_hot);
-    t.cold = static_cast<const uint4*>(h->d_cold);
-    t.rank2 = static_cast<const unsigned short*>(h->d_rank2);
-    t.next2 = static_cast<const uint32_t*>(h->d_next2);
+    const void* d = nullptr;
+#define PFAC_UP(field, type, src, bytes)                                                   \
+    if ((st = uploadArray(h, &d, src, bytes)) != PFAC_STATUS_SUCCESS) return st;           \
+    t.field = static_cast<type>(d);
+    PFAC_UP(root, const int32_t*, L.root, sizeof(L.root))
+    PFAC_UP(pre2, const uint32_t*, L.pre2.data(), L.pre2.size() * 4)
+    PFAC_UP(rank2, const unsigned short*, L.rank2.data(), L.rank2.size() * 2)
+    PFAC_UP(next2, const uint32_t*, L.next2.data(), L.next2.size() * 4)
+    PFAC_UP(hot, const uint4*, L.hot.data(), L.hot.size() * 4)
+    PFAC_UP(cold, const uint4*, L.cold.data(), L.cold.size() * 4)
+    PFAC_UP(chains, const uint4*, L.chains.data(), L.chains.size() * 4)
+    PFAC_UP(tails, const unsigned char*, L.tails.data(), L.tails.size())
+#undef PFAC_UP
+    t.next2Bytes = uint32_t(((L.next2.size() * 4 + 15) / 16) * 16);
     t.next2Hot = L.next2Hot;
-    t.chains = static_cast<const uint4*>(h->d_chains);
-    t.tails = static_cast<const unsigned char*>(h->d_tails);
     t.chainBytes = uint32_t(L.chains.size() * 4);
     t.tailBytes = uint32_t(L.tails.size());
     t.chainsHot = L.chainsHot;
@@ -164,6 +147,17 @@ PFAC_status_t bindTable(PFAC_handle_t h) {
     t.numFinal = h->machine.numFinal;
     t.maxPatternLen = h->machine.maxPatternLen;
     return PFAC_STATUS_SUCCESS;
+}
+
+// compile the device layouts for the current perf mode and upload them (reference
+// PFAC_bindTable, PFAC.cpp:321-343, which picks the dense 2-D table or the hash table)
+PFAC_status_t bindTable(PFAC_handle_t h) {
+    freeDeviceTable(h);
+    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout);
+    pfac::compileLayout(h->machine, hotBudget(h, true), h->layoutReduce);
+    PFAC_status_t st = uploadLayout(h, h->layout, h->table);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    return uploadLayout(h, h->layoutReduce, h->tableReduce);
 }
 
 PFAC_status_t loadImage(PFAC_handle_t h, const char* image, size_t size) {
@@ -222,7 +216,7 @@ PFAC_status_t reduceShard(PFAC_handle_t h, const unsigned char* d_in, size_t n_o
     if (st != PFAC_STATUS_SUCCESS) return st;
     if (cudaMemsetAsync(h->d_ws, 0, words * 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     if (cudaMemsetAsync(h->d_total, 0, 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
-    cudaError_t e = pfac::launchMatchReduce(h->table, h->launch, d_in, n_owned, n_total, pos_base, d_id,
+    cudaError_t e = pfac::launchMatchReduce(h->tableReduce, h->launch, d_in, n_owned, n_total, pos_base, d_id,
                                             d_pos, pos64, h->d_ws, h->d_total, stream);
     if (e != cudaSuccess) return cudaToStatus(e);
     if (cudaMemcpyAsync(h->h_total, h->d_total, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess)

@@ -17,7 +17,9 @@
 //     (id, position) pairs in one pass.
 #include "pfac_kernels.h"
 
+#include <algorithm>
 #include <atomic>
+#include <cstdio>
 
 namespace pfac {
 
@@ -34,12 +36,6 @@ constexpr int kDenseWarps = 32;
 constexpr int kDenseThreads = kDenseWarps * 32;
 constexpr int kDenseMaxHalo = 512;             // staged halo cap; longer walks read global
 
-// ---- reduce kernel geometry ------------------------------------------------------------------
-constexpr int kRedThreads = 256;
-constexpr int kRedWarps = kRedThreads / 32;
-constexpr int kRedTile = kRedThreads * kPosPerThread;  // 4096
-constexpr int kRedMaxHalo = 1024;
-
 // look-back descriptor: [63:62] status, [61:0] value
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kStatusIncl = 2ull << 62;
@@ -49,13 +45,12 @@ struct KParams {
     const unsigned char* in;
     long long n_owned;
     long long n_total;
-    long long num_tiles;        // dense: 512-position warp tiles; reduce: 4096-position CTA tiles
+    long long num_tiles;        // 512-position warp tiles
     int* out;                   // dense
     int* out_id;                // reduce
     void* out_pos;              // reduce
     long long pos_base;
     unsigned long long* desc;
-    unsigned long long* ticket;  // tile ticket counter (zeroed with desc)
     unsigned long long* total;
     const int32_t* root;
     const uint32_t* pre2;
@@ -270,12 +265,13 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, int lb, unsigned sh
 // bytes, no hashing) -> then per step either a chain (tail compared 4 bytes at a time) or a
 // hash probe (hot rows in shared memory below hot_depth, cold rows through L1/L2).
 template <bool DENSE>
-__device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
+__device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
                                            const unsigned char* __restrict__ gin, int tile_rem,
                                            const unsigned short* q16, int wtotal, int* wres, int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
     int head = 0;
     bool active = false;
+    bool wrote = false;  // dense: this lane patched a non-zero id into wres
     int pl = 0, d = 0, limit = 0, best = 0, slot = 0;
     uint32_t v = kEmpty;
     auto text_byte = [&](int at) -> uint32_t { return (at < stage_bytes) ? inb[at] : gin[at]; };
@@ -285,8 +281,9 @@ __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char*
             const uint32_t* w = reinterpret_cast<const uint32_t*>(inb + (at & ~3));
             return __funnelshift_r(w[0], w[1], (at & 3) * 8);
         }
-        uint32_t x = 0;
-        for (int k = 0; k < n; k++) x |= text_byte(at + k) << (8 * k);
+        uint32_t x = 0;  // past the staged halo: byte-wise, never beyond the bytes that exist
+        const int nn = n < 4 ? n : 4;
+        for (int k = 0; k < nn; k++) x |= text_byte(at + k) << (8 * k);
         return x;
     };
     for (;;) {
@@ -326,15 +323,24 @@ __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char*
                     done = true;  // cut off by the end of the input: nothing more to report
                 } else {
                     const int at0 = pl + d + 1;
-                    uint32_t tw = rec.w;
-                    int i = 0;
-                    for (;;) {
-                        const int n = len - i;
-                        const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
-                        if ((text_word(at0 + i, n) ^ tw) & mask) { done = true; break; }
-                        i += 4;
-                        if (i >= len) break;
-                        tw = *reinterpret_cast<const uint32_t*>(T.tails + rec.x + i);
+                    {   // first 4 tail bytes travel inside the record: most candidates die here
+                        const uint32_t mask = (len >= 4) ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
+                        if ((text_word(at0, len) ^ rec.w) & mask) done = true;
+                    }
+                    // the rest 16 bytes per trip: four independent tail loads in flight at once
+                    const uint32_t* tw = reinterpret_cast<const uint32_t*>(T.tails + rec.x);
+                    for (int i = 4; i < len && !done; i += 16) {
+                        uint32_t t[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) t[k] = (i + 4 * k < len) ? tw[(i >> 2) + k] : 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int n = len - (i + 4 * k);
+                            if (n > 0 && !done) {
+                                const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
+                                if ((text_word(at0 + i + 4 * k, n) ^ t[k]) & mask) done = true;
+                            }
+                        }
                     }
                     if (!done) {
                         s = rec.z & ~kChainBit;
@@ -360,7 +366,7 @@ __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char*
             }
             if (done) {
                 if (DENSE) {
-                    if (best) wres[pl] = best;
+                    if (best) { wres[pl] = best; wrote = true; }
                 } else {
                     wres[slot] = best;
                 }
@@ -368,6 +374,7 @@ __device__ __forceinline__ void walk_queue(const Tables& T, const unsigned char*
             }
         }
     }
+    return wrote;
 }
 
 // =================================================================================================
@@ -437,6 +444,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 
     uint32_t parity = 0u;  // bit s = phase of bar[s]
     int st = 0;
+    bool dirty = true;     // wres holds non-zeros (or was never cleared): zero it before the walk
     for (; tile < num_tiles; tile += tstride) {
         unsigned char* inb = s_in + st * stage;
         const size_t start = static_cast<size_t>(tile) * kWarpTile;
@@ -466,14 +474,17 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
         }
         const int wtotal = push_survivors(cand, lb, q16, lane);
 
-        // the previous bulk store of this warp must have finished reading wres
+        // the previous bulk store of this warp must have finished reading wres before it is
+        // patched again; wres is all-zero here unless the previous tile had matches
         if (elect_one()) tma_store_wait_read();
         __syncwarp();
+        if (dirty) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(wres)[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
-
-        walk_queue<true>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane);
+            for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(wres)[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+        }
+        dirty = __any_sync(0xffffffffu,
+                           walk_queue<true>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
 
         int* gout = p.out + start;
         if (p.out_aligned && full) {
@@ -496,178 +507,343 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 }
 
 // =================================================================================================
-// Reduce kernel: 256-thread CTAs, 4096-position tiles handed out by a global ticket counter.
-// shared memory: [bars 16][base 8][misc][root 1K | pre2 8K | rank2 4K][queue 8K][ids 16K]
-// [2 input stages][next2][hot][chains][tails]
+// Reduce kernel: fused match + ordered stream compaction, one pass.
+//
+// Same warp-autonomous pipeline as the dense kernel (persistent 32-warp CTA per SM, per-warp TMA
+// input stages, prefilter, queue, walk).  Ordering:
+//   * "CTA tile" c = 32 consecutive warp tiles (16 KB of input); CTA b handles c = r*G + b in
+//     round r (G = grid).  The launch is cooperative, so all G CTAs are co-resident.
+//   * each warp deposits its match count in a shared-memory ring slot and arrives; the last warp
+//     to arrive is the CTA tile's leader: it publishes the tile aggregate, reads the aggregates
+//     of the same round's earlier CTAs (all loads in flight at once: one L2 round trip) and the
+//     running total of all earlier rounds, and posts the CTA tile's base in the ring slot.  The
+//     last CTA to finish a round publishes the next running total.
+//   * warps do not wait for the base: they keep the tile's compacted matches in a small pending
+//     buffer, match the next tile, and only then write (id, position) pairs at
+//     base + (counts of lower warps) -- by then the base is normally there.
+// shared memory: [mbarriers][root | pre2 | rank2][ring 4 slots][per warp: queue 1K | ids 2K |
+// pending 768 B | NSTAGE input stages][next2][hot][chains][tails]
 // =================================================================================================
-constexpr int kROffBar = 0;        // 2 x uint64 mbarrier
-constexpr int kROffBase = 16;      // uint64 tile base
-constexpr int kROffWcount = 32;    // int[8]
-constexpr int kROffWoff = 64;      // int[8]
-constexpr int kROffTicket = 96;    // long long[2]
-constexpr int kROffFixed = 128;    // root | pre2 | rank2
-constexpr int kROffQueue = kROffFixed + kFixedTableBytes;
-constexpr int kROffIds = kROffQueue + kRedWarps * kWarpTile * 2;
-constexpr int kROffIn = kROffIds + kRedTile * 4;
+constexpr int kRedWarps = 32;                  // 31 matcher warps + 1 scanner warp
+constexpr int kRedMatchers = kRedWarps - 1;
+constexpr int kRedThreads = kRedWarps * 32;
+constexpr int kRedMaxHalo = kDenseMaxHalo;
+constexpr int kRedStages = 2;                  // input stages per matcher warp
+constexpr int kRing = 8;                       // arrival ring slots
+constexpr int kLag = 6;                        // a warp may run this many rounds ahead (kRing >= kLag + 2)
+constexpr int kPendCap = 128;                  // matches a warp can park while bases are computed
+constexpr int kPendRecs = 4;                   // ... spread over at most this many rounds
+constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base | before
+constexpr int kRingBytes = kRing * kSlotBytes;
+static_assert(kRing >= kLag + 2 && (kRing & (kRing - 1)) == 0, "ring size");
+static_assert((kPendCap & (kPendCap - 1)) == 0, "pending buffer is a power-of-two ring");
+
+// per-round word: [63:40] CTAs that published, [39:0] matches of the round so far
+constexpr int kRoundShift = 40;
+constexpr unsigned long long kRoundMask = (1ull << kRoundShift) - 1;
+
+struct RingSlot {
+    int counts[kRedWarps];
+    int arrived;
+    int ready;                 // round+1 once base is valid
+    unsigned long long base;
+    unsigned long long before; // round word before this CTA's contribution (scanner only)
+    int pad[kSlotBytes / 4 - kRedWarps - 6];
+};
+static_assert(sizeof(RingSlot) == kSlotBytes, "ring slot layout");
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+#ifdef PFAC_DEBUG_SPIN
+#define PFAC_SPIN_GUARD(n, what, a, b_, c)                                                          \
+    if (++(n) > (1ull << 22)) {                                                                      \
+        printf("STUCK %s blk %d warp %d lane %d : %lld %lld %lld\n", what, int(blockIdx.x),         \
+               int(threadIdx.x >> 5), int(threadIdx.x & 31), (long long)(a), (long long)(b_), (long long)(c)); \
+        __trap();                                                                                    \
+    }
+#else
+#define PFAC_SPIN_GUARD(n, what, a, b_, c)
+#endif
 
 template <bool POS64>
-__global__ void __launch_bounds__(kRedThreads) pfac_reduce_kernel(const KParams p) {
+__global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KParams p) {
+    constexpr int NSTAGE = kRedStages;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + kROffBar);
-    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(smem + kROffBase);
-    int* s_wcount = reinterpret_cast<int*>(smem + kROffWcount);
-    int* s_woff = reinterpret_cast<int*>(smem + kROffWoff);
-    long long* s_ticket = reinterpret_cast<long long*>(smem + kROffTicket);
-    unsigned short* s_queue = reinterpret_cast<unsigned short*>(smem + kROffQueue);
-    int* s_ids = reinterpret_cast<int*>(smem + kROffIds);
-    const int stage = kRedTile + p.halo;
-    unsigned char* s_in = smem + kROffIn;
+    const int stage = kWarpTile + p.halo;
+    const int per_warp = kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + NSTAGE * stage;
+    constexpr int kBarBytes = ((kRedWarps * NSTAGE * 8 + 127) / 128) * 128;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
+    unsigned char* s_fixed = smem + kBarBytes;
+    RingSlot* ring = reinterpret_cast<RingSlot*>(s_fixed + kFixedTableBytes);
+    unsigned char* s_warp = s_fixed + kFixedTableBytes + kRingBytes;
+    unsigned char* s_var = s_warp + kRedMatchers * per_warp;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const uint32_t warp = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tid) >> 5, 0);
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    const Tables T = stage_tables(p, smem + kROffFixed, smem + kROffIn + 2 * stage, tid, kRedThreads);
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+    const Tables T = stage_tables(p, s_fixed, s_var, tid, kRedThreads);
+    unsigned long long* bar = s_bar + warp * NSTAGE;
+    if (lane == 0) {
+        for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    for (int i = tid; i < kRingBytes / 4; i += kRedThreads) reinterpret_cast<int*>(ring)[i] = 0;
+    __syncthreads();  // the only CTA-wide barrier
 
-    auto tile_is_bulk = [&](long long t) -> bool {
-        return p.in_aligned && (t * kRedTile + stage <= p.n_total);
-    };
-    auto load_tile = [&](long long t, int buf) {
-        if (t >= p.num_tiles) return;
-        unsigned char* dst = s_in + buf * stage;
-        const long long start = t * kRedTile;
-        if (tile_is_bulk(t)) {
-            if (tid == 0) {
-                mbar_arrive_expect_tx(&s_bar[buf], static_cast<uint32_t>(stage));
-                tma_load_1d(dst, p.in + start, static_cast<uint32_t>(stage), &s_bar[buf]);
-            }
-        } else {
-            for (int i = tid; i < stage; i += kRedThreads) {
-                const long long g = start + i;
-                dst[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
-            }
-        }
-    };
+    const uint32_t G = gridDim.x;
+    const uint32_t b = blockIdx.x;
+    const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
+    const uint32_t num_ctiles = (num_tiles + kRedMatchers - 1) / kRedMatchers;
+    const uint32_t num_rounds = (num_ctiles + G - 1) / G;
+    // rounds this CTA takes part in: r with r*G + b < num_ctiles
+    const uint32_t my_rounds = (num_ctiles > b) ? (num_ctiles - b + G - 1) / G : 0;
+    unsigned long long* g_desc = p.desc;                      // [num_ctiles] aggregate per CTA tile
+    unsigned long long* g_rt = p.desc + num_ctiles;           // [num_rounds] inclusive total of rounds <= r
+    unsigned long long* g_rs = g_rt + num_rounds;             // [num_rounds] {CTAs published, matches} of round r
 
-    // Tiles are tickets from a global counter, so a tile index is only ever held by a running
-    // CTA and the look-back below can never wait on a CTA that is not resident.
-    long long tile, next_tile;
-    if (tid == 0) {
-        s_ticket[0] = static_cast<long long>(atomicAdd(p.ticket, 1ull));
-        s_ticket[1] = static_cast<long long>(atomicAdd(p.ticket, 1ull));
-    }
-    __syncthreads();
-    tile = s_ticket[0];
-    next_tile = s_ticket[1];
-    __syncthreads();
-    load_tile(tile, 0);
-    load_tile(next_tile, 1);
-    __syncthreads();
-
-    uint32_t parity = 0u;
-    unsigned short* q16 = s_queue + warp * kWarpTile;
-    int* wids = s_ids + warp * kWarpTile;  // ids by queue slot
-
-    for (int it = 0; tile < p.num_tiles; ++it) {
-        unsigned long long my_ticket = 0;
-        if (tid == 0) my_ticket = atomicAdd(p.ticket, 1ull);  // consumed just before (A)
-        const int buf = it & 1;
-        const unsigned char* inb = s_in + buf * stage;
-        const long long start = tile * kRedTile;
-        if (tile_is_bulk(tile)) {
-            mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
-            parity ^= 1u << buf;
-        }
-        const long long owned_left = p.n_owned - start;
-        const int valid = owned_left < kRedTile ? static_cast<int>(owned_left) : kRedTile;
-        const long long total_left = p.n_total - start;
-        const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
-
-        const int lb = tid * kPosPerThread;
-        uint32_t cand = prefilter16(inb, lb, T.pre2);
-        if (valid < kRedTile) {
-            int nv = valid - lb;
-            nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
-            cand &= (1u << nv) - 1u;
-        }
-        const int wtotal = push_survivors(cand, lb, q16, lane);
-        __syncwarp();
-        walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane);
-        __syncwarp();
-
-        // ---- ordered compaction: warp count -> CTA scan -> look-back -> write pairs -----------
-        int nmatch = 0;
-        for (int base = 0; base < wtotal; base += 32) {
-            const int i = base + lane;
-            const int id = (i < wtotal) ? wids[i] : 0;
-            nmatch += __popc(__ballot_sync(0xffffffffu, id != 0));
-        }
-        if (lane == 0) s_wcount[warp] = nmatch;
-        if (tid == 0) s_ticket[0] = static_cast<long long>(my_ticket);
-        __syncthreads();  // (A) all walks done: s_in[buf] is free, counts are published
-        const long long future_tile = s_ticket[0];
-        load_tile(future_tile, buf);
-        if (warp == 0) {
-            const int c = (lane < kRedWarps) ? s_wcount[lane] : 0;
-            int inc = c;
+    if (warp == kRedMatchers) {
+        // ======================= scanner warp: publishes aggregates, resolves bases ==================
+        // Never blocks on one round: publishing round r (needs only this CTA's counts) is not held up
+        // by resolving an earlier round (needs other CTAs' aggregates and the previous round total).
+        uint32_t pub_r = 0, res_r = 0;
+        while (res_r < my_rounds) {
+            bool progress = false;
+            if (pub_r < my_rounds) {
+                RingSlot* slot = &ring[pub_r & (kRing - 1)];
+                if (ld_volatile_s32(&slot->arrived) == kRedMatchers) {
+                    __threadfence_block();
+                    int c = (lane < kRedMatchers) ? slot->counts[lane] : 0;
 #pragma unroll
-            for (int dd = 1; dd < kRedWarps; dd <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, inc, dd);
-                if (lane >= dd) inc += o;
-            }
-            if (lane < kRedWarps) s_woff[lane] = inc - c;
-            const unsigned long long ttotal =
-                static_cast<unsigned long long>(__shfl_sync(0xffffffffu, inc, kRedWarps - 1));
-            unsigned long long base = 0;
-            if (tile > 0) {
-                if (lane == 0) st_relaxed_u64(p.desc + tile, kStatusAgg | ttotal);
-                long long t = tile - 1;
-                for (;;) {
-                    const long long idx = t - lane;
-                    unsigned long long v = (idx >= 0) ? ld_relaxed_u64(p.desc + idx) : kStatusIncl;
-                    while (__any_sync(0xffffffffu, (v >> 62) == 0)) {
-                        if ((v >> 62) == 0) v = ld_relaxed_u64(p.desc + idx);
+                    for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
+                    if (lane == 0) {
+                        const unsigned long long ttotal = static_cast<unsigned long long>(c);
+                        st_relaxed_u64(g_desc + pub_r * G + b, kStatusAgg | ttotal);
+                        slot->before = atomicAdd(g_rs + pub_r, (1ull << kRoundShift) | ttotal);
+                        slot->counts[kRedMatchers] = c;  // this CTA tile's total
+                        slot->arrived = 0;               // matchers are at most kLag rounds ahead
                     }
-                    const unsigned incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
-                    unsigned long long part = (lane <= first) ? (v & kValueMask) : 0ull;
-#pragma unroll
-                    for (int dd = 16; dd > 0; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
-                    base += part;
-                    if (incl_mask) break;
-                    t -= 32;
+                    __syncwarp();
+                    pub_r++;
+                    progress = true;
                 }
             }
-            if (lane == 0) {
-                st_relaxed_u64(p.desc + tile, kStatusIncl | (base + ttotal));
-                *s_base = base;
-                if (tile == p.num_tiles - 1) *p.total = base + ttotal;
+            if (res_r < pub_r) {
+                const uint32_t r = res_r;
+                // everything needed: aggregates of the same round's earlier CTAs + total of earlier rounds
+                unsigned long long part = 0;
+                bool have = true;
+                for (uint32_t k = lane; k < b; k += 32) {
+                    const unsigned long long v = ld_relaxed_u64(g_desc + r * G + k);
+                    have = have && ((v >> 62) != 0);
+                    part += v & kValueMask;
+                }
+                unsigned long long prev = 0;
+                if (r > 0 && lane == 0) {
+                    const unsigned long long v = ld_relaxed_u64(g_rt + (r - 1));
+                    have = have && ((v >> 62) != 0);
+                    prev = v & kValueMask;
+                }
+                if (__all_sync(0xffffffffu, have)) {
+#pragma unroll
+                    for (int dd = 16; dd > 0; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+                    if (lane == 0) {
+                        RingSlot* slot = &ring[r & (kRing - 1)];
+                        slot->base = prev + part;
+                        __threadfence_block();
+                        slot->ready = static_cast<int>(r + 1);
+                        const uint32_t in_round = (r + 1 < num_rounds) ? G : (num_ctiles - r * G);
+                        const unsigned long long before = slot->before;
+                        if ((before >> kRoundShift) == in_round - 1) {  // this CTA completed round r
+                            const unsigned long long incl =
+                                prev + (before & kRoundMask) + static_cast<unsigned long long>(slot->counts[kRedMatchers]);
+                            st_relaxed_u64(g_rt + r, kStatusIncl | incl);
+                            if (r + 1 == num_rounds) *p.total = incl;
+                        }
+                    }
+                    __syncwarp();
+                    res_r++;
+                    progress = true;
+                }
             }
+            if (!progress) __nanosleep(40);
         }
-        __syncthreads();  // (B)
-        unsigned long long obase = *s_base + static_cast<unsigned long long>(s_woff[warp]);
-        for (int base = 0; base < wtotal; base += 32) {
-            const int i = base + lane;
-            const int id = (i < wtotal) ? wids[i] : 0;
-            const unsigned m = __ballot_sync(0xffffffffu, id != 0);
-            if (id != 0) {
-                const unsigned long long o = obase + __popc(m & lt_mask);
-                const long long gpos = p.pos_base + start + q16[i];
-                p.out_id[o] = id;
-                if (POS64) reinterpret_cast<long long*>(p.out_pos)[o] = gpos;
-                else reinterpret_cast<int*>(p.out_pos)[o] = static_cast<int>(gpos);
+        return;
+    }
+
+    // ============================ matcher warps ==========================================================
+    unsigned char* mine = s_warp + warp * per_warp;
+    unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
+    int* wids = reinterpret_cast<int*>(mine + kWarpTile * 2);
+    int* pend_id = reinterpret_cast<int*>(mine + kWarpTile * 6);                                      // ring of kPendCap
+    unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kWarpTile * 6 + kPendCap * 4);  // ring of kPendCap
+    unsigned char* s_in = mine + kWarpTile * 6 + kPendCap * 6;
+    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kWarpTile);
+
+    auto issue_load = [&](uint32_t t, int st) {
+        if (t < p.bulk_tiles) {
+            mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
+            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kWarpTile, static_cast<uint32_t>(stage),
+                        &bar[st]);
+        }
+    };
+    auto tile_of = [&](uint32_t r) -> uint32_t { return (r * G + b) * kRedMatchers + warp; };
+    if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < NSTAGE; i++) issue_load(tile_of(i), i);
+    }
+
+    auto round_ready = [&](uint32_t r) -> bool {
+        return ld_volatile_s32(&ring[r & (kRing - 1)].ready) >= static_cast<int>(r + 1);
+    };
+    auto wait_ready = [&](uint32_t r, const char* what) {
+        unsigned long long spins = 0;
+        (void)spins; (void)what;
+        while (!round_ready(r)) {
+            __nanosleep(100);
+            PFAC_SPIN_GUARD(spins, what, r, ld_volatile_s32(&ring[r & (kRing - 1)].ready), 0)
+        }
+    };
+    // write n of one warp's matches of round r (entries [first, first+n) of a ring of `cap` slots)
+    auto write_out = [&](uint32_t r, const int* ids, const unsigned short* pos, int first, int n, int cap_mask,
+                         size_t tile_start) {
+        RingSlot* slot = &ring[r & (kRing - 1)];
+        __threadfence_block();
+        int lower = (static_cast<uint32_t>(lane) < warp) ? slot->counts[lane] : 0;
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) lower += __shfl_xor_sync(0xffffffffu, lower, dd);
+        const unsigned long long off = slot->base + static_cast<unsigned long long>(lower);
+        const long long gbase = p.pos_base + static_cast<long long>(tile_start);
+        for (int i = lane; i < n; i += 32) {
+            const int e = (first + i) & cap_mask;
+            p.out_id[off + i] = ids[e];
+            const long long gpos = gbase + pos[e];
+            if (POS64) reinterpret_cast<long long*>(p.out_pos)[off + i] = gpos;
+            else reinterpret_cast<int*>(p.out_pos)[off + i] = static_cast<int>(gpos);
+        }
+    };
+
+    // pending FIFO: matches of up to kPendRecs earlier rounds wait here for their CTA tile's base
+    uint32_t rec_round[kPendRecs];
+    int rec_n[kPendRecs];
+    size_t rec_start[kPendRecs];
+    int nrec = 0;         // records in use; record 0 is the oldest
+    int pend_head = 0;    // ring index of the oldest parked entry
+    int pend_used = 0;
+    auto pop_oldest = [&]() {  // caller made sure its round is ready
+        write_out(rec_round[0], pend_id, pend_pos, pend_head, rec_n[0], kPendCap - 1, rec_start[0]);
+        __syncwarp();
+        pend_head = (pend_head + rec_n[0]) & (kPendCap - 1);
+        pend_used -= rec_n[0];
+#pragma unroll
+        for (int i = 0; i + 1 < kPendRecs; i++) {
+            rec_round[i] = rec_round[i + 1];
+            rec_n[i] = rec_n[i + 1];
+            rec_start[i] = rec_start[i + 1];
+        }
+        nrec--;
+    };
+
+    uint32_t parity = 0u;
+    int st = 0;
+    for (uint32_t r = 0; r < my_rounds; ++r) {
+        const uint32_t tile = tile_of(r);
+        const size_t start = static_cast<size_t>(tile) * kWarpTile;
+        int nmatch = 0;
+        if (tile < num_tiles) {
+            unsigned char* inb = s_in + st * stage;
+            if (tile < p.bulk_tiles) {
+                mbar_wait(&bar[st], (parity >> st) & 1u);
+                parity ^= 1u << st;
+            } else {
+                for (int i = lane; i < stage; i += 32) {
+                    const long long g = static_cast<long long>(start) + i;
+                    inb[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
+                }
+                __syncwarp();
             }
-            obase += __popc(m);
+            const long long total_left = p.n_total - static_cast<long long>(start);
+            const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
+            const int lb = lane * kPosPerThread;
+            uint32_t cand = prefilter16(inb, lb, T.pre2);
+            if (tile >= full_tiles) {
+                const int valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
+                int nv = valid - lb;
+                nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
+                cand &= (1u << nv) - 1u;
+            }
+            const int wtotal = push_survivors(cand, lb, q16, lane);
+            __syncwarp();
+            walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane);
+            __syncwarp();
+            // in-place ordered compaction of (position, id) to the front of q16 / wids
+            for (int base = 0; base < wtotal; base += 32) {
+                const int i = base + lane;
+                const int id = (i < wtotal) ? wids[i] : 0;
+                const unsigned short pos = (i < wtotal) ? q16[i] : static_cast<unsigned short>(0);
+                const unsigned m = __ballot_sync(0xffffffffu, id != 0);
+                if (id != 0) {
+                    const int o = nmatch + __popc(m & lt_mask);
+                    wids[o] = id;
+                    q16[o] = pos;
+                }
+                nmatch += __popc(m);
+            }
+            __syncwarp();
+            if (elect_one()) issue_load(tile_of(r + NSTAGE), st);  // this stage is consumed
+            st = (st + 1 == NSTAGE) ? 0 : st + 1;
         }
-        tile = next_tile;
-        next_tile = future_tile;
+
+        // ---- flow control: nobody runs more than kLag rounds ahead of the scanner, so a ring slot
+        // (round r-kRing) is never rewritten while a warp may still read it
+        if (r >= kLag) wait_ready(r - kLag, "lag");
+
+        // ---- arrive: deposit the count; the scanner warp takes it from here -------------------------
+        RingSlot* slot = &ring[r & (kRing - 1)];
+        if (lane == 0) {
+            slot->counts[warp] = nmatch;
+            __threadfence_block();
+            atomicAdd(&slot->arrived, 1);
+        }
+
+        // ---- write parked matches whose base has arrived; park (or write) this round's ----------------
+        while (nrec > 0 && round_ready(rec_round[0])) pop_oldest();
+        if (nmatch > kPendCap) {
+            while (nrec > 0) { wait_ready(rec_round[0], "drain"); pop_oldest(); }
+            wait_ready(r, "direct");
+            write_out(r, wids, q16, 0, nmatch, 0x7fffffff, start);  // too many to park
+            __syncwarp();
+        } else if (nmatch > 0) {
+            while (nrec == kPendRecs || pend_used + nmatch > kPendCap) {
+                wait_ready(rec_round[0], "room");
+                pop_oldest();
+            }
+            const int tail = (pend_head + pend_used) & (kPendCap - 1);
+            for (int i = lane; i < nmatch; i += 32) {
+                const int e = (tail + i) & (kPendCap - 1);
+                pend_id[e] = wids[i];
+                pend_pos[e] = q16[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kPendRecs; i++) {
+                if (i == nrec) {
+                    rec_round[i] = r;
+                    rec_n[i] = nmatch;
+                    rec_start[i] = start;
+                }
+            }
+            nrec++;
+            pend_used += nmatch;
+        }
+    }
+    while (nrec > 0) {
+        wait_ready(rec_round[0], "final");
+        pop_oldest();
     }
 }
 
@@ -688,6 +864,12 @@ size_t denseFixedBytes(int halo) {
     const size_t bar = size_t((kDenseWarps * nst * 8 + 127) / 128) * 128;
     return bar + kFixedTableBytes +
            size_t(kDenseWarps) * (kWarpTile * 2 + kWarpTile * 4 + nst * (kWarpTile + halo));
+}
+
+size_t reduceFixedBytes(int halo) {
+    const size_t bar = size_t((kRedWarps * kRedStages * 8 + 127) / 128) * 128;
+    return bar + kFixedTableBytes + kRingBytes +
+           size_t(kRedMatchers) * (kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + kRedStages * (kWarpTile + halo));
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
@@ -727,12 +909,18 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
 
 }  // namespace
 
-size_t tableSmemBudget(int maxPatternLen) {
-    const size_t fixed = denseFixedBytes(roundHalo(maxPatternLen, kDenseMaxHalo));
+size_t tableSmemBudget(int maxPatternLen, bool reduceKernel) {
+    const int halo = roundHalo(maxPatternLen, kDenseMaxHalo);
+    const size_t fixed = reduceKernel ? reduceFixedBytes(halo) : denseFixedBytes(halo);
     return fixed < size_t(kMaxSmem) ? size_t(kMaxSmem) - fixed : 0;
 }
 
-size_t reduceWorkspaceWords(size_t n_owned) { return (n_owned + kRedTile - 1) / kRedTile + 1; }
+// per CTA tile (16 KB of input): one aggregate word; per round: a running total and a counter
+size_t reduceWorkspaceWords(size_t n_owned) {
+    const size_t tiles = (n_owned + kWarpTile - 1) / kWarpTile;
+    const size_t ctiles = (tiles + kRedMatchers - 1) / kRedMatchers;
+    return 3 * ctiles + 8;
+}
 
 unsigned long long kernelLaunchCount() { return g_launches.load(); }
 
@@ -771,27 +959,32 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
                               unsigned long long* d_total, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
     const int halo = roundHalo(t.maxPatternLen, kRedMaxHalo);
-    KParams p = baseParams(t, in, n_owned, n_total, halo, kRedTile);
+    KParams p = baseParams(t, in, n_owned, n_total, halo, kWarpTile);
+    if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.out_id = out_id;
     p.out_pos = out_pos;
     p.pos_base = pos_base;
     p.desc = desc;
-    p.ticket = desc + p.num_tiles;  // last workspace word
     p.total = d_total;
-    const size_t smem = size_t(kROffIn) + 2 * size_t(kRedTile + halo) + tableSmemBytes(t);
+    {
+        const long long stage = kWarpTile + halo;
+        long long bulk = 0;
+        if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kWarpTile + 1;
+        if (bulk > p.num_tiles) bulk = p.num_tiles;
+        p.bulk_tiles = static_cast<uint32_t>(bulk);
+    }
+    const size_t smem = reduceFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
-    auto kernel = pos64 ? pfac_reduce_kernel<true> : pfac_reduce_kernel<false>;
+    const void* kernel = pos64 ? (const void*)pfac_reduce_kernel<true> : (const void*)pfac_reduce_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    int perSM = cfg.ctasPerSM;
-    if (perSM <= 0) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kRedThreads, smem);
-        if (e != cudaSuccess) return e;
-        if (perSM < 1) return cudaErrorLaunchOutOfResources;
-    }
-    long long grid = static_cast<long long>(cfg.numSMs) * perSM;
-    if (grid > p.num_tiles) grid = p.num_tiles;
-    kernel<<<int(grid), kRedThreads, smem, stream>>>(p);
+    const long long ctaTiles = (p.num_tiles + kRedMatchers - 1) / kRedMatchers;
+    long long grid = cfg.numSMs;
+    if (grid > ctaTiles) grid = ctaTiles;
+    // cooperative launch: every CTA is resident, so waiting on another CTA's aggregate is safe
+    void* args[] = {&p};
+    e = cudaLaunchCooperativeKernel(kernel, dim3(unsigned(grid)), dim3(kRedThreads), args, smem, stream);
+    if (e != cudaSuccess) return e;
     g_launches++;
     return cudaGetLastError();
 }

@@ -35,9 +35,10 @@ struct LaunchConfig {
     int ctasPerSM = 0;   // 0 = ask the occupancy API
 };
 
-// Shared-memory bytes the dense kernel can spare for hash rows / chains / tails, given the
-// longest pattern (which fixes the staged halo).  The table compiler is run with this budget.
-size_t tableSmemBudget(int maxPatternLen);
+// Shared-memory bytes the dense (or reduce) kernel can spare for next2 / hash rows / chains /
+// tails, given the longest pattern (which fixes the staged halo).  The table compiler is run
+// once per kernel with its budget; the two layouts differ only in what is marked hot.
+size_t tableSmemBudget(int maxPatternLen, bool reduceKernel);
 
 // Look-back descriptor words needed by the reduce kernel for an n_owned-byte shard.
 size_t reduceWorkspaceWords(size_t n_owned);

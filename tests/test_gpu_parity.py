@@ -94,6 +94,7 @@ CASES = [
     ("c2_1k", lambda: synth.patterns_c2(1000), "random", (1 << 22) + 13, 4096),
     ("snort_small", lambda: synth.patterns_snort_like(1500, seed=12), "ascii", (1 << 21) + 5, 1024),
     ("dna_small", lambda: synth.patterns_dna(400, seed=13, short=8), "dna", 1_000_003, 0),
+    ("snort_10k", lambda: synth.patterns_snort_like(10000, seed=14), "ascii", (1 << 23) + 777, 2048),
 ]
 
 
@@ -124,3 +125,150 @@ def test_dense_and_reduce_vs_oracle(cuda, tmp_path, name, gen, kind, n, every):
         assert np.array_equal(pf.matchFromHost(text), want)
         hid, hpos = pf.matchFromHostReduce(text)
         assert np.array_equal(hid, want_ids) and np.array_equal(hpos.astype(np.int64), want_pos)
+
+
+def _check_all(pf, orc, text, cuda, n_owned=None):
+    """dense (+ shard form) and both reduce widths against the oracle on one text."""
+    n = text.size if n_owned is None else n_owned
+    want = orc.match_shard(text, n) if n_owned is not None else orc.match(text)
+    got = _dev_match(pf, text, cuda, owned=n_owned)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "dense mismatch at %d: got %d want %d (n=%d)" % (bad[0], got[bad[0]], want[bad[0]], n)
+    wid, wpos = orc.reduce(want)
+    if n_owned is None:
+        m, ids, pos = _dev_reduce(pf, text, cuda)
+        assert m == wid.size and np.array_equal(ids[:m], wid) and np.array_equal(pos[:m].astype(np.int64), wpos)
+    d_in = torch.from_numpy(text).to(cuda)
+    d_id = torch.full((max(n, 1),), -7, dtype=torch.int32, device=cuda)
+    d_pos = torch.full((max(n, 1),), -7, dtype=torch.int64, device=cuda)
+    base = 5_000_000_000  # positions beyond 2^32 must survive
+    m = pf.matchShardFromDeviceReduce64(d_in, n, text.size, base, d_id, d_pos)
+    assert m == wid.size
+    assert np.array_equal(d_id[:m].cpu().numpy(), wid)
+    assert np.array_equal(d_pos[:m].cpu().numpy(), wpos + base)
+    assert (d_id[m:] == -7).all() and (d_pos[m:] == -7).all()
+
+
+def test_edge_sizes_tail_tiles_and_shards(cuda, tmp_path):
+    """Empty / tiny / ragged inputs, tile-boundary sizes, patterns cut off by the end of the input,
+    and the shard form (owned positions + tail halo)."""
+    from pfac_b200 import PFAC
+    pats = synth.patterns_c2(300, seed=21, min_len=1, max_len=40, prefix_pairs=60)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        for n in [1, 2, 3, 15, 16, 17, 39, 40, 511, 512, 513, 527, 528, 1023, 1024, 4095, 4096, 4097,
+                  16383, 16384, 16385, 70001, 262144 + 17]:
+            text = synth.make_text("random", 300 + n, 0, n, n, pats, 96)
+            _check_all(pf, orc, text, cuda)
+        text = synth.make_text("random", 77, 0, 100_000, 100_000, pats, 64)
+        for owned in [1, 511, 512, 4096, 50_000, 99_961, 99_999, 100_000]:
+            _check_all(pf, orc, text, cuda, n_owned=owned)
+        # size 0: SUCCESS, nothing written (reference PFAC.cpp:860-862)
+        d_in = torch.zeros(16, dtype=torch.uint8, device=cuda)
+        d_out = torch.full((16,), -7, dtype=torch.int32, device=cuda)
+        pf.matchFromDevice(d_in, 0, d_out)
+        assert pf.matchFromDeviceReduce(d_in, 0, d_out, d_out) == 0
+        torch.cuda.synchronize()
+        assert (d_out == -7).all()
+
+
+def test_unaligned_device_pointers(cuda, tmp_path):
+    """Any pointer alignment is accepted (the reference needs 4-byte aligned input and reads up to
+    3 bytes past the end, PFAC.cpp:838-841; this library does neither)."""
+    from pfac_b200 import PFAC
+    pats = synth.patterns_snort_like(400, seed=22)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = 150_001
+    text = synth.make_text("ascii", 901, 0, n, n, pats, 200)
+    want = orc.match(text)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        for in_off, out_off in [(1, 0), (3, 1), (16, 2), (5, 3), (0, 1)]:
+            buf = torch.zeros(n + 64, dtype=torch.uint8, device=cuda)
+            buf[in_off:in_off + n] = torch.from_numpy(text).to(cuda)
+            obuf = torch.full((n + 8,), -7, dtype=torch.int32, device=cuda)
+            pf.matchFromDevice(buf[in_off:], n, obuf[out_off:])
+            torch.cuda.synchronize()
+            got = obuf.cpu().numpy()
+            assert np.array_equal(got[out_off:out_off + n], want), (in_off, out_off)
+            assert (got[:out_off] == -7).all() and (got[out_off + n:] == -7).all()
+
+
+def test_high_match_density_compaction(cuda, tmp_path):
+    """More matches per 512-byte tile than a warp can park (reduce kernel's synchronous path), several
+    rounds of CTA tiles, 1-byte and 2-byte patterns (every occurrence of a byte matches)."""
+    from pfac_b200 import PFAC
+    pats = [b"AC", b"GT", b"TT", b"CA", b"G", b"ACGTAC", b"TTTT", b"CAT", b"GATTACA", b"AA", b"TG", b"CC"]
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = 148 * 16384 * 2 + 12_345   # > 2 rounds of CTA tiles
+    text = synth.dna_bytes(4242, 0, n)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        _check_all(pf, orc, text, cuda)
+        want = orc.match(text)
+        assert (want > 0).mean() > 0.5
+
+
+def test_patterns_longer_than_the_staged_halo(cuda, tmp_path):
+    """Walks that run past the shared-memory halo (512 bytes) continue from global memory."""
+    from pfac_b200 import PFAC
+    rng = np.random.default_rng(5)
+    longp = [bytes(rng.integers(32, 127, size=L, dtype=np.uint8).tolist()) for L in (600, 900, 1500, 2300)]
+    pats = longp + [longp[0][:300], longp[1][:513], b"xyz", longp[2][:1499]]
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = 400_000
+    text = synth.make_text("ascii", 99, 0, n, n, pats, 3000)
+    # near misses: a long pattern with its last byte changed, and one cut off by the end
+    t2 = np.frombuffer(longp[3], dtype=np.uint8).copy()
+    t2[-1] ^= 1
+    text[1000:1000 + t2.size] = t2
+    text[n - 1400:n] = np.frombuffer(longp[2][:1400], dtype=np.uint8)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        _check_all(pf, orc, text, cuda)
+        assert set(np.unique(orc.match(text))) >= {1, 2, 3, 4, 5, 6}
+
+
+def test_two_handles_and_pattern_reload(cuda, golden_dir, tmp_path):
+    """Reference SimpleMultiGPU_pthread.cpp pattern: independent handles with different pattern sets;
+    plus re-reading patterns into a live handle (PFAC.cpp:663-666)."""
+    from pfac_b200 import PFAC
+    t1 = np.fromfile(os.path.join(golden_dir, "example_input"), dtype=np.uint8)
+    t2 = np.fromfile(os.path.join(golden_dir, "example_input2"), dtype=np.uint8)
+    with PFAC() as a, PFAC() as b:
+        a.readPatternFromFile(os.path.join(golden_dir, "example_pattern"))
+        b.readPatternFromFile(os.path.join(golden_dir, "example_pattern2"))
+        assert _dev_match(a, t1, cuda).tolist() == [1, 3, 4, 0, 4, 0, 2, 0, 0, 0]
+        assert _dev_match(b, t2, cuda).tolist() == [4, 3, 0, 4, 5, 0, 0, 1, 7, 9, 1, 8, 9, 1, 0]
+        a.readPatternFromFile(os.path.join(golden_dir, "example_pattern2"))
+        assert _dev_match(a, t2, cuda).tolist() == [4, 3, 0, 4, 5, 0, 0, 1, 7, 9, 1, 8, 9, 1, 0]
+        a.readPatternFromMemory(b"ED\nAB\n")
+        assert _dev_match(a, t1, cuda).tolist() == [2, 0, 1, 0, 1, 0, 2, 0, 0, 0]
+
+
+def test_errors_with_a_live_handle(cuda, tmp_path):
+    from pfac_b200 import PFAC, PFACError, Status
+    with PFAC() as pf:
+        d = torch.zeros(32, dtype=torch.int32, device=cuda)
+        with pytest.raises(PFACError) as e:
+            pf.matchFromDevice(d, 8, d)
+        assert e.value.status == Status.PATTERNS_NOT_READY
+        with pytest.raises(PFACError) as e:
+            pf.readPatternFromFile(str(tmp_path / "missing"))
+        assert e.value.status == Status.FILE_OPEN_ERROR
+        pf.readPatternFromMemory(b"AB\n")
+        for call in (lambda: pf.matchFromDevice(None, 8, d), lambda: pf.matchFromDevice(d, 8, None)):
+            with pytest.raises(PFACError) as e:
+                call()
+            assert e.value.status == Status.INVALID_PARAMETER
+        with pytest.raises(PFACError) as e:
+            pf.setPlatform(7)
+        assert e.value.status == Status.INVALID_PARAMETER
+        pf.setPlatform(1)      # CPU / CPU_OMP are accepted; work still runs on the GPU
+        pf.setTextureMode(1)
+        assert pf.matchFromHost(np.frombuffer(b"xxABxx", dtype=np.uint8)).tolist() == [0, 0, 1, 0, 0, 0]
