@@ -529,13 +529,17 @@ constexpr int kRedMatchers = kRedWarps - 1;
 constexpr int kRedThreads = kRedWarps * 32;
 constexpr int kRedMaxHalo = kDenseMaxHalo;
 constexpr int kRedStages = 2;                  // input stages per matcher warp
-constexpr int kRing = 8;                       // arrival ring slots
-constexpr int kLag = 6;                        // a warp may run this many rounds ahead (kRing >= kLag + 2)
+constexpr int kLag = 6;                        // a matcher may run this many rounds ahead of the scanner
+// Ring slot reuse: a matcher that passed the lag wait of iteration j has written out every parked
+// record of rounds <= j-kLag, so after iteration j it holds records > j-kLag only.  Slot r is
+// rewritten by the first arrival at r+kRing, which needs ready(r+kRing-kLag), i.e. every matcher
+// finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
+constexpr int kRing = 16;                      // arrival ring slots
 constexpr int kPendCap = 128;                  // matches a warp can park while bases are computed
 constexpr int kPendRecs = 4;                   // ... spread over at most this many rounds
 constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base | before
 constexpr int kRingBytes = kRing * kSlotBytes;
-static_assert(kRing >= kLag + 2 && (kRing & (kRing - 1)) == 0, "ring size");
+static_assert(kRing >= 2 * kLag + 1 && (kRing & (kRing - 1)) == 0, "ring size");
 static_assert((kPendCap & (kPendCap - 1)) == 0, "pending buffer is a power-of-two ring");
 
 // per-round word: [63:40] CTAs that published, [39:0] matches of the round so far

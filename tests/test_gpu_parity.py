@@ -272,3 +272,33 @@ def test_errors_with_a_live_handle(cuda, tmp_path):
         pf.setPlatform(1)      # CPU / CPU_OMP are accepted; work still runs on the GPU
         pf.setTextureMode(1)
         assert pf.matchFromHost(np.frombuffer(b"xxABxx", dtype=np.uint8)).tolist() == [0, 0, 1, 0, 0, 0]
+
+
+def test_reduce_repeated_large_is_stable(cuda, tmp_path):
+    """Many rounds of CTA tiles (ring-slot reuse in the reduce kernel), repeated calls: the list
+    must equal the compaction of the dense result every time."""
+    from pfac_b200 import PFAC
+    pats = synth.patterns_c2(1000)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    n = (96 << 20) + 4099
+    text = synth.make_text("random", 31337, 0, n, n, pats, 1024)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        d_in = torch.from_numpy(text).to(cuda)
+        d_out = torch.empty(n, dtype=torch.int32, device=cuda)
+        pf.matchFromDevice(d_in, n, d_out)
+        torch.cuda.synchronize()
+        want_pos = torch.nonzero(d_out).flatten()
+        want_id = d_out[want_pos]
+        assert want_pos.numel() > 90_000
+        d_id = torch.empty(n // 8, dtype=torch.int32, device=cuda)
+        d_pos = torch.empty(n // 8, dtype=torch.int64, device=cuda)
+        for rep in range(12):
+            m = pf.matchFromDeviceReduce64(d_in, n, d_id, d_pos)
+            assert m == want_pos.numel()
+            assert torch.equal(d_pos[:m], want_pos), "rep %d: positions differ" % rep
+            assert torch.equal(d_id[:m], want_id), "rep %d: ids differ" % rep
+    # and the dense result itself against the oracle on a prefix
+    orc = _oracle(pfile)
+    k = 4 << 20
+    assert np.array_equal(d_out[:k].cpu().numpy(), orc.match_shard(text[:k + 64], k))
