@@ -271,7 +271,7 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
     const unsigned lt_mask = (1u << lane) - 1u;
     int head = 0;
     bool active = false;
-    bool wrote = false;  // dense: this lane patched a non-zero id into wres
+    bool wrote = false;  // this lane produced a non-zero id
     int pl = 0, d = 0, limit = 0, best = 0, slot = 0;
     uint32_t v = kEmpty;
     auto text_byte = [&](int at) -> uint32_t { return (at < stage_bytes) ? inb[at] : gin[at]; };
@@ -369,6 +369,7 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
                     if (best) { wres[pl] = best; wrote = true; }
                 } else {
                     wres[slot] = best;
+                    wrote = wrote || (best != 0);
                 }
                 active = false;
             }
@@ -509,20 +510,22 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 // =================================================================================================
 // Reduce kernel: fused match + ordered stream compaction, one pass.
 //
-// Same warp-autonomous pipeline as the dense kernel (persistent 32-warp CTA per SM, per-warp TMA
-// input stages, prefilter, queue, walk).  Ordering:
-//   * "CTA tile" c = 32 consecutive warp tiles (16 KB of input); CTA b handles c = r*G + b in
-//     round r (G = grid).  The launch is cooperative, so all G CTAs are co-resident.
-//   * each warp deposits its match count in a shared-memory ring slot and arrives; the last warp
-//     to arrive is the CTA tile's leader: it publishes the tile aggregate, reads the aggregates
-//     of the same round's earlier CTAs (all loads in flight at once: one L2 round trip) and the
-//     running total of all earlier rounds, and posts the CTA tile's base in the ring slot.  The
-//     last CTA to finish a round publishes the next running total.
-//   * warps do not wait for the base: they keep the tile's compacted matches in a small pending
-//     buffer, match the next tile, and only then write (id, position) pairs at
-//     base + (counts of lower warps) -- by then the base is normally there.
-// shared memory: [mbarriers][root | pre2 | rank2][ring 4 slots][per warp: queue 1K | ids 2K |
-// pending 768 B | NSTAGE input stages][next2][hot][chains][tails]
+// Same warp-autonomous pipeline as the dense kernel (persistent CTA per SM, per-warp TMA input
+// stages, prefilter, queue, walk), with 31 matcher warps and one scanner warp per CTA.  Ordering:
+//   * "CTA tile" c = 31 consecutive warp tiles; CTA b handles c = r*G + b in round r (G = grid).
+//     The launch is cooperative, so all G CTAs are co-resident and may wait on each other.
+//   * a matcher deposits its tile's match count in a shared-memory ring slot, arrives, parks the
+//     compacted (id, position) pairs in a small FIFO and goes on matching; it writes a parked
+//     round's pairs at base + (counts of lower warps) once the scanner has posted the base, and
+//     never runs more than kLag rounds ahead of the scanner.
+//   * the scanner publishes each round's CTA-tile aggregate as soon as all 31 counts are in
+//     (one store for the same round's later CTAs, one 64-bit atomic {1 CTA, matches} into the
+//     round word) and, independently, resolves bases in order: base(r, b) = matches of rounds < r
+//     (round words with every CTA accounted for) + aggregates of CTAs < b in round r, all read
+//     with the loads in flight at once.  No CTA publishes a prefix for the others, so rounds are
+//     not chained through a single writer.
+// shared memory: [mbarriers][root | pre2 | rank2][ring][per matcher: queue 1K | ids 2K |
+// pending 768 B | 2 input stages][next2][hot][chains][tails]
 // =================================================================================================
 constexpr int kRedWarps = 32;                  // 31 matcher warps + 1 scanner warp
 constexpr int kRedMatchers = kRedWarps - 1;
@@ -536,7 +539,8 @@ constexpr int kLag = 6;                        // a matcher may run this many ro
 // finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
 constexpr int kRing = 16;                      // arrival ring slots
 constexpr int kPendCap = 128;                  // matches a warp can park while bases are computed
-constexpr int kPendRecs = 4;                   // ... spread over at most this many rounds
+constexpr int kPendRecs = 4;                   // ... spread over at most this many rounds (power of two)
+constexpr int kPendRecBytes = kPendRecs * 16;  // {round, n, tile start (u64)} per record
 constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base | before
 constexpr int kRingBytes = kRing * kSlotBytes;
 static_assert(kRing >= 2 * kLag + 1 && (kRing & (kRing - 1)) == 0, "ring size");
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     constexpr int NSTAGE = kRedStages;
     extern __shared__ __align__(128) unsigned char smem[];
     const int stage = kWarpTile + p.halo;
-    const int per_warp = kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + NSTAGE * stage;
+    const int per_warp = kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + kPendRecBytes + NSTAGE * stage;
     constexpr int kBarBytes = ((kRedWarps * NSTAGE * 8 + 127) / 128) * 128;
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
     unsigned char* s_fixed = smem + kBarBytes;
@@ -607,14 +611,15 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     // rounds this CTA takes part in: r with r*G + b < num_ctiles
     const uint32_t my_rounds = (num_ctiles > b) ? (num_ctiles - b + G - 1) / G : 0;
     unsigned long long* g_desc = p.desc;                      // [num_ctiles] aggregate per CTA tile
-    unsigned long long* g_rt = p.desc + num_ctiles;           // [num_rounds] inclusive total of rounds <= r
-    unsigned long long* g_rs = g_rt + num_rounds;             // [num_rounds] {CTAs published, matches} of round r
+    unsigned long long* g_rs = p.desc + num_ctiles;           // [num_rounds] {CTAs published, matches} of round r
 
     if (warp == kRedMatchers) {
         // ======================= scanner warp: publishes aggregates, resolves bases ==================
         // Never blocks on one round: publishing round r (needs only this CTA's counts) is not held up
         // by resolving an earlier round (needs other CTAs' aggregates and the previous round total).
         uint32_t pub_r = 0, res_r = 0;
+        unsigned long long run_total = 0;  // matches of all rounds < res_r - 1 (lane 0)
+        auto round_size = [&](uint32_t r) -> uint32_t { return (r + 1 < num_rounds) ? G : (num_ctiles - r * G); };
         while (res_r < my_rounds) {
             bool progress = false;
             if (pub_r < my_rounds) {
@@ -627,9 +632,8 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                     if (lane == 0) {
                         const unsigned long long ttotal = static_cast<unsigned long long>(c);
                         st_relaxed_u64(g_desc + pub_r * G + b, kStatusAgg | ttotal);
-                        slot->before = atomicAdd(g_rs + pub_r, (1ull << kRoundShift) | ttotal);
-                        slot->counts[kRedMatchers] = c;  // this CTA tile's total
-                        slot->arrived = 0;               // matchers are at most kLag rounds ahead
+                        atomicAdd(g_rs + pub_r, (1ull << kRoundShift) | ttotal);
+                        slot->arrived = 0;  // matchers are at most kLag rounds ahead
                     }
                     __syncwarp();
                     pub_r++;
@@ -638,7 +642,9 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             }
             if (res_r < pub_r) {
                 const uint32_t r = res_r;
-                // everything needed: aggregates of the same round's earlier CTAs + total of earlier rounds
+                // needed: aggregates of the same round's earlier CTAs, and the previous round's word
+                // with every CTA accounted for (its total then completes the running prefix: no CTA
+                // has to publish a prefix for the others, so there is no serial chain between rounds)
                 unsigned long long part = 0;
                 bool have = true;
                 for (uint32_t k = lane; k < b; k += 32) {
@@ -647,10 +653,13 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                     part += v & kValueMask;
                 }
                 unsigned long long prev = 0;
-                if (r > 0 && lane == 0) {
-                    const unsigned long long v = ld_relaxed_u64(g_rt + (r - 1));
-                    have = have && ((v >> 62) != 0);
-                    prev = v & kValueMask;
+                if (lane == 0) {
+                    prev = run_total;
+                    if (r > 0) {
+                        const unsigned long long v = ld_relaxed_u64(g_rs + (r - 1));
+                        have = have && ((v >> kRoundShift) == round_size(r - 1));
+                        prev += v & kRoundMask;
+                    }
                 }
                 if (__all_sync(0xffffffffu, have)) {
 #pragma unroll
@@ -660,14 +669,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                         slot->base = prev + part;
                         __threadfence_block();
                         slot->ready = static_cast<int>(r + 1);
-                        const uint32_t in_round = (r + 1 < num_rounds) ? G : (num_ctiles - r * G);
-                        const unsigned long long before = slot->before;
-                        if ((before >> kRoundShift) == in_round - 1) {  // this CTA completed round r
-                            const unsigned long long incl =
-                                prev + (before & kRoundMask) + static_cast<unsigned long long>(slot->counts[kRedMatchers]);
-                            st_relaxed_u64(g_rt + r, kStatusIncl | incl);
-                            if (r + 1 == num_rounds) *p.total = incl;
-                        }
+                        run_total = prev;
                     }
                     __syncwarp();
                     res_r++;
@@ -675,6 +677,14 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                 }
             }
             if (!progress) __nanosleep(40);
+        }
+        if (b == 0 && lane == 0) {  // CTA 0 takes part in every round: it owns the grand total
+            unsigned long long v = ld_relaxed_u64(g_rs + (num_rounds - 1));
+            while ((v >> kRoundShift) != round_size(num_rounds - 1)) {
+                __nanosleep(40);
+                v = ld_relaxed_u64(g_rs + (num_rounds - 1));
+            }
+            *p.total = run_total + (v & kRoundMask);
         }
         return;
     }
@@ -685,7 +695,9 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     int* wids = reinterpret_cast<int*>(mine + kWarpTile * 2);
     int* pend_id = reinterpret_cast<int*>(mine + kWarpTile * 6);                                      // ring of kPendCap
     unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kWarpTile * 6 + kPendCap * 4);  // ring of kPendCap
-    unsigned char* s_in = mine + kWarpTile * 6 + kPendCap * 6;
+    struct PendRec { uint32_t round; int n; unsigned long long start; };
+    PendRec* recs = reinterpret_cast<PendRec*>(mine + kWarpTile * 6 + kPendCap * 6);  // ring of kPendRecs
+    unsigned char* s_in = mine + kWarpTile * 6 + kPendCap * 6 + kPendRecBytes;
     const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kWarpTile);
 
     auto issue_load = [&](uint32_t t, int st) {
@@ -732,23 +744,18 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     };
 
     // pending FIFO: matches of up to kPendRecs earlier rounds wait here for their CTA tile's base
-    uint32_t rec_round[kPendRecs];
-    int rec_n[kPendRecs];
-    size_t rec_start[kPendRecs];
-    int nrec = 0;         // records in use; record 0 is the oldest
+    int nrec = 0;         // records in use
+    int rec_head = 0;     // ring index of the oldest record
     int pend_head = 0;    // ring index of the oldest parked entry
     int pend_used = 0;
+    auto oldest_round = [&]() -> uint32_t { return recs[rec_head].round; };
     auto pop_oldest = [&]() {  // caller made sure its round is ready
-        write_out(rec_round[0], pend_id, pend_pos, pend_head, rec_n[0], kPendCap - 1, rec_start[0]);
+        const PendRec rec = recs[rec_head];
+        write_out(rec.round, pend_id, pend_pos, pend_head, rec.n, kPendCap - 1, static_cast<size_t>(rec.start));
         __syncwarp();
-        pend_head = (pend_head + rec_n[0]) & (kPendCap - 1);
-        pend_used -= rec_n[0];
-#pragma unroll
-        for (int i = 0; i + 1 < kPendRecs; i++) {
-            rec_round[i] = rec_round[i + 1];
-            rec_n[i] = rec_n[i + 1];
-            rec_start[i] = rec_start[i + 1];
-        }
+        pend_head = (pend_head + rec.n) & (kPendCap - 1);
+        pend_used -= rec.n;
+        rec_head = (rec_head + 1) & (kPendRecs - 1);
         nrec--;
     };
 
@@ -782,10 +789,11 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             }
             const int wtotal = push_survivors(cand, lb, q16, lane);
             __syncwarp();
-            walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane);
+            const bool any_match = __any_sync(
+                0xffffffffu, walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
             __syncwarp();
             // in-place ordered compaction of (position, id) to the front of q16 / wids
-            for (int base = 0; base < wtotal; base += 32) {
+            for (int base = 0; any_match && base < wtotal; base += 32) {
                 const int i = base + lane;
                 const int id = (i < wtotal) ? wids[i] : 0;
                 const unsigned short pos = (i < wtotal) ? q16[i] : static_cast<unsigned short>(0);
@@ -815,15 +823,15 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
         }
 
         // ---- write parked matches whose base has arrived; park (or write) this round's ----------------
-        while (nrec > 0 && round_ready(rec_round[0])) pop_oldest();
+        while (nrec > 0 && round_ready(oldest_round())) pop_oldest();
         if (nmatch > kPendCap) {
-            while (nrec > 0) { wait_ready(rec_round[0], "drain"); pop_oldest(); }
+            while (nrec > 0) { wait_ready(oldest_round(), "drain"); pop_oldest(); }
             wait_ready(r, "direct");
             write_out(r, wids, q16, 0, nmatch, 0x7fffffff, start);  // too many to park
             __syncwarp();
         } else if (nmatch > 0) {
             while (nrec == kPendRecs || pend_used + nmatch > kPendCap) {
-                wait_ready(rec_round[0], "room");
+                wait_ready(oldest_round(), "room");
                 pop_oldest();
             }
             const int tail = (pend_head + pend_used) & (kPendCap - 1);
@@ -833,20 +841,19 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                 pend_pos[e] = q16[i];
             }
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < kPendRecs; i++) {
-                if (i == nrec) {
-                    rec_round[i] = r;
-                    rec_n[i] = nmatch;
-                    rec_start[i] = start;
-                }
+            if (lane == 0) {
+                PendRec& rec = recs[(rec_head + nrec) & (kPendRecs - 1)];
+                rec.round = r;
+                rec.n = nmatch;
+                rec.start = static_cast<unsigned long long>(start);
             }
+            __syncwarp();
             nrec++;
             pend_used += nmatch;
         }
     }
     while (nrec > 0) {
-        wait_ready(rec_round[0], "final");
+        wait_ready(oldest_round(), "final");
         pop_oldest();
     }
 }
@@ -873,7 +880,7 @@ size_t denseFixedBytes(int halo) {
 size_t reduceFixedBytes(int halo) {
     const size_t bar = size_t((kRedWarps * kRedStages * 8 + 127) / 128) * 128;
     return bar + kFixedTableBytes + kRingBytes +
-           size_t(kRedMatchers) * (kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + kRedStages * (kWarpTile + halo));
+           size_t(kRedMatchers) * (kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + kPendRecBytes + kRedStages * (kWarpTile + halo));
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
