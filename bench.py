@@ -225,6 +225,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # NCCL prints its version / debug lines to stdout by default: keep stdout for the JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from pfac_b200 import PFAC

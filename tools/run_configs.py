@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""Runs one BASELINE.json config end to end: generate the synthetic workload, check the CUDA
+path bit-exactly against the oracle (chunked, so inputs >= 2^31 bytes work), time it, and print
+one JSON line (also appended to gpurun_out/configs.jsonl).
+
+    python tools/run_configs.py --config c2|c3|c4|c4dense|c5 [--bytes N] [--check-bytes M] [--steps K]
+    python -m torch.distributed.run --nproc-per-node 8 ... tools/run_configs.py --config c5
+
+Configs:
+  c2       1,000 patterns len 4-32 (255-symbol alphabet), 1 GiB planted random text, dense
+  c3       20,000 Snort-like patterns, 4 GiB ASCII-weighted text, dense (64-bit indexing)
+  c4       DNA, 5,000 patterns len 8-24, 2e9 bytes, reduce (both perf modes), natural density
+  c4dense  c4 + 64 short patterns (len 4-6): high match density compaction
+  c5       10,000 Snort-like patterns, 32 GiB sharded over the ranks, reduce + global offset scan
+The oracle is test infrastructure (oracle/); the timed path is libpfac.so only.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from pfac_b200 import synth  # noqa: E402
+from pfac_b200.sharding import shard_bounds  # noqa: E402
+
+GIB = 1 << 30
+
+CONFIGS = {
+    "c2": dict(patterns=lambda: synth.patterns_c2(1000), kind="random", seed=synth.SEED_BASE + 2,
+               bytes=GIB, every=4096, api="dense"),
+    "c3": dict(patterns=lambda: synth.patterns_snort_like(20000), kind="ascii", seed=synth.SEED_BASE + 3,
+               bytes=4 * GIB, every=2048, api="dense"),
+    "c4": dict(patterns=lambda: synth.patterns_dna(5000), kind="dna", seed=synth.SEED_BASE + 4,
+               bytes=2_000_000_000, every=0, api="reduce"),
+    "c4dense": dict(patterns=lambda: synth.patterns_dna(5000, short=64), kind="dna", seed=synth.SEED_BASE + 4,
+                    bytes=2_000_000_000, every=0, api="reduce"),
+    "c5": dict(patterns=lambda: synth.patterns_snort_like(10000, seed=synth.SEED_BASE + 5), kind="ascii",
+               seed=synth.SEED_BASE + 5, bytes=32 * GIB, every=2048, api="reduce64"),
+}
+
+
+def gen_text(kind, seed, start, n, total_len, pats, every):
+    out = np.empty(n, dtype=np.uint8)
+    piece = 64 << 20
+    for off in range(0, n, piece):
+        m = min(piece, n - off)
+        if kind == "random":
+            out[off:off + m] = synth.random_bytes(seed, start + off, m)
+        elif kind == "ascii":
+            out[off:off + m] = synth.ascii_weighted_bytes(seed, start + off, m)
+        else:
+            out[off:off + m] = synth.dna_bytes(seed, start + off, m)
+    if every:
+        synth.plant(out, start, total_len, pats, seed, every=every)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=sorted(CONFIGS))
+    ap.add_argument("--bytes", type=int, default=0, help="override the total input size")
+    ap.add_argument("--check-bytes", type=int, default=-1,
+                    help="bytes per rank to verify against the oracle (-1 = all, 0 = none)")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--perf-mode", type=int, default=0)
+    args = ap.parse_args()
+
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    import torch
+    import torch.distributed as dist
+    from oracle import Oracle
+    from pfac_b200 import PFAC
+    from pfac_b200.sharding import allgather_count_offsets
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = CONFIGS[args.config]
+    total_len = args.bytes or cfg["bytes"]
+    pats = cfg["patterns"]()
+    tmp = tempfile.mkdtemp(prefix="pfac_cfg_")
+    pfile = synth.write_pattern_file(os.path.join(tmp, "p%d.txt" % rank), pats)
+    t0 = time.time()
+    pf = PFAC()
+    pf.readPatternFromFile(pfile)
+    compile_s = time.time() - t0
+    if args.perf_mode:
+        pf.setPerfMode(args.perf_mode)
+    info = pf.tableInfo()
+    maxlen = info["max_pattern_len"]
+
+    start, owned, total = shard_bounds(total_len, world, rank, maxlen)
+    t0 = time.time()
+    text = gen_text(cfg["kind"], cfg["seed"], start, total, total_len, pats, cfg["every"])
+    gen_s = time.time() - t0
+    d_in = torch.from_numpy(text).to(dev)
+    api = cfg["api"]
+    res = {"config": args.config, "api": api, "rank": rank, "world": world, "total_bytes": total_len,
+           "owned_bytes": owned, "patterns": len(pats), "states": info["num_states"],
+           "max_pattern_len": maxlen, "table": {k: info[k] for k in (
+               "hash_edges", "num_chains", "tail_bytes", "hot_depth", "hot_buckets", "cold_buckets",
+               "next2_hot", "chains_hot", "pre2_bits_set", "device_bytes")},
+           "compile_s": round(compile_s, 3), "gen_s": round(gen_s, 1), "perf_mode": args.perf_mode}
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- run + time ---------------------------------------------------------------------------
+    if api == "dense":
+        d_out = torch.empty(owned, dtype=torch.int32, device=dev)
+        run = lambda: pf.matchShardFromDevice(d_in, owned, total, d_out)  # noqa: E731
+    else:
+        cap = owned if args.config == "c4dense" else max(owned // 8, 1 << 20)
+        d_id = torch.empty(cap, dtype=torch.int32, device=dev)
+        pos64 = api == "reduce64" or owned >= 2 ** 31
+        d_pos = torch.empty(cap, dtype=torch.int64 if pos64 else torch.int32, device=dev)
+        if pos64:
+            run = lambda: pf.matchShardFromDeviceReduce64(d_in, owned, total, start, d_id, d_pos)  # noqa: E731
+        else:
+            run = lambda: pf.matchFromDeviceReduce(d_in, owned, d_id, d_pos)  # noqa: E731
+    for _ in range(3):
+        m = run()
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        m = run()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1) / args.steps if api == "dense" else wall / args.steps * 1e3
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    res["ms_per_step"] = ms_max
+    res["input_GBps_all_ranks"] = total_len / (ms_max * 1e-3) / 1e9
+
+    # ---- cross-GPU step for the reduced list ------------------------------------------------------
+    if api != "dense":
+        count = int(m)
+        if world > 1:
+            t0 = time.perf_counter()
+            off, total_m, counts = allgather_count_offsets(count, device=dev)
+            res["count_scan_ms"] = (time.perf_counter() - t0) * 1e3
+        else:
+            off, total_m = 0, count
+        res["matches_rank"] = count
+        res["matches_total"] = total_m
+        res["global_offset"] = off
+        res["algorithmic_bytes"] = owned + (12 if pos64 else 8) * count
+    else:
+        res["algorithmic_bytes"] = 5 * owned
+    res["roofline_frac_of_6548.5"] = res["algorithmic_bytes"] / (ms_max * 1e-3) / 1e9 / 6548.5
+
+    # ---- parity vs the oracle, chunked ---------------------------------------------------------------
+    check = owned if args.check_bytes < 0 else min(args.check_bytes, owned)
+    if check:
+        orc = Oracle(pfile)
+        chunk = 256 << 20
+        halo = maxlen - 1
+        nmis = 0
+        t0 = time.time()
+        g_ids, g_pos = [], []
+        for c0 in range(0, check, chunk):
+            c1 = min(c0 + chunk, check)
+            seg = text[c0:min(c1 + halo, total)]
+            want = orc.match_shard(seg, c1 - c0)
+            if api == "dense":
+                got = d_out[c0:c1].cpu().numpy()
+                nmis += int((got != want).sum())
+            else:
+                ids, pos = orc.reduce(want)
+                g_ids.append(ids)
+                g_pos.append(pos + c0 + (start if pos64 else 0))
+        if api != "dense":
+            w_ids = np.concatenate(g_ids)
+            w_pos = np.concatenate(g_pos)
+            k = w_ids.size
+            got_ids = d_id[:k].cpu().numpy()
+            got_pos = d_pos[:k].cpu().numpy().astype(np.int64)
+            if check == owned and k != count:
+                nmis += abs(k - count) + 1
+            nmis += int((got_ids != w_ids).sum()) + int((got_pos != w_pos).sum())
+            res["oracle_matches_checked"] = int(k)
+        res["checked_bytes"] = check
+        res["mismatches"] = nmis
+        res["oracle_s"] = round(time.time() - t0, 1)
+        res["bit_exact"] = nmis == 0
+    print(json.dumps(res), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "a") as f:
+        f.write(json.dumps(res) + "\n")
+    pf.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+    if check and not res["bit_exact"]:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
