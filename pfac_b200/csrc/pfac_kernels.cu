@@ -6,7 +6,7 @@
 // is new -- see DESIGN.md:
 //   * a 64-Kbit two-byte prefilter in shared memory rejects most start positions with one
 //     LDS; survivors are compacted into a per-warp queue;
-//   * lanes pull survivors from the queue and walk them (refill on early exit): root row and
+//   * survivors are walked 32 at a time (one per lane, until the batch's longest walk ends): root row and
 //     shallow ("hot") hash rows in shared memory, deep ("cold") rows through L1/L2, and
 //     path-compressed chains whose tail bytes are compared directly against the text;
 //   * dense kernel: one persistent 32-warp CTA per SM, every warp runs its own pipeline --
@@ -268,12 +268,7 @@ template <bool DENSE>
 __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
                                            const unsigned char* __restrict__ gin, int tile_rem,
                                            const unsigned short* q16, int wtotal, int* wres, int lane) {
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int head = 0;
-    bool active = false;
     bool wrote = false;  // this lane produced a non-zero id
-    int pl = 0, d = 0, limit = 0, best = 0, slot = 0;
-    uint32_t v = kEmpty;
     auto text_byte = [&](int at) -> uint32_t { return (at < stage_bytes) ? inb[at] : gin[at]; };
     // n (1..4) text bytes from `at`, little-endian, possibly with junk above byte n-1
     auto text_word = [&](int at, int n) -> uint32_t {
@@ -286,92 +281,90 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
         for (int k = 0; k < nn; k++) x |= text_byte(at + k) << (8 * k);
         return x;
     };
-    for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
-        if (need) {
-            const int my = head + __popc(need & lt_mask);
-            if (!active && my < wtotal) {
-                slot = my;
-                pl = q16[my];
-                const uint32_t c0 = inb[pl], c1 = inb[pl + 1];  // pl+1 is always staged (halo >= 16)
-                const int r = T.root[c0];                        // valid: the prefilter bit is set
-                best = (r <= T.num_final) ? r : 0;
-                limit = tile_rem - pl;                           // real input bytes from this position
-                v = kEmpty;
-                if (limit >= 2) {
-                    const uint32_t idx = c0 | (c1 << 8);
-                    const uint32_t word = T.pre2[idx >> 5];
-                    const uint32_t before = __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
-                    v = T.next2[T.rank2[idx >> 5] + before];
-                }
-                d = 1;
-                active = true;
-            }
-            head += __popc(need);
-        }
-        if (!__any_sync(0xffffffffu, active)) break;
+    // 32 survivors per batch, one per lane; the batch steps until its longest walk ends.  Most
+    // survivors die at their first step, so a batch is usually one trip through the loop.
+    for (int base = 0; base < wtotal; base += 32) {
+        const int slot = base + lane;
+        bool active = slot < wtotal;
+        int pl = 0, d = 1, limit = 0, best = 0;
+        uint32_t v = kEmpty;
         if (active) {
-            // v = the transition out of depth d (d bytes consumed): trap, chain or plain state
-            bool done = false;
-            uint32_t s = 0;
-            if (v == kEmpty) {
-                done = true;
-            } else if (v & kChainBit) {
-                const uint4 rec = T.chains[v & ~kChainBit];  // {tail offset, len, end|leaf, first 4 bytes}
-                const int len = static_cast<int>(rec.y);
-                if (d + 1 + len > limit) {
-                    done = true;  // cut off by the end of the input: nothing more to report
-                } else {
-                    const int at0 = pl + d + 1;
-                    {   // first 4 tail bytes travel inside the record: most candidates die here
-                        const uint32_t mask = (len >= 4) ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
-                        if ((text_word(at0, len) ^ rec.w) & mask) done = true;
-                    }
-                    // the rest 16 bytes per trip: four independent tail loads in flight at once
-                    const uint32_t* tw = reinterpret_cast<const uint32_t*>(T.tails + rec.x);
-                    for (int i = 4; i < len && !done; i += 16) {
-                        uint32_t t[4];
+            pl = q16[slot];
+            const uint32_t c0 = inb[pl], c1 = inb[pl + 1];  // pl+1 is always staged (halo >= 16)
+            const int r = T.root[c0];                        // valid: the prefilter bit is set
+            best = (r <= T.num_final) ? r : 0;
+            limit = tile_rem - pl;                           // real input bytes from this position
+            if (limit >= 2) {
+                const uint32_t idx = c0 | (c1 << 8);
+                const uint32_t word = T.pre2[idx >> 5];
+                const uint32_t before = __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
+                v = T.next2[T.rank2[idx >> 5] + before];
+            }
+        }
+        // v = the transition out of depth d (d bytes consumed): trap, chain or plain state
+        while (__any_sync(0xffffffffu, active)) {
+            if (active) {
+                bool done = false;
+                uint32_t s = 0;
+                if (v == kEmpty) {
+                    done = true;
+                } else if (v & kChainBit) {
+                    const uint4 rec = T.chains[v & ~kChainBit];  // {tail offset, len, end|leaf, first 4 bytes}
+                    const int len = static_cast<int>(rec.y);
+                    if (d + 1 + len > limit) {
+                        done = true;  // cut off by the end of the input: nothing more to report
+                    } else {
+                        const int at0 = pl + d + 1;
+                        {   // first 4 tail bytes travel inside the record: most candidates die here
+                            const uint32_t mask = (len >= 4) ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
+                            if ((text_word(at0, len) ^ rec.w) & mask) done = true;
+                        }
+                        // the rest 16 bytes per trip: four independent tail loads in flight at once
+                        const uint32_t* tw = reinterpret_cast<const uint32_t*>(T.tails + rec.x);
+                        for (int i = 4; i < len && !done; i += 16) {
+                            uint32_t t[4];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) t[k] = (i + 4 * k < len) ? tw[(i >> 2) + k] : 0u;
+                            for (int k = 0; k < 4; k++) t[k] = (i + 4 * k < len) ? tw[(i >> 2) + k] : 0u;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int n = len - (i + 4 * k);
-                            if (n > 0 && !done) {
-                                const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
-                                if ((text_word(at0 + i + 4 * k, n) ^ t[k]) & mask) done = true;
+                            for (int k = 0; k < 4; k++) {
+                                const int n = len - (i + 4 * k);
+                                if (n > 0 && !done) {
+                                    const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
+                                    if ((text_word(at0 + i + 4 * k, n) ^ t[k]) & mask) done = true;
+                                }
                             }
                         }
+                        if (!done) {
+                            s = rec.z & ~kChainBit;
+                            d += 1 + len;
+                            if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                            if (rec.z & kChainBit) done = true;  // leaf: no out-edges
+                        }
                     }
-                    if (!done) {
-                        s = rec.z & ~kChainBit;
-                        d += 1 + len;
-                        if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
-                        if (rec.z & kChainBit) done = true;  // leaf: no out-edges
+                } else {
+                    s = v;
+                    if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                    d++;
+                }
+                if (!done) {
+                    if (d >= limit) {
+                        done = true;
+                    } else {
+                        const uint32_t key = (s << 8) | text_byte(pl + d);
+                        v = (d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
+                                              : probe_cold(T.cold, T.cold_buckets, T.mul, key);
+                        if (v == kEmpty) done = true;
                     }
                 }
-            } else {
-                s = v;
-                if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
-                d++;
-            }
-            if (!done) {
-                if (d >= limit) {
-                    done = true;
-                } else {
-                    const uint32_t key = (s << 8) | text_byte(pl + d);
-                    v = (d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
-                                          : probe_cold(T.cold, T.cold_buckets, T.mul, key);
-                    if (v == kEmpty) done = true;
+                if (done) {
+                    if (DENSE) {
+                        if (best) { wres[pl] = best; wrote = true; }
+                    } else {
+                        wres[slot] = best;
+                        wrote = wrote || (best != 0);
+                    }
+                    active = false;
                 }
-            }
-            if (done) {
-                if (DENSE) {
-                    if (best) { wres[pl] = best; wrote = true; }
-                } else {
-                    wres[slot] = best;
-                    wrote = wrote || (best != 0);
-                }
-                active = false;
             }
         }
     }
