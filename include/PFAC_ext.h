@@ -71,7 +71,10 @@ typedef struct {
     int num_chains;        /* compressed single-child runs (tail compared byte-wise) */
     int tail_bytes;        /* bytes of chain tails (padded) */
     int chains_hot;        /* 1: chain records and tails also live in shared memory */
-    int next2_hot;         /* 1: the direct depth-2 table lives in shared memory */
+    int next2_hot;         /* 1: the direct K-gram table lives in shared memory */
+    int code_bits;         /* b: bits per symbol in the prefilter index (8, 4 or 2) */
+    int gram_len;          /* K = 16 / b symbols covered by the prefilter + direct table */
+    int has_best2;         /* 1: patterns shorter than K exist (best2 array present) */
     int max_depth;
     int hot_depth;         /* edges whose source state has depth in [1,hot_depth) are "hot" */
     unsigned hot_buckets;  /* 16-byte buckets (2 slots) of the shared-memory hash rows */
@@ -92,7 +95,7 @@ PFAC_status_t PFAC_tableDump(PFAC_table_t table, FILE *fp);
 PFAC_status_t PFAC_tableDumpToFile(PFAC_table_t table, const char *filename);
 PFAC_status_t PFAC_tableGetInfo(PFAC_table_t table, PFAC_tableInfo_t *info);
 /* read-only views of the layout arrays (valid until PFAC_tableDestroy):
- * root: 256 int; pre2: 2048 unsigned (bit idx=c0|c1<<8 at word idx>>5, bit 31-(idx&31));
+ * root: 256 int; pre2: 2048 unsigned (bit idx = sum code(c_i)<<(b*i) at word idx>>5, bit 31-(idx&31));
  * rank2: 2048 unsigned short prefix popcounts; next2: pre2_bits_set unsigned (state, chain
  * reference or 0xFFFFFFFF); hot/cold: 4 unsigned per bucket {key0,val0,key1,val1} (val bit 31
  * set = chain index); chains: 4 unsigned per record {tail offset, len, end state | leaf bit
@@ -101,6 +104,10 @@ PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int **root, const un
                                   const unsigned short **rank2, const unsigned **next2,
                                   const unsigned **hot, const unsigned **cold,
                                   const unsigned **chains, const unsigned char **tails);
+/* lut: 256 bytes (symbol code | 0x80 = byte in no pattern); best2: parallel to next2, NULL when
+ * has_best2 == 0 */
+PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut,
+                                   const unsigned **best2);
 
 /* info / dump-to-path for a live handle */
 PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);

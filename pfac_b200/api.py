@@ -56,7 +56,8 @@ class TableInfo(ctypes.Structure):
                 ("num_leaves", ctypes.c_int), ("num_edges", ctypes.c_int),
                 ("hash_edges", ctypes.c_int), ("num_chains", ctypes.c_int),
                 ("tail_bytes", ctypes.c_int), ("chains_hot", ctypes.c_int),
-                ("next2_hot", ctypes.c_int),
+                ("next2_hot", ctypes.c_int), ("code_bits", ctypes.c_int),
+                ("gram_len", ctypes.c_int), ("has_best2", ctypes.c_int),
                 ("max_depth", ctypes.c_int), ("hot_depth", ctypes.c_int),
                 ("hot_buckets", ctypes.c_uint), ("cold_buckets", ctypes.c_uint),
                 ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
@@ -121,6 +122,7 @@ def load_library():
         "PFAC_tableDumpToFile": [vp, cp],
         "PFAC_tableGetInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_tableGetLayout": [vp] + [ctypes.POINTER(vp)] * 8,
+        "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 2,
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
     }
     for name, args in sig.items():
@@ -326,6 +328,8 @@ class TableCompiler:
         ptrs = [ctypes.c_void_p() for _ in range(8)]
         _check(self._L.PFAC_tableGetLayout(self._t, *[ctypes.byref(p) for p in ptrs]),
                "PFAC_tableGetLayout")
+        p2 = [ctypes.c_void_p() for _ in range(2)]
+        _check(self._L.PFAC_tableGetLayout2(self._t, *[ctypes.byref(p) for p in p2]), "PFAC_tableGetLayout2")
         info = self.info()
 
         def arr(p, nbytes, dt):
@@ -342,5 +346,8 @@ class TableCompiler:
             "cold": arr(ptrs[5], info["cold_buckets"] * 16, np.uint32).reshape(-1, 4),
             "chains": arr(ptrs[6], max(info["num_chains"], 1) * 16, np.uint32).reshape(-1, 4),
             "tails": arr(ptrs[7], info["tail_bytes"], np.uint8),
+            "lut": arr(p2[0], 256, np.uint8),
+            "best2": arr(p2[1], max(info["pre2_bits_set"], 1) * 4 if info["has_best2"] else 0, np.uint32),
+            "code_bits": info["code_bits"], "gram_len": info["gram_len"],
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
         }

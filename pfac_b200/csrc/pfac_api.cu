@@ -129,7 +129,12 @@ PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::D
     PFAC_UP(root, const int32_t*, L.root, sizeof(L.root))
     PFAC_UP(pre2, const uint32_t*, L.pre2.data(), L.pre2.size() * 4)
     PFAC_UP(rank2, const unsigned short*, L.rank2.data(), L.rank2.size() * 2)
+    PFAC_UP(lut, const unsigned char*, L.lut, sizeof(L.lut))
     PFAC_UP(next2, const uint32_t*, L.next2.data(), L.next2.size() * 4)
+    PFAC_UP(best2, const uint32_t*, L.best2.data(), L.best2.size() * 4)
+    t.hasBest2 = !L.best2.empty();
+    t.codeBits = L.codeBits;
+    t.gramLen = L.gramLen;
     PFAC_UP(hot, const uint4*, L.hot.data(), L.hot.size() * 4)
     PFAC_UP(cold, const uint4*, L.cold.data(), L.cold.size() * 4)
     PFAC_UP(chains, const uint4*, L.chains.data(), L.chains.size() * 4)
@@ -571,6 +576,9 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->tail_bytes = int(L.tails.size());
     info->chains_hot = L.chainsHot ? 1 : 0;
     info->next2_hot = L.next2Hot ? 1 : 0;
+    info->code_bits = L.codeBits;
+    info->gram_len = L.gramLen;
+    info->has_best2 = L.best2.empty() ? 0 : 1;
     info->max_depth = L.maxDepth;
     info->hot_depth = L.hotDepth;
     info->hot_buckets = L.hotBuckets;
@@ -645,6 +653,13 @@ PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int** root, const un
     if (cold) *cold = table->layout.cold.data();
     if (chains) *chains = table->layout.chains.data();
     if (tails) *tails = table->layout.tails.data();
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char** lut, const unsigned** best2) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    if (lut) *lut = table->layout.lut;
+    if (best2) *best2 = table->layout.best2.empty() ? nullptr : table->layout.best2.data();
     return PFAC_STATUS_SUCCESS;
 }
 

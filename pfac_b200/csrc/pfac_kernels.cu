@@ -29,6 +29,10 @@ constexpr int kPosPerThread = 16;
 constexpr int kWarpTile = 32 * kPosPerThread;  // 512 start positions per warp per iteration
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;       // empty hash slot / trap
 constexpr uint32_t kChainBit = 0x80000000u;
+constexpr int kChainByteShift = 23;               // chain reference: bits 23..30 = first tail byte
+constexpr uint32_t kChainIndexMask = (1u << kChainByteShift) - 1u;
+constexpr uint32_t kLeafPlainBit = 0x40000000u;  // plain state without out-edges
+constexpr unsigned kSlowFlag = 0x8000u;           // queue entry: walk from the root row (generic path)
 constexpr int kMaxSmem = 232448;               // 227 KB opt-in dynamic shared memory per CTA
 
 // ---- dense kernel geometry -------------------------------------------------------------------
@@ -55,12 +59,15 @@ struct KParams {
     const int32_t* root;
     const uint32_t* pre2;
     const unsigned short* rank2;
+    const unsigned char* lut;
     const uint32_t* next2;
+    const uint32_t* best2;
     const uint4* hot;
     const uint4* cold;
     const uint4* chains;
     const unsigned char* tails;
-    uint32_t next2_bytes;       // multiple of 16 (copied to smem when next2_hot)
+    uint32_t next2_bytes;       // multiple of 16 (copied to smem when next2_hot; best2 has the same size)
+    int has_best2;
     uint32_t hot_buckets;
     uint32_t cold_buckets;
     uint32_t chain_bytes;       // bytes of chain records (copied to smem when chains_hot)
@@ -81,7 +88,9 @@ struct Tables {
     const int* root;            // smem
     const uint32_t* pre2;       // smem
     const unsigned short* rank2;  // smem
+    const unsigned char* lut;   // smem: symbol code | 0x80 (byte in no pattern)
     const uint32_t* next2;      // smem or global
+    const uint32_t* best2;      // smem or global; nullptr when no pattern is shorter than K
     const uint4* hot;           // smem
     const uint4* cold;          // global
     const uint4* chains;        // smem or global
@@ -170,8 +179,8 @@ __device__ __forceinline__ uint32_t probe_cold(const uint4* __restrict__ tab, ui
 }
 
 // copy the compiled tables into shared memory (whole CTA), returns the walker's view.
-// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB;  s_var: [next2][hot buckets][chains][tails]
-constexpr int kFixedTableBytes = 1024 + 8192 + 4096;
+// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB | lut 256 B;  s_var: [next2][best2][hot buckets][chains][tails]
+constexpr int kFixedTableBytes = 1024 + 8192 + 4096 + 256;
 __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* s_fixed, unsigned char* s_var,
                                                int tid, int nthreads) {
     int* root = reinterpret_cast<int*>(s_fixed);
@@ -180,17 +189,27 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     for (int i = tid; i < 256; i += nthreads) root[i] = p.root[i];
     for (int i = tid; i < 8192 / 16; i += nthreads) pre2[i] = reinterpret_cast<const uint4*>(p.pre2)[i];
     for (int i = tid; i < 4096 / 16; i += nthreads) rank2[i] = reinterpret_cast<const uint4*>(p.rank2)[i];
+    uint4* lut = reinterpret_cast<uint4*>(s_fixed + 1024 + 8192 + 4096);
+    for (int i = tid; i < 256 / 16; i += nthreads) lut[i] = reinterpret_cast<const uint4*>(p.lut)[i];
     Tables t;
     t.root = root;
     t.pre2 = reinterpret_cast<const uint32_t*>(pre2);
     t.rank2 = reinterpret_cast<const unsigned short*>(rank2);
+    t.lut = reinterpret_cast<const unsigned char*>(lut);
     t.next2 = p.next2;
+    t.best2 = p.has_best2 ? p.best2 : nullptr;
     uint4* var = reinterpret_cast<uint4*>(s_var);
     if (p.next2_hot) {
         for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
             var[i] = reinterpret_cast<const uint4*>(p.next2)[i];
         t.next2 = reinterpret_cast<const uint32_t*>(var);
         var += p.next2_bytes / 16;
+        if (p.has_best2) {
+            for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
+                var[i] = reinterpret_cast<const uint4*>(p.best2)[i];
+            t.best2 = reinterpret_cast<const uint32_t*>(var);
+            var += p.next2_bytes / 16;
+        }
     }
     for (uint32_t i = tid; i < p.hot_buckets; i += nthreads) var[i] = p.hot[i];
     t.hot = var;
@@ -214,32 +233,76 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     return t;
 }
 
-// 16 consecutive start positions at inb[lb..]: one LDS.128 + one LDS.32 of text, one prefilter
-// LDS per position.  Bit q of the result = position lb+q survives.
-__device__ __forceinline__ uint32_t prefilter16(const unsigned char* inb, int lb, const uint32_t* s_pre2) {
-    uint32_t w[5];
-    const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    w[4] = *reinterpret_cast<const uint32_t*>(inb + lb + 16);
-    uint32_t cand = 0;
+// 16 consecutive start positions at inb[lb..].  The prefilter index of a position is K = 16/CODE
+// symbols of CODE bits each.  CODE == 8: the two text bytes themselves (one LDS.128 + one LDS.32
+// of text, one prefilter LDS per position).  CODE == 4 / 2: every byte goes through the symbol
+// lut once (code | 0x80 = byte in no pattern), the codes are packed into a bit stream and each
+// position's index is a 16-bit window of it; a window holding a byte outside the alphabet cannot
+// be indexed and is flagged for the generic path instead.
+// Bit q of `cand` = position lb+q survives the prefilter; bit q of `slow` = it needs the generic path.
+template <int CODE>
+__device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const Tables& T, uint32_t& cand,
+                                            uint32_t& slow) {
+    constexpr int K = 16 / CODE;
+    const uint32_t* s_pre2 = T.pre2;
+    cand = 0;
+    slow = 0;
+    if (CODE == 8) {
+        uint32_t w[5];
+        const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        w[4] = *reinterpret_cast<const uint32_t*>(inb + lb + 16);
 #pragma unroll
-    for (int k = 3; k >= 0; k--) {
+        for (int k = 3; k >= 0; k--) {
 #pragma unroll
-        for (int j = 3; j >= 0; j--) {
-            const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
+            for (int j = 3; j >= 0; j--) {
+                const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
+                const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
+                // the table stores bit idx at position 31-(idx&31): one shift brings it to bit 31,
+                // one funnel shift moves it into cand from the right
+                const uint32_t t = word << (x & 31u);
+                cand = __funnelshift_l(t, cand, 1);
+            }
+        }
+    } else {
+        constexpr int NBYTES = 16 + K - 1;            // 23 (CODE 2) or 19 (CODE 4)
+        constexpr int NWORDS = (NBYTES + 3) / 4;      // 6 or 5
+        constexpr int PER = 32 / CODE;                // symbols per 32-bit stream word
+        uint32_t w[6];
+        const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        w[4] = *reinterpret_cast<const uint32_t*>(inb + lb + 16);
+        w[5] = (NWORDS > 5) ? *reinterpret_cast<const uint32_t*>(inb + lb + 20) : 0u;
+        uint32_t st[3] = {0u, 0u, 0u};                // packed symbol codes
+        uint32_t bad = 0;                             // bit i: byte i is outside the alphabet
+#pragma unroll
+        for (int i = 0; i < NBYTES; i++) {
+            const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            const uint32_t e = T.lut[byte];
+            st[i / PER] |= (e & ((1u << CODE) - 1u)) << (CODE * (i % PER));
+            bad |= (e >> 7) << i;
+        }
+#pragma unroll
+        for (int q = 15; q >= 0; q--) {
+            const int wi = (q * CODE) / 32, sh = (q * CODE) % 32;
+            const uint32_t x = (sh == 0) ? st[wi] : __funnelshift_r(st[wi], st[wi + 1], sh);
             const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
-            // the table stores bit idx at position 31-(idx&31): one shift brings it to bit 31,
-            // one funnel shift moves it into cand from the right
             const uint32_t t = word << (x & 31u);
             cand = __funnelshift_l(t, cand, 1);
         }
+        if (bad) {  // rare: some window holds a byte that occurs in no pattern
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+                if ((bad >> q) & ((1u << K) - 1u)) slow |= 1u << q;
+            cand &= ~slow;
+        }
     }
-    return cand;
 }
 
 // exclusive offset of this lane's survivors in the warp queue + warp total; pushes positions
-__device__ __forceinline__ int push_survivors(uint32_t cand, int lb, unsigned short* q16, int lane) {
-    const int cnt = __popc(cand);
+__device__ __forceinline__ int push_survivors(uint32_t cand, uint32_t slow, int lb, unsigned short* q16, int lane) {
+    uint32_t all = cand | slow;
+    const int cnt = __popc(all);
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -248,10 +311,10 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, int lb, unsigned sh
     }
     const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
     int off = incl - cnt;
-    while (cand) {
-        const int b = __ffs(cand) - 1;
-        cand &= cand - 1;
-        q16[off++] = static_cast<unsigned short>(lb + b);
+    while (all) {
+        const int b = __ffs(all) - 1;
+        all &= all - 1;
+        q16[off++] = static_cast<unsigned short>((lb + b) | (((slow >> b) & 1u) ? kSlowFlag : 0u));
     }
     return wtotal;
 }
@@ -264,7 +327,7 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, int lb, unsigned sh
 // Per survivor: root row (is c0 alone a match?) -> next2[rank of (c0,c1)] (the walk after two
 // bytes, no hashing) -> then per step either a chain (tail compared 4 bytes at a time) or a
 // hash probe (hot rows in shared memory below hot_depth, cold rows through L1/L2).
-template <bool DENSE>
+template <bool DENSE, int CODE>
 __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
                                            const unsigned char* __restrict__ gin, int tile_rem,
                                            const unsigned short* q16, int wtotal, int* wres, int lane) {
@@ -283,22 +346,42 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
     };
     // 32 survivors per batch, one per lane; the batch steps until its longest walk ends.  Most
     // survivors die at their first step, so a batch is usually one trip through the loop.
+    constexpr int K = 16 / CODE;
     for (int base = 0; base < wtotal; base += 32) {
         const int slot = base + lane;
         bool active = slot < wtotal;
         int pl = 0, d = 1, limit = 0, best = 0;
         uint32_t v = kEmpty;
         if (active) {
-            pl = q16[slot];
-            const uint32_t c0 = inb[pl], c1 = inb[pl + 1];  // pl+1 is always staged (halo >= 16)
-            const int r = T.root[c0];                        // valid: the prefilter bit is set
-            best = (r <= T.num_final) ? r : 0;
+            const unsigned qe = q16[slot];
+            pl = qe & (kSlowFlag - 1u);
             limit = tile_rem - pl;                           // real input bytes from this position
-            if (limit >= 2) {
-                const uint32_t idx = c0 | (c1 << 8);
+            if (!(qe & kSlowFlag)) {
+                // prefilter index again (survivors are few), its rank, and the direct tables
+                uint32_t idx;
+                if (CODE == 8) {
+                    idx = inb[pl] | (static_cast<uint32_t>(inb[pl + 1]) << 8);  // pl+1 is always staged
+                } else {
+                    idx = 0;
+#pragma unroll
+                    for (int i = 0; i < K; i++)
+                        idx |= (T.lut[inb[pl + i]] & ((1u << CODE) - 1u)) << (CODE * i);
+                }
                 const uint32_t word = T.pre2[idx >> 5];
-                const uint32_t before = __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
-                v = T.next2[T.rank2[idx >> 5] + before];
+                const uint32_t rank = T.rank2[idx >> 5] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
+                if (CODE == 8) {  // K-1 = 1 symbol: the root row tells whether c0 alone is a pattern
+                    const int r = T.root[idx & 0xFFu];
+                    best = (r <= T.num_final) ? r : 0;
+                } else {
+                    best = T.best2 ? static_cast<int>(T.best2[rank]) : 0;  // longest pattern inside K-1 symbols
+                }
+                v = (limit >= K) ? T.next2[rank] : kEmpty;             // CODE 8: last byte of the input
+                d = K - 1;
+            } else {
+                // generic path: from the root row, hash rows for every further step
+                const int r = T.root[inb[pl]];
+                v = (r < 0) ? kEmpty : static_cast<uint32_t>(r);
+                d = 0;
             }
         }
         // v = the transition out of depth d (d bytes consumed): trap, chain or plain state
@@ -309,10 +392,15 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
                 if (v == kEmpty) {
                     done = true;
                 } else if (v & kChainBit) {
-                    const uint4 rec = T.chains[v & ~kChainBit];  // {tail offset, len, end|leaf, first 4 bytes}
+                    // the reference carries the chain's first tail byte: most false candidates end
+                    // here, before the record (usually an L2 access) is touched
+                    const bool first_ok =
+                        (d + 1 < limit) && text_byte(pl + d + 1) == ((v >> kChainByteShift) & 0xFFu);
+                    const uint4 rec = first_ok ? T.chains[v & kChainIndexMask]  // {tail offset, len, end|leaf, 4 bytes}
+                                               : make_uint4(0u, 0u, 0u, 0u);
                     const int len = static_cast<int>(rec.y);
-                    if (d + 1 + len > limit) {
-                        done = true;  // cut off by the end of the input: nothing more to report
+                    if (!first_ok || d + 1 + len > limit) {
+                        done = true;  // no match, or cut off by the end of the input
                     } else {
                         const int at0 = pl + d + 1;
                         {   // first 4 tail bytes travel inside the record: most candidates die here
@@ -342,17 +430,20 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
                         }
                     }
                 } else {
-                    s = v;
+                    s = v & ~kLeafPlainBit;
                     if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
                     d++;
+                    if (v & kLeafPlainBit) done = true;  // no out-edges
                 }
                 if (!done) {
                     if (d >= limit) {
                         done = true;
                     } else {
                         const uint32_t key = (s << 8) | text_byte(pl + d);
-                        v = (d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
-                                              : probe_cold(T.cold, T.cold_buckets, T.mul, key);
+                        // hot rows hold the edges of depth [K, hot_depth); the generic path's
+                        // shallow edges and everything deeper are cold
+                        v = (d >= K && d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
+                                                        : probe_cold(T.cold, T.cold_buckets, T.mul, key);
                         if (v == kEmpty) done = true;
                     }
                 }
@@ -388,7 +479,21 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <int NSTAGE>
+// positions of this thread whose K-symbol window would run past the end of the input cannot use
+// the prefilter (their padding is not text): route them to the generic path
+template <int CODE>
+__device__ __forceinline__ void clip_windows(int tile_rem, int lb, uint32_t& cand, uint32_t& slow) {
+    constexpr int K = 16 / CODE;
+    if (CODE != 8 && tile_rem < kWarpTile + K - 1) {
+        int nfast = tile_rem - (K - 1) - lb;  // leading positions of this thread with a full window
+        nfast = nfast < 0 ? 0 : (nfast > kPosPerThread ? kPosPerThread : nfast);
+        const uint32_t tail = 0xFFFFu & ~((1u << nfast) - 1u);
+        slow |= tail;
+        cand &= ~tail;
+    }
+}
+
+template <int NSTAGE, int CODE>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int stage = kWarpTile + p.halo;
@@ -458,15 +563,18 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
         const bool full = tile < full_tiles;
 
         const int lb = lane * kPosPerThread;
-        uint32_t cand = prefilter16(inb, lb, T.pre2);
+        uint32_t cand, slow;
+        prefilter16<CODE>(inb, lb, T, cand, slow);
+        clip_windows<CODE>(tile_rem, lb, cand, slow);
         int valid = kWarpTile;
         if (!full) {  // tail tile: drop positions we do not own
             valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
             int nv = valid - lb;
             nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
             cand &= (1u << nv) - 1u;
+            slow &= (1u << nv) - 1u;
         }
-        const int wtotal = push_survivors(cand, lb, q16, lane);
+        const int wtotal = push_survivors(cand, slow, lb, q16, lane);
 
         // the previous bulk store of this warp must have finished reading wres before it is
         // patched again; wres is all-zero here unless the previous tile had matches
@@ -478,7 +586,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
             __syncwarp();
         }
         dirty = __any_sync(0xffffffffu,
-                           walk_queue<true>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
+                           walk_queue<true, CODE>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
 
         int* gout = p.out + start;
         if (p.out_aligned && full) {
@@ -569,7 +677,7 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
 #define PFAC_SPIN_GUARD(n, what, a, b_, c)
 #endif
 
-template <bool POS64>
+template <bool POS64, int CODE>
 __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KParams p) {
     constexpr int NSTAGE = kRedStages;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -773,23 +881,27 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             const long long total_left = p.n_total - static_cast<long long>(start);
             const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
             const int lb = lane * kPosPerThread;
-            uint32_t cand = prefilter16(inb, lb, T.pre2);
+            uint32_t cand, slow;
+            prefilter16<CODE>(inb, lb, T, cand, slow);
+            clip_windows<CODE>(tile_rem, lb, cand, slow);
             if (tile >= full_tiles) {
                 const int valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
                 int nv = valid - lb;
                 nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
                 cand &= (1u << nv) - 1u;
+                slow &= (1u << nv) - 1u;
             }
-            const int wtotal = push_survivors(cand, lb, q16, lane);
+            const int wtotal = push_survivors(cand, slow, lb, q16, lane);
             __syncwarp();
             const bool any_match = __any_sync(
-                0xffffffffu, walk_queue<false>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
+                0xffffffffu, walk_queue<false, CODE>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
             __syncwarp();
             // in-place ordered compaction of (position, id) to the front of q16 / wids
             for (int base = 0; any_match && base < wtotal; base += 32) {
                 const int i = base + lane;
                 const int id = (i < wtotal) ? wids[i] : 0;
-                const unsigned short pos = (i < wtotal) ? q16[i] : static_cast<unsigned short>(0);
+                const unsigned short pos =
+                    (i < wtotal) ? static_cast<unsigned short>(q16[i] & (kSlowFlag - 1u)) : static_cast<unsigned short>(0);
                 const unsigned m = __ballot_sync(0xffffffffu, id != 0);
                 if (id != 0) {
                     const int o = nmatch + __popc(m & lt_mask);
@@ -877,7 +989,7 @@ size_t reduceFixedBytes(int halo) {
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
-    return (t.next2Hot ? size_t(t.next2Bytes) : 0) + size_t(t.hotBuckets) * 16 +
+    return (t.next2Hot ? size_t(t.next2Bytes) * (t.hasBest2 ? 2 : 1) : 0) + size_t(t.hotBuckets) * 16 +
            (t.chainsHot ? size_t(t.chainBytes) + t.tailBytes : 0);
 }
 
@@ -891,7 +1003,10 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
     p.root = t.root;
     p.pre2 = t.pre2;
     p.rank2 = t.rank2;
+    p.lut = t.lut;
     p.next2 = t.next2;
+    p.best2 = t.best2;
+    p.has_best2 = t.hasBest2 ? 1 : 0;
     p.next2_bytes = t.next2Bytes;
     p.next2_hot = t.next2Hot ? 1 : 0;
     p.hot = t.hot;
@@ -946,7 +1061,13 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
     const size_t smem = denseFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const int nst = denseStages(halo);
-    auto kernel = (nst == 3) ? pfac_dense_kernel<3> : pfac_dense_kernel<2>;
+    void (*kernel)(KParams) = nullptr;
+    switch (t.codeBits) {
+        case 8: kernel = (nst == 3) ? pfac_dense_kernel<3, 8> : pfac_dense_kernel<2, 8>; break;
+        case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4> : pfac_dense_kernel<2, 4>; break;
+        case 2: kernel = (nst == 3) ? pfac_dense_kernel<3, 2> : pfac_dense_kernel<2, 2>; break;
+        default: return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
@@ -979,7 +1100,13 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     }
     const size_t smem = reduceFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
-    const void* kernel = pos64 ? (const void*)pfac_reduce_kernel<true> : (const void*)pfac_reduce_kernel<false>;
+    const void* kernel = nullptr;
+    switch (t.codeBits) {
+        case 8: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8> : (const void*)pfac_reduce_kernel<false, 8>; break;
+        case 4: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 4> : (const void*)pfac_reduce_kernel<false, 4>; break;
+        case 2: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2> : (const void*)pfac_reduce_kernel<false, 2>; break;
+        default: return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kRedMatchers - 1) / kRedMatchers;

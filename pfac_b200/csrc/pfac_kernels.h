@@ -12,9 +12,14 @@ struct DeviceTable {
     const int32_t* root = nullptr;    // 256
     const uint32_t* pre2 = nullptr;   // 2048
     const unsigned short* rank2 = nullptr;  // 2048
+    const unsigned char* lut = nullptr;     // 256: symbol code | 0x80
     const uint32_t* next2 = nullptr;  // next2Bytes / 4 (padded to 16 bytes)
+    const uint32_t* best2 = nullptr;  // parallel to next2 (valid when hasBest2)
     uint32_t next2Bytes = 0;
-    bool next2Hot = false;            // kernels copy next2 into shared memory
+    bool next2Hot = false;            // kernels copy next2 (+ best2) into shared memory
+    bool hasBest2 = false;
+    int codeBits = 8;                 // bits per symbol of the prefilter index
+    int gramLen = 2;                  // symbols covered by the prefilter
     const uint4* hot = nullptr;       // hotBuckets (copied into shared memory by each CTA)
     const uint4* cold = nullptr;      // coldBuckets (read through L1/L2)
     const uint4* chains = nullptr;    // chain records (16 B each)

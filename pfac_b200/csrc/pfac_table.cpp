@@ -231,37 +231,41 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     }
     auto isFinal = [&](int s) { return s >= 1 && s <= m.numFinal; };
 
-    // ---- root row + prefilter.  Bit idx = c0 | c1<<8 is set iff a walk starting with c0,c1 can
-    // produce a result: root[c0] is a final state (1-byte pattern: any c1), or (root[c0], c1) is
-    // an edge.  Clear bit => result 0 with certainty; set bit => the walker decides.
-    auto setBit = [&](uint32_t idx) { L.pre2[idx >> 5] |= 0x80000000u >> (idx & 31); };
-    auto getBit = [&](uint32_t idx) { return (L.pre2[idx >> 5] << (idx & 31)) >> 31; };
+    // ---- root row --------------------------------------------------------------------------------
     if (!frontier.empty()) {
         for (const Edge& e : out[size_t(m.initialState)]) {
             L.root[e.ch] = e.next;
             L.rootFanout++;
-            const uint32_t c0 = uint32_t(e.ch);
-            if (isFinal(e.next))
-                for (uint32_t c1 = 0; c1 < 256; c1++) setBit(c0 | (c1 << 8));
-            for (const Edge& e2 : out[size_t(e.next)]) setBit(c0 | (uint32_t(e2.ch) << 8));
         }
     }
-    L.rank2.assign(2048, 0);
-    for (size_t w = 0; w < 2048; w++) {
-        L.rank2[w] = uint16_t(L.pre2BitsSet);  // <= 65504 for every word but the sum itself
-        L.pre2BitsSet += __builtin_popcount(L.pre2[w]);
-    }
 
-    // ---- hash edges with chain compression.  From every lookup source (root children, plain
-    // edge targets, chain ends) follow each out-edge; a run of >= kMinChain non-final
-    // single-child states behind it becomes one chain record whose tail bytes are compared
-    // directly against the text (independent loads) instead of one dependent lookup per byte.
+    // ---- symbol codes: b bits per symbol, K = 16/b symbols per prefilter index ---------------------
+    bool used[kCharSet] = {false};
+    int alphabet = 0;
+    for (size_t st = 0; st < S; st++)
+        for (const Edge& e : out[st])
+            if (!used[e.ch]) { used[e.ch] = true; alphabet++; }
+    L.codeBits = (alphabet <= 4) ? 2 : (alphabet <= 16) ? 4 : 8;
+    L.gramLen = 16 / L.codeBits;
+    const int K = L.gramLen, B = L.codeBits;
+    uint8_t byteOfCode[kCharSet];
+    int ncodes = 0;
+    for (int c = 0; c < kCharSet; c++) {
+        if (B == 8) { L.lut[c] = uint8_t(c); byteOfCode[c] = uint8_t(c); continue; }  // identity
+        if (used[c]) { byteOfCode[ncodes] = uint8_t(c); L.lut[c] = uint8_t(ncodes++); }
+        else L.lut[c] = 0x80;
+    }
+    if (B == 8) ncodes = 256;
+
+    // ---- hash edges with chain compression.  A run of >= kMinChain non-final single-child
+    // states behind an edge becomes one chain record whose tail bytes are compared directly
+    // against the text (independent loads) instead of one dependent lookup per byte.
     std::vector<FlatEdge> edges;
     std::vector<char> queued(S, 0);
     std::vector<int> sources;
     std::vector<uint8_t> tail;
-    // follow the edge s -ch-> e.next: returns the value to store (state or chain reference) and
-    // queues the state the walk stands in afterwards when it has out-edges of its own
+    // follow the edge e: returns the value to store (state or chain reference) and queues the
+    // state the walk stands in afterwards when it has out-edges of its own
     auto compress = [&](const Edge& e) -> uint32_t {
         int cur = e.next;
         tail.clear();
@@ -285,10 +289,10 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
             L.chains.push_back(uint32_t(tail.size()));
             L.chains.push_back(uint32_t(cur) | (leaf ? kLeafFlag : 0u));
             L.chains.push_back(inline4);
-            val = kChainFlag | idx;
+            val = kChainFlag | (uint32_t(tail[0]) << kChainByteShift) | idx;
             target = cur;
         } else {
-            val = uint32_t(e.next);
+            val = uint32_t(e.next) | (out[size_t(e.next)].empty() ? kLeafPlain : 0u);
             target = e.next;
         }
         if (!out[size_t(target)].empty() && !queued[size_t(target)]) {
@@ -297,24 +301,111 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
         }
         return val;
     };
-    // depth-1 transitions: direct-indexed through the prefilter's rank (no hashing)
-    L.next2.assign(size_t(std::max(L.pre2BitsSet, 1)), kTrap);
+    auto findEdge = [&](int st, int ch) -> const Edge* {
+        for (const Edge& e : out[size_t(st)]) if (e.ch == ch) return &e;
+        return nullptr;
+    };
+
+    // ---- K-gram prefilter + direct table: walk every K-gram over the pattern alphabet ------------
+    // outcome per gram: dies inside the K symbols (result = longest pattern seen, bit set iff
+    // non-zero), or alive after K symbols (bit set; next = the edge into the K-th state)
+    struct Gram { uint32_t idx; uint32_t next; uint32_t best; };
+    std::vector<Gram> grams;
     if (!frontier.empty()) {
-        for (const Edge& e : out[size_t(m.initialState)]) {
-            for (const Edge& e2 : out[size_t(e.next)]) {
-                const uint32_t idx = uint32_t(e.ch) | (uint32_t(e2.ch) << 8);
-                const uint32_t w = idx >> 5, b = idx & 31;
-                const uint32_t before = b ? uint32_t(__builtin_popcount(L.pre2[w] >> (32 - b))) : 0u;
-                L.next2[size_t(L.rank2[w]) + before] = compress(e2);
+        // depth-first over codes so that shared prefixes are walked once
+        struct Frame { int state; int best; };
+        std::vector<Frame> stack(size_t(K) + 1);
+        stack[0] = Frame{m.initialState, 0};
+        // iterative enumeration of all code strings of length K (codes < ncodes)
+        std::vector<int> pos(size_t(K), -1);
+        int depthNow = 0;
+        uint32_t idxNow = 0;
+        while (depthNow >= 0) {
+            if (depthNow == K) { depthNow--; continue; }
+            int& dgt = pos[size_t(depthNow)];
+            dgt++;
+            if (dgt >= ncodes) { dgt = -1; depthNow--; continue; }
+            idxNow = (idxNow & ((1u << (B * depthNow)) - 1u)) | (uint32_t(dgt) << (B * depthNow));
+            const Frame& f = stack[size_t(depthNow)];
+            const Edge* e = (f.state >= 0) ? findEdge(f.state, byteOfCode[dgt]) : nullptr;
+            if (!e) {
+                // the walk dies here: every completion of this prefix reports f.best
+                if (f.best != 0) {
+                    const int rest = K - depthNow - 1;
+                    uint64_t count = 1;
+                    for (int r = 0; r < rest; r++) count *= uint64_t(ncodes);
+                    for (uint64_t t = 0; t < count; t++) {
+                        uint32_t idx = idxNow & ((1u << (B * (depthNow + 1))) - 1u);
+                        uint64_t tt = t;
+                        for (int r = 0; r < rest; r++) {
+                            idx |= uint32_t(tt % uint64_t(ncodes)) << (B * (depthNow + 1 + r));
+                            tt /= uint64_t(ncodes);
+                        }
+                        grams.push_back(Gram{idx, kTrap, uint32_t(f.best)});
+                    }
+                }
+                continue;
             }
+            if (depthNow == K - 1) {
+                // alive after K symbols: the value of the edge into the K-th state
+                grams.push_back(Gram{idxNow, compress(*e), uint32_t(f.best)});
+                continue;
+            }
+            stack[size_t(depthNow) + 1] = Frame{e->next, isFinal(e->next) ? e->next : f.best};
+            depthNow++;
         }
     }
-    (void)getBit;
-    // deeper transitions: hash rows
+    std::sort(grams.begin(), grams.end(), [](const Gram& a, const Gram& b) { return a.idx < b.idx; });
+    auto setBit = [&](uint32_t idx) { L.pre2[idx >> 5] |= 0x80000000u >> (idx & 31); };
+    bool anyBest = false;
+    for (const Gram& g : grams) { setBit(g.idx); anyBest = anyBest || g.best != 0; }
+    L.rank2.assign(2048, 0);
+    for (size_t w = 0; w < 2048; w++) {
+        L.rank2[w] = uint16_t(L.pre2BitsSet);
+        L.pre2BitsSet += __builtin_popcount(L.pre2[w]);
+    }
+    L.next2.assign(std::max<size_t>(grams.size(), 1), kTrap);
+    // K == 2: the only pattern inside K-1 symbols is a 1-byte pattern, which the root row already
+    // tells (kernels read root[c0] instead): no best2 array, more shared memory for next2
+    if (K == 2) anyBest = false;
+    if (anyBest) L.best2.assign(L.next2.size(), 0u);
+    for (size_t i = 0; i < grams.size(); i++) {  // sorted by idx == rank order
+        L.next2[i] = grams[i].next;
+        if (anyBest) L.best2[i] = grams[i].best;
+    }
+
+    // deeper transitions (source depth >= K): hash rows, hot by depth
     for (size_t qi = 0; qi < sources.size(); qi++) {
         const int s = sources[qi];
         for (const Edge& e : out[size_t(s)])
             edges.push_back(FlatEdge{edgeKey(s, e.ch), int(compress(e)), depth[size_t(s)]});
+    }
+    // generic path (K > 2 only): walks that start with a byte outside the alphabet or too close
+    // to the end of the input go root row -> hash rows from depth 1.  Those edges are rarely
+    // used; they are given depth 0x7fff so that they always land in the cold table.
+    if (K > 2 && !frontier.empty()) {
+        std::vector<int> low;  // states of depth 1..K-1 with out-edges
+        for (const Edge& e : out[size_t(m.initialState)])
+            if (!out[size_t(e.next)].empty()) low.push_back(e.next);
+        for (size_t qi = 0; qi < low.size(); qi++) {
+            const int s = low[qi];
+            for (const Edge& e : out[size_t(s)]) {
+                const uint32_t val = uint32_t(e.next) | (out[size_t(e.next)].empty() ? kLeafPlain : 0u);
+                edges.push_back(FlatEdge{edgeKey(s, e.ch), int(val), 0x7fff});
+                if (depth[size_t(e.next)] < K && !out[size_t(e.next)].empty()) low.push_back(e.next);
+                else if (depth[size_t(e.next)] >= K && !out[size_t(e.next)].empty() && !queued[size_t(e.next)]) {
+                    // first reached through the generic path only: its out-edges must exist too
+                    queued[size_t(e.next)] = 1;
+                    const size_t before = sources.size();
+                    sources.push_back(e.next);
+                    for (size_t q2 = before; q2 < sources.size(); q2++) {
+                        const int s2 = sources[q2];
+                        for (const Edge& e2 : out[size_t(s2)])
+                            edges.push_back(FlatEdge{edgeKey(s2, e2.ch), int(compress(e2)), depth[size_t(s2)]});
+                    }
+                }
+            }
+        }
     }
     L.hashEdges = int(edges.size());
     while (L.tails.size() & 15) L.tails.push_back(0);
@@ -325,11 +416,15 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     std::stable_sort(edges.begin(), edges.end(),
                      [](const FlatEdge& a, const FlatEdge& b) { return a.depth < b.depth; });
     std::vector<size_t> upto(size_t(L.maxDepth) + 2, 0);  // upto[d] = #edges with depth < d
-    for (const FlatEdge& e : edges) upto[size_t(e.depth) + 1]++;
+    size_t genericOnly = 0;                               // depth 0x7fff: generic-path edges, never hot
+    for (const FlatEdge& e : edges) {
+        if (e.depth == 0x7fff) genericOnly++;
+        else upto[size_t(e.depth) + 1]++;
+    }
     for (size_t d = 1; d < upto.size(); d++) upto[d] += upto[d - 1];
     // shared-memory budget: next2 first (touched by every survivor), then hash rows by depth,
     // and chains + tails too when everything fits
-    const size_t next2Bytes = ((L.next2.size() * 4 + 15) / 16) * 16;
+    const size_t next2Bytes = ((L.next2.size() * 4 + 15) / 16) * 16 * (L.best2.empty() ? 1 : 2);
     if (next2Bytes <= hotBudgetBytes) {
         L.next2Hot = true;
         hotBudgetBytes -= next2Bytes;
@@ -338,7 +433,7 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     }
     const size_t chainBytes = L.chains.size() * 4 + L.tails.size();
     int H = 1;
-    if (L.next2Hot && edges.size() * 16 + chainBytes <= hotBudgetBytes) {
+    if (L.next2Hot && (edges.size() - genericOnly) * 16 + chainBytes <= hotBudgetBytes) {
         H = int(upto.size()) - 1;      // everything in shared memory, chains and tails too
         L.chainsHot = true;
     } else {

@@ -48,30 +48,45 @@ void dumpMachine(const Machine& m, FILE* fp);
 // What gets uploaded.
 //   hash rows: buckets of 4 x uint32 {key0, val0, key1, val1}; key = state<<8|ch; slot 0 is
 //     filled before slot 1; bucket = umulhi(key * mul, nbuckets); linear probing.
-//     val = next state, or kChainFlag | chain index when the edge starts a compressed chain.
+//     val = next state, or kChainFlag | first tail byte << kChainByteShift | chain index when the
+//     edge starts a compressed chain: the walker checks that one byte against the text before it
+//     fetches the chain record (which usually sits in L2), so most false candidates never do.
 //   chains: 4 x uint32 {tail offset (bytes, multiple of 4), len, end state | kLeafFlag,
 //     first 4 tail bytes}: after the edge's own byte, `len` more bytes must equal the tail; the
 //     walk then stands in the end state.  Chain interiors are non-final single-child states, so
 //     skipping them cannot change any result; kLeafFlag = the end state has no out-edges.
 constexpr uint32_t kChainFlag = 0x80000000u;
+constexpr int kChainByteShift = 23;            // bits 23..30 of a chain reference: first tail byte
+constexpr uint32_t kChainIndexMask = (1u << kChainByteShift) - 1u;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr int kMinChain = 2;          // compress runs of at least this many single-child states
 
-//   pre2 / rank2 / next2: the first two bytes need no hashing.  pre2 is a 65536-bit set over
-//     idx = c0 | c1<<8, stored bit-reversed inside each 32-bit word (idx -> word idx>>5, bit
-//     31-(idx&31)) so that `word << (idx&31)` moves the wanted bit to the sign position.
+//   lut / pre2 / rank2 / next2 / best2: the first K symbols need no hashing.  Every byte has a
+//     b-bit code (lut[c] = code, bit 7 set = byte occurs in no pattern); b = 8 (identity, K = 2),
+//     4 (K = 4) or 2 (K = 8) depending on the pattern alphabet.  pre2 is a 65536-bit set over
+//     idx = sum code(c_i) << (b*i), stored bit-reversed inside each 32-bit word (idx -> word
+//     idx>>5, bit 31-(idx&31)) so that `word << (idx&31)` moves the wanted bit to the sign
+//     position.  A bit is set iff a walk over those K symbols can produce a result.
 //     rank2[w] = number of set bits in words [0,w); next2[rank] = what the walk holds after
-//     consuming c0,c1: a state, kChainFlag|chain index, or kTrap when the bit is only set
-//     because root[c0] is final (1-byte pattern) and (root[c0],c1) is not an edge.
+//     its K-th symbol: a state (kLeafPlain = it has no out-edges), kChainFlag|chain index, or
+//     kTrap when the walk dies inside the K symbols; best2[rank] = longest pattern matched
+//     within the first K-1 symbols (0 if none; array omitted when it would be all zero).
+//     K-grams containing a byte outside the alphabet, or cut off by the end of the input, take
+//     the generic path from the root row (hash rows then also hold the edges of depth < K).
 constexpr uint32_t kTrap = 0xFFFFFFFFu;
+constexpr uint32_t kLeafPlain = 0x40000000u;  // plain state value: no out-edges, stop after it
 
 struct DeviceLayout {
     int32_t root[kCharSet];          // next state from the initial state, -1 = trap
+    uint8_t lut[kCharSet];           // symbol code | 0x80 if the byte occurs in no pattern
+    int codeBits = 8;                // b
+    int gramLen = 2;                 // K = 16 / b
     std::vector<uint32_t> pre2;      // 2048 words, bit-reversed within each word
     std::vector<uint16_t> rank2;     // 2048 prefix popcounts
     std::vector<uint32_t> next2;     // one entry per set bit, in idx order
-    bool next2Hot = false;           // next2 fits the shared-memory budget
-    std::vector<uint32_t> hot;       // edges with source depth in [2,hotDepth)  -> smem
+    std::vector<uint32_t> best2;     // parallel to next2; empty when all zero
+    bool next2Hot = false;           // next2 (+ best2) fit the shared-memory budget
+    std::vector<uint32_t> hot;       // edges with source depth in [K,hotDepth)  -> smem
     std::vector<uint32_t> cold;      // edges with source depth >= hotDepth      -> global/L2
     std::vector<uint32_t> chains;    // 4 words per chain record
     std::vector<uint8_t> tails;      // chain tail bytes, each tail padded to 4
@@ -87,7 +102,8 @@ struct DeviceLayout {
     int pre2BitsSet = 0;
     int rootFanout = 0;
     size_t deviceBytes() const {
-        return sizeof(root) + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 + hot.size() * 4 +
+        return sizeof(root) + sizeof(lut) + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 +
+               best2.size() * 4 + hot.size() * 4 +
                cold.size() * 4 + chains.size() * 4 + tails.size();
     }
 };

@@ -11,33 +11,50 @@ def read_patterns(path):
 
 def emulate_layout_walk(L, num_final, text, start, n_total=None):
     """Python restatement of the lookup sequence the CUDA kernels run on the compiled device
-    layout (pfac_b200/csrc/pfac_kernels.cu): prefilter bit -> root row -> bucketed hash rows
-    (hot for depth < hot_depth else cold) -> chain records with byte-wise tail compare.
+    layout (pfac_b200/csrc/pfac_kernels.cu): symbol codes -> K-gram prefilter bit -> rank ->
+    next2/best2 (or, for K-grams with a byte outside the alphabet / cut off by the end of the
+    input, the generic path from the root row) -> bucketed hash rows (hot for K <= depth <
+    hot_depth, else cold) -> chain records with tail compare.
     Test-only; checks the table compiler without a GPU.  L = TableCompiler.layout()."""
     n_total = len(text) if n_total is None else n_total
     avail = n_total - start
     if avail <= 0:
         return 0
-    c0 = int(text[start])
-    c1 = int(text[start + 1]) if avail >= 2 else 0
-    idx = c0 | (c1 << 8)
-    word = int(L["pre2"][idx >> 5])
-    b = idx & 31
-    if not ((word << b) >> 31) & 1:           # bit 31-(idx&31) of the word
-        return 0
-    s = int(L["root"][c0])
-    assert s >= 0, "prefilter bit set but root row traps"
-    best = s if s <= num_final else 0
-    if avail < 2:
-        return best                            # c1 was padding: only the 1-byte result counts
-    rank = int(L["rank2"][idx >> 5]) + (bin(word >> (32 - b)).count("1") if b else 0)
-    v = int(L["next2"][rank])                  # the walk after consuming c0, c1
-    d = 1
+    K, B = L["gram_len"], L["code_bits"]
+    lut = L["lut"]
+    syms = [int(text[start + i]) if i < avail else 0 for i in range(K)]
+    fast = B == 8 or (avail >= K and all(not (int(lut[c]) & 0x80) for c in syms))
+    if fast:
+        idx = 0
+        for i, c in enumerate(syms):
+            idx |= (int(lut[c]) & 0x7F if B != 8 else c) << (B * i)
+        word = int(L["pre2"][idx >> 5])
+        b = idx & 31
+        if not ((word << b) >> 31) & 1:           # bit 31-(idx&31) of the word
+            return 0
+        rank = int(L["rank2"][idx >> 5]) + (bin(word >> (32 - b)).count("1") if b else 0)
+        if B == 8:   # one symbol inside K-1: the root row tells whether c0 alone is a pattern
+            r0 = int(L["root"][syms[0]])
+            best = r0 if 0 <= r0 <= num_final else 0
+        else:
+            best = int(L["best2"][rank]) if L["best2"].size else 0
+        if avail < K:
+            return best                            # b == 8 only: the second symbol was padding
+        v = int(L["next2"][rank])                  # the walk after its K-th symbol
+        d = K - 1
+    else:
+        s0 = int(L["root"][syms[0]])
+        if s0 < 0:
+            return 0
+        best, v, d = 0, s0, 0
     while True:
         if v == 0xFFFFFFFF:
             break
         if v & 0x80000000:
-            off, ln, end, inline4 = (int(x) for x in L["chains"][v & 0x7FFFFFFF])
+            off, ln, end, inline4 = (int(x) for x in L["chains"][v & 0x7FFFFF])
+            assert ((v >> 23) & 0xFF) == (inline4 & 0xFF), "chain reference must carry the first tail byte"
+            if d + 1 >= avail or int(text[start + d + 1]) != ((v >> 23) & 0xFF):
+                break  # the kernels stop here without touching the chain record
             if d + 1 + ln > avail:
                 break  # cut off by the end of the input: nothing more can be reported
             tail = bytes(L["tails"][off:off + ln])
@@ -51,14 +68,16 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None):
             if end & 0x80000000:
                 break
         else:
-            s = v
+            s = v & 0x3FFFFFFF
             if s <= num_final:
                 best = s
             d += 1
+            if v & 0x40000000:
+                break  # plain leaf: no out-edges
         if d >= avail:
             break
         key = ((s << 8) | int(text[start + d])) & 0xFFFFFFFF
-        tab = L["hot"] if d < L["hot_depth"] else L["cold"]
+        tab = L["hot"] if K <= d < L["hot_depth"] else L["cold"]
         v = probe(tab, L["mul"], key)
         if v < 0:
             break

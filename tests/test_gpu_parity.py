@@ -302,3 +302,45 @@ def test_reduce_repeated_large_is_stable(cuda, tmp_path):
     orc = _oracle(pfile)
     k = 4 << 20
     assert np.array_equal(d_out[:k].cpu().numpy(), orc.match_shard(text[:k + 64], k))
+
+
+def _noisy(text, seed, junk=b"Nn\x00\xff-"):
+    rng = np.random.default_rng(seed)
+    t = text.copy()
+    idx = rng.integers(0, t.size, size=max(t.size // 700, 8))
+    t[idx] = np.frombuffer(junk, dtype=np.uint8)[rng.integers(0, len(junk), size=idx.size)]
+    return t
+
+
+def test_small_alphabets_symbol_coded_prefilter(cuda, tmp_path):
+    """2-bit x 8 (DNA) and 4-bit x 4 (hex) prefilter indices; bytes outside the alphabet, patterns
+    shorter than K and input ends inside a K-gram go through the generic path."""
+    from pfac_b200 import PFAC
+    rng = np.random.default_rng(23)
+    hexa = np.frombuffer(b"0123456789abcdef", dtype=np.uint8)
+    hexp = list({hexa[rng.integers(0, 16, size=int(rng.integers(1, 14)))].tobytes() for _ in range(900)})
+    cases = [
+        ("dna", synth.patterns_dna(2000, seed=31, min_len=3, max_len=24, short=12), "dna", None),
+        ("dna_long_only", synth.patterns_dna(5000), "dna", None),
+        ("hex", hexp, None, hexa),
+    ]
+    for name, pats, kind, alpha in cases:
+        pfile = synth.write_pattern_file(str(tmp_path / (name + ".txt")), pats)
+        orc = _oracle(pfile)
+        with PFAC() as pf:
+            pf.readPatternFromFile(pfile)
+            info = pf.tableInfo()
+            assert info["code_bits"] == (2 if kind == "dna" else 4), info
+            for n in [7, 8, 9, 33, 511, 512, 513, 519, 520, 70_001, 1_500_003]:
+                if kind == "dna":
+                    text = synth.dna_bytes(900 + n, 0, n)
+                else:
+                    text = alpha[np.random.default_rng(n).integers(0, 16, size=n)].copy()
+                if n > 1000:
+                    synth.plant(text, 0, n, pats, 1234 + n, every=700)
+                    text = _noisy(text, n)
+                _check_all(pf, orc, text, cuda)
+            text = _noisy(synth.dna_bytes(5, 0, 300_000), 5) if kind == "dna" else _noisy(
+                alpha[np.random.default_rng(5).integers(0, 16, size=300_000)].copy(), 5)
+            for owned in [1, 100_000, 299_990, 299_999, 300_000]:
+                _check_all(pf, orc, text, cuda, n_owned=owned)

@@ -45,8 +45,9 @@ def test_info_readme_example(golden_dir):
     info = TableCompiler(os.path.join(golden_dir, "example_pattern")).info()
     assert (info["num_patterns"], info["num_states"], info["initial_state"], info["max_pattern_len"]) == (4, 11, 5, 4)
     assert info["num_leaves"] == 3 and info["num_edges"] == 9 and info["root_fanout"] == 3
-    assert info["num_chains"] == 1 and info["hash_edges"] == 1  # B-E-(D-E) is the only run >= 2; (1,G)->2 hashed
-    assert info["pre2_bits_set"] == 3  # AB, BE, ED
+    assert info["pre2_bits_set"] == 51
+    assert info["code_bits"] == 4 and info["gram_len"] == 4  # alphabet {A,B,D,E,G}: 4-bit symbol codes
+    # 4-grams over 5 symbols that can yield a result: AB??, ED?? (2 x 25) + BEDE
 
 
 @pytest.mark.parametrize("hot_kb", [0, 1, 24, 512])
@@ -69,7 +70,12 @@ def test_layout_walk_equals_oracle(golden_dir, case, hot_kb):
         assert info["hot_depth"] == 1 and info["hot_buckets"] == 0 and not info["chains_hot"]
     if hot_kb == 512:
         assert info["hot_depth"] == info["max_depth"] + 1 and info["chains_hot"]  # everything fits
-        assert info["hot_buckets"] == info["hash_edges"] and info["next2_hot"]
+        assert info["next2_hot"]
+        if info["gram_len"] == 2:
+            assert info["hot_buckets"] == info["hash_edges"]
+        else:  # edges of depth < K serve only the generic path: always cold
+            assert 0 < info["hot_buckets"] < info["hash_edges"]
+            assert info["hot_buckets"] + info["cold_buckets"] == info["hash_edges"]
     if hot_kb == 0:
         assert not info["next2_hot"]
     assert info["num_chains"] > 0 and info["hash_edges"] < info["num_edges"]
@@ -87,6 +93,7 @@ def test_layout_root_and_prefilter_against_dense_table(golden_dir):
     root, pre2, hot, cold = L["root"], L["pre2"], L["hot"], L["cold"]
     init, k = o.initial_state, o.num_patterns
     assert np.array_equal(root, T[init])
+    assert tc.info()["code_bits"] == 8 and tc.info()["gram_len"] == 2
     nset = 0
     for c1 in range(256):
         for c0 in range(256):
@@ -95,14 +102,14 @@ def test_layout_root_and_prefilter_against_dense_table(golden_dir):
             bit = (int(pre2[idx >> 5]) << (idx & 31) >> 31) & 1
             expect = s >= 0 and (s <= k or T[s, c1] >= 0)
             assert bool(bit) == bool(expect), (c0, c1)
-            if bit:  # next2 is indexed by the rank of the bit, in idx order
+            if bit:  # next2 / best2 are indexed by the rank of the bit, in idx order
                 if (idx & 31) == 0:
                     assert int(L["rank2"][idx >> 5]) == nset
                 v = int(L["next2"][nset])
                 if T[s, c1] < 0:
                     assert v == 0xFFFFFFFF
                 elif not (v & 0x80000000):
-                    assert v == T[s, c1]
+                    assert (v & 0x3FFFFFFF) == T[s, c1]
                 nset += 1
     assert nset == tc.info()["pre2_bits_set"]
     # every hash entry is unique; chain compression accounts for the missing transitions
@@ -113,6 +120,7 @@ def test_layout_root_and_prefilter_against_dense_table(golden_dir):
     chain_len = int(L["chains"][:info["num_chains"], 1].sum())
     depth1 = int((L["next2"] != 0xFFFFFFFF).sum())  # (root child, c1) edges live in next2
     assert info["num_edges"] == info["root_fanout"] + depth1 + info["hash_edges"] + chain_len
+    assert info["has_best2"] == 0  # K == 2: 1-byte patterns are told by the root row
 
 
 def test_duplicates_prefixes_and_one_byte_patterns():
@@ -149,3 +157,43 @@ def test_state_numbering_matches_oracle_on_binary_patterns(tmp_path):
     o.dump(str(a))
     tc.dump(str(b))
     assert a.read_bytes() == b.read_bytes()
+
+
+def _small_alphabet_cases():
+    rng = np.random.default_rng(17)
+    dna = synth.patterns_dna(300, seed=5, min_len=3, max_len=14, short=10)          # < K-long patterns too
+    hexa = np.frombuffer(b"0123456789abcdef", dtype=np.uint8)
+    hexp = list({hexa[rng.integers(0, 16, size=int(rng.integers(1, 11)))].tobytes() for _ in range(400)})
+    return [("dna", dna, np.frombuffer(b"ACGT", dtype=np.uint8), 2, 8),
+            ("hex", hexp, hexa, 4, 4)]
+
+
+@pytest.mark.parametrize("hot_kb", [0, 512])
+@pytest.mark.parametrize("which", [0, 1])
+def test_symbol_coded_prefilter_small_alphabets(which, hot_kb):
+    """Alphabets of <= 4 / <= 16 symbols use 2-bit x 8 / 4-bit x 4 prefilter indices.  Text with bytes
+    outside the alphabet, patterns shorter than K and walks cut off by the end of the input must take
+    the generic path and still give the oracle's result."""
+    name, pats, alpha, bits, k = _small_alphabet_cases()[which]
+    image = synth.pattern_file_image(pats)
+    o = Oracle(image=image)
+    tc = TableCompiler(image=image, hot_budget_bytes=hot_kb * 1024)
+    info = tc.info()
+    assert (info["code_bits"], info["gram_len"]) == (bits, k)
+    assert info["has_best2"] == 1
+    L = tc.layout()
+    rng = np.random.default_rng(3)
+    n = 5000
+    text = alpha[rng.integers(0, alpha.size, size=n)].copy()
+    text[rng.integers(0, n, size=60)] = ord("N")          # bytes that occur in no pattern
+    text[rng.integers(0, n, size=20)] = 0
+    for p in pats[:40]:                                    # plant some, including at the very end
+        at = int(rng.integers(0, n - len(p)))
+        text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    longest = max(pats, key=len)
+    text[n - len(longest) + 1:] = np.frombuffer(longest[:-1], dtype=np.uint8)
+    want = o.match(text)
+    got = np.array([emulate_layout_walk(L, o.num_patterns, text, i) for i in range(n)], dtype=np.int32)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "%s: first mismatch at %d: got %d want %d" % (name, bad[0], got[bad[0]], want[bad[0]])
+    assert (want > 0).sum() > 100
