@@ -448,7 +448,9 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     const size_t nHot = upto[size_t(H)];
     const size_t nCold = edges.size() - nHot;
     L.hotBuckets = uint32_t(nHot);         // 0 => kernels never probe the hot table
-    L.coldBuckets = uint32_t(std::max<size_t>(nCold, 1));
+    // cold rows live in L2 where space is cheap and every extra bucket probe is a dependent L2
+    // access: load factor 0.25 (a miss leaves its home bucket 9 % of the time instead of 26 %)
+    L.coldBuckets = uint32_t(std::max<size_t>(nCold * 2, 1));
 
     static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu,
                                     0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};

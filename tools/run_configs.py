@@ -171,6 +171,7 @@ def main():
     # ---- parity vs the oracle, chunked ---------------------------------------------------------------
     check = owned if args.check_bytes < 0 else min(args.check_bytes, owned)
     if check:
+        Oracle.set_threads(max(1, (os.cpu_count() or 1) // world))  # torchrun exports OMP_NUM_THREADS=1
         orc = Oracle(pfile)
         chunk = 256 << 20
         halo = maxlen - 1
