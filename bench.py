@@ -225,8 +225,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    # NCCL prints its version / debug lines to stdout by default: keep stdout for the JSON line
+    # NCCL prints its version banner / debug lines to stdout: keep stdout for the one JSON line by
+    # pointing fd 1 at stderr while the ranks run and printing the line to the saved stdout
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from pfac_b200 import PFAC
@@ -396,7 +400,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "gbps_reference_unit": value * 8.0,
         }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     pf.destroy()
     if world > 1:
         dist.destroy_process_group()

@@ -344,3 +344,34 @@ def test_small_alphabets_symbol_coded_prefilter(cuda, tmp_path):
                 alpha[np.random.default_rng(5).integers(0, 16, size=300_000)].copy(), 5)
             for owned in [1, 100_000, 299_990, 299_999, 300_000]:
                 _check_all(pf, orc, text, cuda, n_owned=owned)
+
+
+def test_host_apis_across_pipeline_chunks(cuda, tmp_path, monkeypatch):
+    """PFAC_matchFromHost / PFAC_matchFromHostReduce split the input into chunks with a tail halo and
+    run a two-stream H2D / kernel / D2H pipeline: matches that straddle chunk edges, pageable and pinned
+    buffers, and the running output offset of the reduce variant."""
+    from pfac_b200 import PFAC
+    monkeypatch.setenv("PFAC_B200_HOST_CHUNK_MB", "4")   # force many chunks
+    pats = synth.patterns_snort_like(3000, seed=41)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = (4 << 20) * 5 + 123_457
+    text = synth.make_text("ascii", 4141, 0, n, n, pats, 1500)
+    synth.plant(text, 0, n, pats, 77, every=1 << 30, boundary=4 << 20)  # straddle every chunk edge
+    want = orc.match(text)
+    wid, wpos = orc.reduce(want)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        got = pf.matchFromHost(text)                                    # pageable numpy buffers
+        assert np.array_equal(got, want)
+        h_in = torch.from_numpy(text).pin_memory()
+        h_out = torch.empty(n, dtype=torch.int32).pin_memory()
+        pf.matchFromHost(h_in, h_out, size=n)                           # pinned buffers
+        assert np.array_equal(h_out.numpy(), want)
+        ids, pos = pf.matchFromHostReduce(text)
+        assert np.array_equal(ids, wid) and np.array_equal(pos.astype(np.int64), wpos)
+        for cut in (1, 4 << 20, (4 << 20) + 1, (8 << 20) - 1):
+            ids, pos = pf.matchFromHostReduce(text[:cut])
+            w = orc.match(text[:cut])
+            wi, wp = orc.reduce(w)
+            assert np.array_equal(ids, wi) and np.array_equal(pos.astype(np.int64), wp)
