@@ -113,6 +113,25 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
 PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);
 PFAC_status_t PFAC_dumpTransitionTableToFile(PFAC_handle_t handle, const char *filename);
 
+/* ---- table-size report to stdout, counterpart of the reference's PFAC_memoryUsage
+ * (src/PFAC.cpp:1250-1306; not in the reference's public header either) */
+PFAC_status_t PFAC_memoryUsage(PFAC_handle_t handle);
+
+/* ---- multi-GPU driver, one process: what reference test/omp_PFAC.cpp:257-394 builds by hand.
+ * One handle per listed device, contiguous shards with a (maxPatternLen-1)-byte tail halo, one host
+ * thread per GPU running the chunked host pipeline; the reduced form places each GPU's run at the
+ * exclusive scan of the per-GPU counts.  h_matched_result / h_pos of the reduced call must hold `size`
+ * entries (the reference asks the same of its reduce buffers).  For one process per GPU use the shard
+ * entry points above with an NCCL all-gather of the counts (pfac_b200/sharding.py). */
+typedef struct PFAC_mgpu *PFAC_mgpu_t;
+PFAC_status_t PFAC_mgpuCreate(PFAC_mgpu_t *mg, const int *devices, int num_devices);
+PFAC_status_t PFAC_mgpuDestroy(PFAC_mgpu_t mg);
+PFAC_status_t PFAC_mgpuReadPatternFromFile(PFAC_mgpu_t mg, char *filename);
+PFAC_status_t PFAC_mgpuMatchFromHost(PFAC_mgpu_t mg, char *h_inputString, size_t size, int *h_matched_result);
+PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char *h_inputString, size_t size,
+                                             int *h_matched_result, long long *h_pos,
+                                             unsigned long long *h_num_matched);
+
 /* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
 unsigned long long PFAC_kernelLaunchCount(void);
 

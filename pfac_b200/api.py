@@ -124,6 +124,12 @@ def load_library():
         "PFAC_tableGetLayout": [vp] + [ctypes.POINTER(vp)] * 8,
         "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 2,
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
+        "PFAC_memoryUsage": [vp],
+        "PFAC_mgpuCreate": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int],
+        "PFAC_mgpuDestroy": [vp],
+        "PFAC_mgpuReadPatternFromFile": [vp, cp],
+        "PFAC_mgpuMatchFromHost": [vp, vp, sz, vp],
+        "PFAC_mgpuMatchFromHostReduce64": [vp, vp, sz, vp, vp, ctypes.POINTER(ull)],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -279,6 +285,55 @@ class PFAC:
         _check(self._L.PFAC_matchFromHostReduce(self._h, _ptr(src), n, _ptr(h_result), _ptr(h_pos),
                                                 ctypes.byref(m)), "PFAC_matchFromHostReduce")
         return h_result[:m.value], h_pos[:m.value]
+
+
+class PFACMultiGPU:
+    """PFAC_mgpu_t: one process, one handle + host thread per listed device (include/PFAC_ext.h)."""
+
+    def __init__(self, devices):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        _check(self._L.PFAC_mgpuCreate(ctypes.byref(self._h), arr, len(devices)), "PFAC_mgpuCreate")
+
+    def destroy(self):
+        if self._h:
+            st = self._L.PFAC_mgpuDestroy(self._h)
+            self._h = ctypes.c_void_p()
+            _check(st, "PFAC_mgpuDestroy")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.destroy()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def readPatternFromFile(self, filename):
+        _check(self._L.PFAC_mgpuReadPatternFromFile(self._h, os.fsencode(filename)),
+               "PFAC_mgpuReadPatternFromFile")
+
+    def matchFromHost(self, h_input):
+        src = _host_u8(h_input)
+        n = _host_len(src)
+        out = np.zeros(n, dtype=np.int32)
+        _check(self._L.PFAC_mgpuMatchFromHost(self._h, _ptr(src), n, _ptr(out)), "PFAC_mgpuMatchFromHost")
+        return out
+
+    def matchFromHostReduce64(self, h_input):
+        src = _host_u8(h_input)
+        n = _host_len(src)
+        ids = np.zeros(max(n, 1), dtype=np.int32)
+        pos = np.zeros(max(n, 1), dtype=np.int64)
+        m = ctypes.c_ulonglong(0)
+        _check(self._L.PFAC_mgpuMatchFromHostReduce64(self._h, _ptr(src), n, _ptr(ids), _ptr(pos),
+                                                      ctypes.byref(m)), "PFAC_mgpuMatchFromHostReduce64")
+        return ids[:m.value], pos[:m.value]
 
 
 def _host_u8(x):

@@ -5,7 +5,9 @@
 // the implementation is new.  There is no CPU matcher in this library.
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -244,7 +246,8 @@ PFAC_status_t ensurePipe(PFAC_handle_t h, bool needPos) {
         if (cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_in[i]), inCap) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
-        if (needPos && cudaMalloc(reinterpret_cast<void**>(&p.d_pos[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
+        // positions may be 64-bit (multi-GPU / shard forms)
+        if (needPos && cudaMalloc(reinterpret_cast<void**>(&p.d_pos[i]), chunk * 8) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
     }
     p.chunk = chunk;
     p.inCap = inCap;
@@ -425,12 +428,9 @@ PFAC_status_t PFAC_matchFromDevice(PFAC_handle_t handle, char* d_in, size_t size
 // reference PFAC.cpp:879-961.  Chunks of the host input (+ tail halo) go H2D on two private
 // streams, each followed by its kernel and the D2H of its 4-byte-per-position results, so
 // copy-in, match and copy-out of neighbouring chunks overlap.  Synchronous, like the reference.
-PFAC_status_t PFAC_matchFromHost(PFAC_handle_t handle, char* h_in, size_t size, int* h_out) {
-    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
-    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
-    if (!h_in) return PFAC_STATUS_INVALID_PARAMETER;
-    if (!h_out) return PFAC_STATUS_INVALID_PARAMETER;
-    if (size == 0) return PFAC_STATUS_SUCCESS;
+// host shard: results for [0,n_owned), input bytes [0,n_total) (owned + tail halo), both on the host
+static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size_t n_owned, size_t n_total,
+                                    int* h_out) {
     std::lock_guard<std::mutex> lock(handle->pipeMu);
     PFAC_status_t st = ensurePipe(handle, false);
     if (st != PFAC_STATUS_SUCCESS) return st;
@@ -438,9 +438,9 @@ PFAC_status_t PFAC_matchFromHost(PFAC_handle_t handle, char* h_in, size_t size, 
     const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
     cudaError_t e = cudaSuccess;
     int slot = 0;
-    for (size_t off = 0; off < size && e == cudaSuccess; off += p.chunk, slot ^= 1) {
-        const size_t owned = (size - off < p.chunk) ? size - off : p.chunk;
-        const size_t total = (size - off < owned + halo) ? size - off : owned + halo;
+    for (size_t off = 0; off < n_owned && e == cudaSuccess; off += p.chunk, slot ^= 1) {
+        const size_t owned = (n_owned - off < p.chunk) ? n_owned - off : p.chunk;
+        const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
         cudaStream_t s = p.stream[slot];
         e = cudaMemcpyAsync(p.d_in[slot], h_in + off, total, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) break;
@@ -453,6 +453,15 @@ PFAC_status_t PFAC_matchFromHost(PFAC_handle_t handle, char* h_in, size_t size, 
     if (e != cudaSuccess) return cudaToStatus(e);
     if (e0 != cudaSuccess) return cudaToStatus(e0);
     return cudaToStatus(e1);
+}
+
+PFAC_status_t PFAC_matchFromHost(PFAC_handle_t handle, char* h_in, size_t size, int* h_out) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!h_in) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_out) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    return hostDenseShard(handle, h_in, size, size, h_out);
 }
 
 PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char* d_in, size_t n_owned,
@@ -507,16 +516,11 @@ PFAC_status_t PFAC_reduceInplaceOnDevice(PFAC_handle_t handle, char* d_in, size_
 // reference PFAC.cpp:1010-1128.  Chunked: H2D of chunk c+1 overlaps the fused match+compaction
 // of chunk c; only 8 bytes per match come back.  Positions are global (chunk offset added on
 // the device), lists are appended in chunk order, so the result is ascending in position.
-PFAC_status_t PFAC_matchFromHostReduce(PFAC_handle_t handle, char* h_in, size_t size, int* h_id, int* h_pos,
-                                       int* h_num) {
-    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
-    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
-    if (!h_in) return PFAC_STATUS_INVALID_PARAMETER;
-    if (!h_id) return PFAC_STATUS_INVALID_PARAMETER;
-    if (!h_pos) return PFAC_STATUS_INVALID_PARAMETER;
-    if (!h_num) return PFAC_STATUS_INVALID_PARAMETER;
-    if (size == 0) return PFAC_STATUS_SUCCESS;
-    if (size >= kInt32Limit) return PFAC_STATUS_INVALID_PARAMETER;
+// host shard, reduced: appends (id, position) for owned positions; position = pos_base + local.
+// h_pos is int* (pos64 == false) or long long* (pos64 == true).
+static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, size_t n_owned, size_t n_total,
+                                     long long pos_base, int* h_id, void* h_pos, bool pos64,
+                                     unsigned long long* h_num) {
     std::lock_guard<std::mutex> lock(handle->pipeMu);
     {
         PFAC_status_t st = ensurePipe(handle, true);
@@ -524,26 +528,28 @@ PFAC_status_t PFAC_matchFromHostReduce(PFAC_handle_t handle, char* h_in, size_t 
     }
     HostPipe& p = handle->pipe;
     const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
+    const size_t posBytes = pos64 ? 8 : 4;
     size_t written = 0;
     int slot = 0;
     // prefetch the first chunk, then: [H2D next chunk on the other stream] || [reduce this chunk]
     auto stageIn = [&](size_t off, int sl) -> cudaError_t {
-        const size_t owned = (size - off < p.chunk) ? size - off : p.chunk;
-        const size_t total = (size - off < owned + halo) ? size - off : owned + halo;
+        const size_t owned = (n_owned - off < p.chunk) ? n_owned - off : p.chunk;
+        const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
         return cudaMemcpyAsync(p.d_in[sl], h_in + off, total, cudaMemcpyHostToDevice, p.stream[sl]);
     };
     if (stageIn(0, 0) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
-    for (size_t off = 0; off < size; off += p.chunk, slot ^= 1) {
-        const size_t owned = (size - off < p.chunk) ? size - off : p.chunk;
-        const size_t total = (size - off < owned + halo) ? size - off : owned + halo;
-        if (off + p.chunk < size && stageIn(off + p.chunk, slot ^ 1) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    for (size_t off = 0; off < n_owned; off += p.chunk, slot ^= 1) {
+        const size_t owned = (n_owned - off < p.chunk) ? n_owned - off : p.chunk;
+        const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
+        if (off + p.chunk < n_owned && stageIn(off + p.chunk, slot ^ 1) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
         unsigned long long count = 0;
-        PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, total, (long long)off, p.d_out[slot],
-                                       p.d_pos[slot], false, p.stream[slot], &count);
+        PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, total, pos_base + (long long)off, p.d_out[slot],
+                                       p.d_pos[slot], pos64, p.stream[slot], &count);
         if (st != PFAC_STATUS_SUCCESS) { cudaDeviceSynchronize(); return st; }
         if (count) {
             if (cudaMemcpyAsync(h_id + written, p.d_out[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess ||
-                cudaMemcpyAsync(h_pos + written, p.d_pos[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess) {
+                cudaMemcpyAsync(static_cast<char*>(h_pos) + written * posBytes, p.d_pos[slot], count * posBytes,
+                                cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess) {
                 cudaDeviceSynchronize();
                 return PFAC_STATUS_INTERNAL_ERROR;
             }
@@ -554,7 +560,179 @@ PFAC_status_t PFAC_matchFromHostReduce(PFAC_handle_t handle, char* h_in, size_t 
     }
     if (cudaStreamSynchronize(p.stream[0]) != cudaSuccess || cudaStreamSynchronize(p.stream[1]) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
-    *h_num = int(written);
+    *h_num = written;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC.cpp:1010-1128.  Chunked: H2D of chunk c+1 overlaps the fused match+compaction
+// of chunk c; only 8 bytes per match come back.  Positions are global (chunk offset added on
+// the device), lists are appended in chunk order, so the result is ascending in position.
+PFAC_status_t PFAC_matchFromHostReduce(PFAC_handle_t handle, char* h_in, size_t size, int* h_id, int* h_pos,
+                                       int* h_num) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!h_in) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_id) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_pos) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!h_num) return PFAC_STATUS_INVALID_PARAMETER;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    if (size >= kInt32Limit) return PFAC_STATUS_INVALID_PARAMETER;
+    unsigned long long n = 0;
+    PFAC_status_t st = hostReduceShard(handle, h_in, size, size, 0, h_id, h_pos, false, &n);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    *h_num = int(n);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// reference PFAC_memoryUsage (PFAC.cpp:1250-1306, not in the public header): table sizes to stdout
+PFAC_status_t PFAC_memoryUsage(PFAC_handle_t handle) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    const pfac::Machine& m = handle->machine;
+    const pfac::DeviceLayout& L = handle->layout;
+    const double dense2d = double(m.numStates) * 256.0 * 4.0;
+    printf("%s: symbol code %d bits x %d, prefilter 8192 bytes (%d of 65536 bits set)\n",
+           handle->perfMode == PFAC_SPACE_DRIVEN ? "space-driven" : "time-driven", L.codeBits, L.gramLen,
+           L.pre2BitsSet);
+    printf("next2 = %zu entries, hash rows = %d entries (%u hot + %u cold buckets), chains = %d, tails = %zu bytes\n",
+           L.next2.size(), L.hashEdges, L.hotBuckets, L.coldBuckets, L.numChains, L.tails.size());
+    printf("total amount = %7.2f MB\n", double(L.deviceBytes()) / 1024. / 1024.);
+    printf("(device layout)/(2-D table) = %5.3f\n", double(L.deviceBytes()) / dense2d);
+    printf("S = number of states (ignore s0) = %d \n", m.numStates - 1);
+    printf("F = number of final states = %d \n", m.numFinal);
+    printf("L = number of leaf nodes = %d\n", m.numLeaves);
+    return PFAC_STATUS_SUCCESS;
+}
+
+// ---- multi-GPU driver (one process, one host thread per GPU) ---------------------------------------
+// What reference test/omp_PFAC.cpp:257-394 builds by hand: one handle per GPU, contiguous shards with
+// a tail halo of maxPatternLen-1 bytes, results stitched on the host.  For the reduced form the
+// per-GPU lists are written at provisional offsets and moved down to the exclusive scan of the
+// per-GPU counts (the one-process counterpart of the NCCL count all-gather in pfac_b200/sharding.py).
+struct PFAC_mgpu {
+    std::vector<int> devices;
+    std::vector<PFAC_handle_t> handles;
+};
+
+static void shardBounds(size_t size, int world, int rank, size_t halo, size_t* start, size_t* owned, size_t* total) {
+    size_t per = (size + size_t(world) - 1) / size_t(world);
+    per = (per + 4095) / 4096 * 4096;
+    const size_t s = std::min(size_t(rank) * per, size);
+    const size_t e = std::min(s + per, size);
+    *start = s;
+    *owned = e - s;
+    *total = std::min(e + halo, size) - s;
+}
+
+PFAC_status_t PFAC_mgpuCreate(PFAC_mgpu_t* mg, const int* devices, int num_devices) {
+    if (!mg || !devices || num_devices <= 0) return PFAC_STATUS_INVALID_PARAMETER;
+    *mg = nullptr;
+    int saved = 0;
+    cudaGetDevice(&saved);
+    PFAC_mgpu* m = new (std::nothrow) PFAC_mgpu();
+    if (!m) return PFAC_STATUS_ALLOC_FAILED;
+    PFAC_status_t st = PFAC_STATUS_SUCCESS;
+    for (int i = 0; i < num_devices && st == PFAC_STATUS_SUCCESS; i++) {
+        cudaError_t e = cudaSetDevice(devices[i]);
+        if (e != cudaSuccess) { st = PFAC_status_t(e); break; }
+        PFAC_handle_t h = nullptr;
+        st = PFAC_create(&h);
+        if (st == PFAC_STATUS_SUCCESS) { m->devices.push_back(devices[i]); m->handles.push_back(h); }
+    }
+    cudaSetDevice(saved);
+    if (st != PFAC_STATUS_SUCCESS) { PFAC_mgpuDestroy(m); return st; }
+    *mg = m;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_mgpuDestroy(PFAC_mgpu_t mg) {
+    if (!mg) return PFAC_STATUS_INVALID_HANDLE;
+    int saved = 0;
+    cudaGetDevice(&saved);
+    for (size_t i = 0; i < mg->handles.size(); i++) {
+        cudaSetDevice(mg->devices[i]);
+        PFAC_destroy(mg->handles[i]);
+    }
+    cudaSetDevice(saved);
+    delete mg;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_mgpuReadPatternFromFile(PFAC_mgpu_t mg, char* filename) {
+    if (!mg) return PFAC_STATUS_INVALID_HANDLE;
+    int saved = 0;
+    cudaGetDevice(&saved);
+    PFAC_status_t st = PFAC_STATUS_SUCCESS;
+    for (size_t i = 0; i < mg->handles.size() && st == PFAC_STATUS_SUCCESS; i++) {
+        cudaSetDevice(mg->devices[i]);
+        st = PFAC_readPatternFromFile(mg->handles[i], filename);
+    }
+    cudaSetDevice(saved);
+    return st;
+}
+
+PFAC_status_t PFAC_mgpuMatchFromHost(PFAC_mgpu_t mg, char* h_in, size_t size, int* h_out) {
+    if (!mg) return PFAC_STATUS_INVALID_HANDLE;
+    if (!h_in || !h_out) return PFAC_STATUS_INVALID_PARAMETER;
+    if (mg->handles.empty() || !mg->handles[0]->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    const int G = int(mg->handles.size());
+    const size_t halo = size_t(std::max(mg->handles[0]->machine.maxPatternLen - 1, 0));
+    std::vector<PFAC_status_t> status(size_t(G), PFAC_STATUS_SUCCESS);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; g++) {
+        workers.emplace_back([&, g]() {
+            size_t s, owned, total;
+            shardBounds(size, G, g, halo, &s, &owned, &total);
+            if (owned == 0) return;
+            if (cudaSetDevice(mg->devices[size_t(g)]) != cudaSuccess) { status[size_t(g)] = PFAC_STATUS_INTERNAL_ERROR; return; }
+            status[size_t(g)] = hostDenseShard(mg->handles[size_t(g)], h_in + s, owned, total, h_out + s);
+        });
+    }
+    for (std::thread& w : workers) w.join();
+    for (PFAC_status_t st : status) if (st != PFAC_STATUS_SUCCESS) return st;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// h_id / h_pos must hold `size` entries (as the reference requires of its reduce buffers, user guide
+// r1.2 p.30): each GPU first writes its run at its shard's start index.
+PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char* h_in, size_t size, int* h_id, long long* h_pos,
+                                             unsigned long long* h_num) {
+    if (!mg) return PFAC_STATUS_INVALID_HANDLE;
+    if (!h_in || !h_id || !h_pos || !h_num) return PFAC_STATUS_INVALID_PARAMETER;
+    if (mg->handles.empty() || !mg->handles[0]->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    *h_num = 0;
+    if (size == 0) return PFAC_STATUS_SUCCESS;
+    const int G = int(mg->handles.size());
+    const size_t halo = size_t(std::max(mg->handles[0]->machine.maxPatternLen - 1, 0));
+    std::vector<PFAC_status_t> status(size_t(G), PFAC_STATUS_SUCCESS);
+    std::vector<unsigned long long> counts(size_t(G), 0);
+    std::vector<size_t> starts(size_t(G), 0);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; g++) {
+        workers.emplace_back([&, g]() {
+            size_t s, owned, total;
+            shardBounds(size, G, g, halo, &s, &owned, &total);
+            starts[size_t(g)] = s;
+            if (owned == 0) return;
+            if (cudaSetDevice(mg->devices[size_t(g)]) != cudaSuccess) { status[size_t(g)] = PFAC_STATUS_INTERNAL_ERROR; return; }
+            status[size_t(g)] = hostReduceShard(mg->handles[size_t(g)], h_in + s, owned, total, (long long)s, h_id + s,
+                                                h_pos + s, true, &counts[size_t(g)]);
+        });
+    }
+    for (std::thread& w : workers) w.join();
+    for (PFAC_status_t st : status) if (st != PFAC_STATUS_SUCCESS) return st;
+    // exclusive scan of the per-GPU counts = each run's place in the global list; runs only move down
+    unsigned long long off = 0;
+    for (int g = 0; g < G; g++) {
+        const unsigned long long c = counts[size_t(g)];
+        if (c && off != starts[size_t(g)]) {
+            memmove(h_id + off, h_id + starts[size_t(g)], c * sizeof(int));
+            memmove(h_pos + off, h_pos + starts[size_t(g)], c * sizeof(long long));
+        }
+        off += c;
+    }
+    *h_num = off;
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -375,3 +375,34 @@ def test_host_apis_across_pipeline_chunks(cuda, tmp_path, monkeypatch):
             w = orc.match(text[:cut])
             wi, wp = orc.reduce(w)
             assert np.array_equal(ids, wi) and np.array_equal(pos.astype(np.int64), wp)
+
+
+def test_multi_gpu_driver_one_process(cuda, tmp_path, monkeypatch):
+    """PFAC_mgpu_* (the library-level replacement of reference test/omp_PFAC.cpp): shards + halo, one
+    host thread per handle, runs placed at the exclusive scan of the per-GPU counts.  Uses every
+    visible GPU; with a single GPU two handles share it, which exercises the same host logic.
+    Like omp_PFAC.cpp:397-439 the result is also compared with the single-handle run."""
+    from pfac_b200 import PFAC, PFACMultiGPU
+    monkeypatch.setenv("PFAC_B200_HOST_CHUNK_MB", "2")
+    pats = synth.patterns_snort_like(2000, seed=51)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = 9_000_017
+    text = synth.make_text("ascii", 5151, 0, n, n, pats, 900)
+    want = orc.match(text)
+    wid, wpos = orc.reduce(want)
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(ndev)) if ndev > 1 else [0, 0]):
+        with PFACMultiGPU(devices) as mg:
+            mg.readPatternFromFile(pfile)
+            assert np.array_equal(mg.matchFromHost(text), want), devices
+            ids, pos = mg.matchFromHostReduce64(text)
+            assert np.array_equal(ids, wid) and np.array_equal(pos, wpos), devices
+            ids, pos = mg.matchFromHostReduce64(text[:5])
+            w5 = orc.match(text[:5])
+            assert ids.tolist() == w5[w5 > 0].tolist()
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        assert np.array_equal(pf.matchFromHost(text), want)
+        pf_mem = pf.tableInfo()
+        assert pf_mem["num_patterns"] == len(pats)
