@@ -75,6 +75,7 @@ typedef struct {
     int code_bits;         /* b: bits per symbol in the prefilter index (8, 4 or 2) */
     int gram_len;          /* K = 16 / b symbols covered by the prefilter + direct table */
     int has_best2;         /* 1: patterns shorter than K exist (best2 array present) */
+    int has_chk2;          /* 1: second prefilter stage (next-symbol sets per K-gram) is on */
     int max_depth;
     int hot_depth;         /* edges whose source state has depth in [1,hot_depth) are "hot" */
     unsigned hot_buckets;  /* 16-byte buckets (2 slots) of the shared-memory hash rows */
@@ -105,9 +106,9 @@ PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int **root, const un
                                   const unsigned **hot, const unsigned **cold,
                                   const unsigned **chains, const unsigned char **tails);
 /* lut: 256 bytes (symbol code | 0x80 = byte in no pattern); best2: parallel to next2, NULL when
- * has_best2 == 0 */
+ * has_best2 == 0; chk2: parallel to next2 (16-bit set of next byte & 15), NULL when has_chk2 == 0 */
 PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut,
-                                   const unsigned **best2);
+                                   const unsigned **best2, const unsigned short **chk2);
 
 /* info / dump-to-path for a live handle */
 PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);

@@ -57,7 +57,7 @@ class TableInfo(ctypes.Structure):
                 ("hash_edges", ctypes.c_int), ("num_chains", ctypes.c_int),
                 ("tail_bytes", ctypes.c_int), ("chains_hot", ctypes.c_int),
                 ("next2_hot", ctypes.c_int), ("code_bits", ctypes.c_int),
-                ("gram_len", ctypes.c_int), ("has_best2", ctypes.c_int),
+                ("gram_len", ctypes.c_int), ("has_best2", ctypes.c_int), ("has_chk2", ctypes.c_int),
                 ("max_depth", ctypes.c_int), ("hot_depth", ctypes.c_int),
                 ("hot_buckets", ctypes.c_uint), ("cold_buckets", ctypes.c_uint),
                 ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
@@ -122,7 +122,7 @@ def load_library():
         "PFAC_tableDumpToFile": [vp, cp],
         "PFAC_tableGetInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_tableGetLayout": [vp] + [ctypes.POINTER(vp)] * 8,
-        "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 2,
+        "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 3,
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_memoryUsage": [vp],
         "PFAC_mgpuCreate": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int],
@@ -383,7 +383,7 @@ class TableCompiler:
         ptrs = [ctypes.c_void_p() for _ in range(8)]
         _check(self._L.PFAC_tableGetLayout(self._t, *[ctypes.byref(p) for p in ptrs]),
                "PFAC_tableGetLayout")
-        p2 = [ctypes.c_void_p() for _ in range(2)]
+        p2 = [ctypes.c_void_p() for _ in range(3)]
         _check(self._L.PFAC_tableGetLayout2(self._t, *[ctypes.byref(p) for p in p2]), "PFAC_tableGetLayout2")
         info = self.info()
 
@@ -403,6 +403,7 @@ class TableCompiler:
             "tails": arr(ptrs[7], info["tail_bytes"], np.uint8),
             "lut": arr(p2[0], 256, np.uint8),
             "best2": arr(p2[1], max(info["pre2_bits_set"], 1) * 4 if info["has_best2"] else 0, np.uint32),
+            "chk2": arr(p2[2], max(info["pre2_bits_set"], 1) * 2 if info["has_chk2"] else 0, np.uint16),
             "code_bits": info["code_bits"], "gram_len": info["gram_len"],
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
         }

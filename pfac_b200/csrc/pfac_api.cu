@@ -134,6 +134,8 @@ PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::D
     PFAC_UP(lut, const unsigned char*, L.lut, sizeof(L.lut))
     PFAC_UP(next2, const uint32_t*, L.next2.data(), L.next2.size() * 4)
     PFAC_UP(best2, const uint32_t*, L.best2.data(), L.best2.size() * 4)
+    PFAC_UP(chk2, const unsigned short*, L.chk2.data(), L.chk2.size() * 2)
+    t.chk2Bytes = uint32_t(((L.chk2.size() * 2 + 15) / 16) * 16);
     t.hasBest2 = !L.best2.empty();
     t.codeBits = L.codeBits;
     t.gramLen = L.gramLen;
@@ -757,6 +759,7 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->code_bits = L.codeBits;
     info->gram_len = L.gramLen;
     info->has_best2 = L.best2.empty() ? 0 : 1;
+    info->has_chk2 = L.chk2.empty() ? 0 : 1;
     info->max_depth = L.maxDepth;
     info->hot_depth = L.hotDepth;
     info->hot_buckets = L.hotBuckets;
@@ -834,10 +837,12 @@ PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int** root, const un
     return PFAC_STATUS_SUCCESS;
 }
 
-PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char** lut, const unsigned** best2) {
+PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char** lut, const unsigned** best2,
+                                   const unsigned short** chk2) {
     if (!table) return PFAC_STATUS_INVALID_HANDLE;
     if (lut) *lut = table->layout.lut;
     if (best2) *best2 = table->layout.best2.empty() ? nullptr : table->layout.best2.data();
+    if (chk2) *chk2 = table->layout.chk2.empty() ? nullptr : table->layout.chk2.data();
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -38,7 +38,7 @@ constexpr int kMaxSmem = 232448;               // 227 KB opt-in dynamic shared m
 // ---- dense kernel geometry -------------------------------------------------------------------
 constexpr int kDenseWarps = 32;
 constexpr int kDenseThreads = kDenseWarps * 32;
-constexpr int kDenseMaxHalo = 512;             // staged halo cap; longer walks read global
+constexpr int kDenseMaxHalo = 64;              // staged halo cap; walks that run further read global memory
 
 // look-back descriptor: [63:62] status, [61:0] value
 constexpr unsigned long long kStatusAgg = 1ull << 62;
@@ -62,10 +62,12 @@ struct KParams {
     const unsigned char* lut;
     const uint32_t* next2;
     const uint32_t* best2;
+    const unsigned short* chk2;
     const uint4* hot;
     const uint4* cold;
     const uint4* chains;
     const unsigned char* tails;
+    uint32_t chk2_bytes;        // multiple of 16, 0 = no second prefilter stage (always staged in smem)
     uint32_t next2_bytes;       // multiple of 16 (copied to smem when next2_hot; best2 has the same size)
     int has_best2;
     uint32_t hot_buckets;
@@ -91,6 +93,7 @@ struct Tables {
     const unsigned char* lut;   // smem: symbol code | 0x80 (byte in no pattern)
     const uint32_t* next2;      // smem or global
     const uint32_t* best2;      // smem or global; nullptr when no pattern is shorter than K
+    const unsigned short* chk2; // smem; nullptr when the second prefilter stage is off
     const uint4* hot;           // smem
     const uint4* cold;          // global
     const uint4* chains;        // smem or global
@@ -179,7 +182,7 @@ __device__ __forceinline__ uint32_t probe_cold(const uint4* __restrict__ tab, ui
 }
 
 // copy the compiled tables into shared memory (whole CTA), returns the walker's view.
-// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB | lut 256 B;  s_var: [next2][best2][hot buckets][chains][tails]
+// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB | lut 256 B;  s_var: [chk2][next2][best2][hot buckets][chains][tails]
 constexpr int kFixedTableBytes = 1024 + 8192 + 4096 + 256;
 __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* s_fixed, unsigned char* s_var,
                                                int tid, int nthreads) {
@@ -199,6 +202,13 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     t.next2 = p.next2;
     t.best2 = p.has_best2 ? p.best2 : nullptr;
     uint4* var = reinterpret_cast<uint4*>(s_var);
+    t.chk2 = nullptr;
+    if (p.chk2_bytes) {
+        for (uint32_t i = tid; i < p.chk2_bytes / 16; i += nthreads)
+            var[i] = reinterpret_cast<const uint4*>(p.chk2)[i];
+        t.chk2 = reinterpret_cast<const unsigned short*>(var);
+        var += p.chk2_bytes / 16;
+    }
     if (p.next2_hot) {
         for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
             var[i] = reinterpret_cast<const uint4*>(p.next2)[i];
@@ -240,11 +250,19 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
 // position's index is a 16-bit window of it; a window holding a byte outside the alphabet cannot
 // be indexed and is flagged for the generic path instead.
 // Bit q of `cand` = position lb+q survives the prefilter; bit q of `slow` = it needs the generic path.
-template <int CODE>
+// second prefilter stage for a position whose first-stage bit is set: the valid K-gram's rank
+// selects a 16-bit set of (next byte & 15) values that can still lead somewhere
+__device__ __forceinline__ bool second_stage(const Tables& T, uint32_t idx, uint32_t word, uint32_t next_byte) {
+    const uint32_t rank = T.rank2[(idx >> 5) & 0x7FFu] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
+    return (T.chk2[rank] >> (next_byte & 15u)) & 1u;
+}
+
+template <int CODE, bool TWO>
 __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const Tables& T, uint32_t& cand,
                                             uint32_t& slow) {
     constexpr int K = 16 / CODE;
     const uint32_t* s_pre2 = T.pre2;
+    constexpr bool two_stage = TWO;  // second stage compiled in only for the tables that use it
     cand = 0;
     slow = 0;
     if (CODE == 8) {
@@ -260,7 +278,11 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
                 const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
                 // the table stores bit idx at position 31-(idx&31): one shift brings it to bit 31,
                 // one funnel shift moves it into cand from the right
-                const uint32_t t = word << (x & 31u);
+                uint32_t t = word << (x & 31u);
+                if (two_stage && static_cast<int>(t) < 0) {
+                    // x holds text bytes q..q+3: byte q+2 is the symbol after the 2-gram
+                    if (!second_stage(T, x & 0xFFFFu, word, x >> 16)) t = 0;
+                }
                 cand = __funnelshift_l(t, cand, 1);
             }
         }
@@ -287,7 +309,11 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
             const int wi = (q * CODE) / 32, sh = (q * CODE) % 32;
             const uint32_t x = (sh == 0) ? st[wi] : __funnelshift_r(st[wi], st[wi + 1], sh);
             const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
-            const uint32_t t = word << (x & 31u);
+            uint32_t t = word << (x & 31u);
+            if (two_stage && static_cast<int>(t) < 0) {
+                const uint32_t nb = (w[(q + K) >> 2] >> (8 * ((q + K) & 3))) & 0xFFu;  // text byte after the K-gram
+                if (!second_stage(T, x & 0xFFFFu, word, nb)) t = 0;
+            }
             cand = __funnelshift_l(t, cand, 1);
         }
         if (bad) {  // rare: some window holds a byte that occurs in no pattern
@@ -493,7 +519,7 @@ __device__ __forceinline__ void clip_windows(int tile_rem, int lb, uint32_t& can
     }
 }
 
-template <int NSTAGE, int CODE>
+template <int NSTAGE, int CODE, bool TWO>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int stage = kWarpTile + p.halo;
@@ -564,7 +590,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 
         const int lb = lane * kPosPerThread;
         uint32_t cand, slow;
-        prefilter16<CODE>(inb, lb, T, cand, slow);
+        prefilter16<CODE, TWO>(inb, lb, T, cand, slow);
         clip_windows<CODE>(tile_rem, lb, cand, slow);
         int valid = kWarpTile;
         if (!full) {  // tail tile: drop positions we do not own
@@ -677,7 +703,7 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
 #define PFAC_SPIN_GUARD(n, what, a, b_, c)
 #endif
 
-template <bool POS64, int CODE>
+template <bool POS64, int CODE, bool TWO>
 __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KParams p) {
     constexpr int NSTAGE = kRedStages;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -882,7 +908,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
             const int lb = lane * kPosPerThread;
             uint32_t cand, slow;
-            prefilter16<CODE>(inb, lb, T, cand, slow);
+            prefilter16<CODE, TWO>(inb, lb, T, cand, slow);
             clip_windows<CODE>(tile_rem, lb, cand, slow);
             if (tile >= full_tiles) {
                 const int valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
@@ -989,7 +1015,8 @@ size_t reduceFixedBytes(int halo) {
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
-    return (t.next2Hot ? size_t(t.next2Bytes) * (t.hasBest2 ? 2 : 1) : 0) + size_t(t.hotBuckets) * 16 +
+    return size_t(t.chk2Bytes) + (t.next2Hot ? size_t(t.next2Bytes) * (t.hasBest2 ? 2 : 1) : 0) +
+           size_t(t.hotBuckets) * 16 +
            (t.chainsHot ? size_t(t.chainBytes) + t.tailBytes : 0);
 }
 
@@ -1006,6 +1033,8 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
     p.lut = t.lut;
     p.next2 = t.next2;
     p.best2 = t.best2;
+    p.chk2 = t.chk2;
+    p.chk2_bytes = t.chk2Bytes;
     p.has_best2 = t.hasBest2 ? 1 : 0;
     p.next2_bytes = t.next2Bytes;
     p.next2_hot = t.next2Hot ? 1 : 0;
@@ -1062,12 +1091,17 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const int nst = denseStages(halo);
     void (*kernel)(KParams) = nullptr;
+    const bool two = t.chk2Bytes != 0;  // the table compiler only emits chk2 for byte alphabets
     switch (t.codeBits) {
-        case 8: kernel = (nst == 3) ? pfac_dense_kernel<3, 8> : pfac_dense_kernel<2, 8>; break;
-        case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4> : pfac_dense_kernel<2, 4>; break;
-        case 2: kernel = (nst == 3) ? pfac_dense_kernel<3, 2> : pfac_dense_kernel<2, 2>; break;
+        case 8:
+            if (two) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, true> : pfac_dense_kernel<2, 8, true>;
+            else kernel = (nst == 3) ? pfac_dense_kernel<3, 8, false> : pfac_dense_kernel<2, 8, false>;
+            break;
+        case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4, false> : pfac_dense_kernel<2, 4, false>; break;
+        case 2: kernel = (nst == 3) ? pfac_dense_kernel<3, 2, false> : pfac_dense_kernel<2, 2, false>; break;
         default: return cudaErrorInvalidValue;
     }
+    if (two && t.codeBits != 8) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
@@ -1101,12 +1135,17 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     const size_t smem = reduceFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const void* kernel = nullptr;
+    const bool two = t.chk2Bytes != 0;
     switch (t.codeBits) {
-        case 8: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8> : (const void*)pfac_reduce_kernel<false, 8>; break;
-        case 4: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 4> : (const void*)pfac_reduce_kernel<false, 4>; break;
-        case 2: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2> : (const void*)pfac_reduce_kernel<false, 2>; break;
+        case 8:
+            if (two) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, true> : (const void*)pfac_reduce_kernel<false, 8, true>;
+            else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, false> : (const void*)pfac_reduce_kernel<false, 8, false>;
+            break;
+        case 4: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 4, false> : (const void*)pfac_reduce_kernel<false, 4, false>; break;
+        case 2: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, false> : (const void*)pfac_reduce_kernel<false, 2, false>; break;
         default: return cudaErrorInvalidValue;
     }
+    if (two && t.codeBits != 8) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kRedMatchers - 1) / kRedMatchers;

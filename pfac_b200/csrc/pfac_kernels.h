@@ -15,6 +15,8 @@ struct DeviceTable {
     const unsigned char* lut = nullptr;     // 256: symbol code | 0x80
     const uint32_t* next2 = nullptr;  // next2Bytes / 4 (padded to 16 bytes)
     const uint32_t* best2 = nullptr;  // parallel to next2 (valid when hasBest2)
+    const unsigned short* chk2 = nullptr;  // second prefilter stage (chk2Bytes > 0), always staged in smem
+    uint32_t chk2Bytes = 0;           // multiple of 16; 0 = stage off
     uint32_t next2Bytes = 0;
     bool next2Hot = false;            // kernels copy next2 (+ best2) into shared memory
     bool hasBest2 = false;

@@ -374,6 +374,28 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
         if (anyBest) L.best2[i] = grams[i].best;
     }
 
+    // second prefilter stage: per valid K-gram a 16-bit set of (next byte & 15) values that keep the
+    // walk alive; all ones when the K symbols alone already produce a result (then the position
+    // must reach the walker whatever follows).  Only worth its shared memory and instructions when
+    // the first stage is unselective.
+    if (B == 8 && L.pre2BitsSet > 65536 * 3 / 100) {  // small alphabets: the K-gram stage is selective enough
+        L.chk2.assign(L.next2.size(), 0);
+        for (size_t i = 0; i < grams.size(); i++) {
+            const Gram& g = grams[i];
+            uint16_t mask = 0;
+            if (g.best != 0 || g.next == kTrap) {
+                mask = 0xFFFF;  // (trap entries exist only with best != 0)
+            } else if (g.next & kChainFlag) {
+                mask = uint16_t(1u << ((g.next >> kChainByteShift) & 15u));
+            } else {
+                const int st = int(g.next & ~kLeafPlain);
+                if (isFinal(st)) mask = 0xFFFF;
+                else for (const Edge& e : out[size_t(st)]) mask |= uint16_t(1u << (e.ch & 15));
+            }
+            L.chk2[i] = mask;
+        }
+    }
+
     // deeper transitions (source depth >= K): hash rows, hot by depth
     for (size_t qi = 0; qi < sources.size(); qi++) {
         const int s = sources[qi];
@@ -424,6 +446,13 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L) {
     for (size_t d = 1; d < upto.size(); d++) upto[d] += upto[d - 1];
     // shared-memory budget: next2 first (touched by every survivor), then hash rows by depth,
     // and chains + tails too when everything fits
+    // the check stage only works from shared memory: it comes first, or it is dropped
+    const size_t chkBytes = ((L.chk2.size() * 2 + 15) / 16) * 16;
+    if (chkBytes > hotBudgetBytes) {
+        L.chk2.clear();
+    } else {
+        hotBudgetBytes -= chkBytes;
+    }
     const size_t next2Bytes = ((L.next2.size() * 4 + 15) / 16) * 16 * (L.best2.empty() ? 1 : 2);
     if (next2Bytes <= hotBudgetBytes) {
         L.next2Hot = true;

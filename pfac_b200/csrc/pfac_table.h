@@ -85,6 +85,10 @@ struct DeviceLayout {
     std::vector<uint16_t> rank2;     // 2048 prefix popcounts
     std::vector<uint32_t> next2;     // one entry per set bit, in idx order
     std::vector<uint32_t> best2;     // parallel to next2; empty when all zero
+    // chk2[rank]: which (byte & 15) values can follow the K-gram and still lead somewhere; 0xFFFF
+    // when the K-gram alone already yields a result.  Used as a second prefilter stage (in shared
+    // memory) when the first one lets many positions through; empty = stage off.
+    std::vector<uint16_t> chk2;
     bool next2Hot = false;           // next2 (+ best2) fit the shared-memory budget
     std::vector<uint32_t> hot;       // edges with source depth in [K,hotDepth)  -> smem
     std::vector<uint32_t> cold;      // edges with source depth >= hotDepth      -> global/L2
@@ -102,7 +106,7 @@ struct DeviceLayout {
     int pre2BitsSet = 0;
     int rootFanout = 0;
     size_t deviceBytes() const {
-        return sizeof(root) + sizeof(lut) + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 +
+        return sizeof(root) + sizeof(lut) + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 + chk2.size() * 2 +
                best2.size() * 4 + hot.size() * 4 +
                cold.size() * 4 + chains.size() * 4 + tails.size();
     }

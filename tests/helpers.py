@@ -40,6 +40,9 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None):
             best = int(L["best2"][rank]) if L["best2"].size else 0
         if avail < K:
             return best                            # b == 8 only: the second symbol was padding
+        if L["chk2"].size and avail > K:           # second stage: can the next byte lead anywhere?
+            if not (int(L["chk2"][rank]) >> (int(text[start + K]) & 15)) & 1:
+                return 0                           # (entries with a result of their own are all ones)
         v = int(L["next2"][rank])                  # the walk after its K-th symbol
         d = K - 1
     else:
