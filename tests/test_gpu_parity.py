@@ -406,3 +406,53 @@ def test_multi_gpu_driver_one_process(cuda, tmp_path, monkeypatch):
         assert np.array_equal(pf.matchFromHost(text), want)
         pf_mem = pf.tableInfo()
         assert pf_mem["num_patterns"] == len(pats)
+
+
+def test_threads_sharing_one_handle_and_private_streams(cuda, tmp_path):
+    """Reference r1.2 supports several host threads on one handle (NOTICE; user guide r1.2 p.2).  Here:
+    concurrent dense and reduce calls from four threads on one handle, and PFAC_setStream with a
+    caller-owned stream, must all give the oracle's result."""
+    import threading
+    from pfac_b200 import PFAC
+    pats = synth.patterns_c2(500, seed=61)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    texts = [synth.make_text("random", 700 + i, 0, 3_000_001 + 7 * i, 3_000_001 + 7 * i, pats, 600) for i in range(4)]
+    wants = [orc.match(t) for t in texts]
+    errors = []
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+
+        def work(i):
+            try:
+                torch.cuda.set_device(0)
+                for rep in range(3):
+                    got = _dev_match(pf, texts[i], cuda)
+                    if not np.array_equal(got, wants[i]):
+                        errors.append("dense thread %d rep %d" % (i, rep))
+                    m, ids, pos = _dev_reduce(pf, texts[i], cuda, pos64=True)
+                    wid, wpos = orc.reduce(wants[i])
+                    if m != wid.size or not np.array_equal(ids[:m], wid) or not np.array_equal(pos[:m], wpos):
+                        errors.append("reduce thread %d rep %d" % (i, rep))
+            except Exception as e:  # noqa: BLE001
+                errors.append("thread %d: %r" % (i, e))
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+
+        # caller-owned stream: work is ordered on it, not on the legacy default stream
+        stream = torch.cuda.Stream()
+        pf.setStream(stream)
+        with torch.cuda.stream(stream):
+            d_in = torch.from_numpy(texts[0]).to(cuda, non_blocking=True)
+            d_out = torch.empty(texts[0].size, dtype=torch.int32, device=cuda)
+            pf.matchFromDevice(d_in, texts[0].size, d_out)
+            host = d_out.to("cpu", non_blocking=False)
+        stream.synchronize()
+        assert np.array_equal(host.numpy(), wants[0])
+        pf.setStream(None)
+        assert np.array_equal(_dev_match(pf, texts[1], cuda), wants[1])
