@@ -35,7 +35,6 @@ size_t envBytes(const char* name, size_t dflt, size_t unit) {
 
 struct HostPipe {  // cached buffers of the matchFromHost* pipelines
     cudaStream_t stream[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
     unsigned char* d_in[2] = {nullptr, nullptr};
     int* d_out[2] = {nullptr, nullptr};  // dense results, or ids (reduce)
     int* d_pos[2] = {nullptr, nullptr};  // reduce positions
@@ -95,7 +94,6 @@ void freePipe(HostPipe& p) {
         if (p.d_in[i]) cudaFree(p.d_in[i]);
         if (p.d_out[i]) cudaFree(p.d_out[i]);
         if (p.d_pos[i]) cudaFree(p.d_pos[i]);
-        if (p.done[i]) cudaEventDestroy(p.done[i]);
         if (p.stream[i]) cudaStreamDestroy(p.stream[i]);
     }
     p = HostPipe();
@@ -245,7 +243,6 @@ PFAC_status_t ensurePipe(PFAC_handle_t h, bool needPos) {
     freePipe(p);
     for (int i = 0; i < 2; i++) {
         if (cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
-        if (cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_in[i]), inCap) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
         // positions may be 64-bit (multi-GPU / shard forms)
@@ -275,7 +272,9 @@ PFAC_status_t PFAC_create(PFAC_handle_t* handle) {
     int major = 0, sms = 0;
     if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device)) != cudaSuccess) return PFAC_status_t(e);
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return PFAC_status_t(e);
-    if (major != 10) return PFAC_STATUS_ARCH_MISMATCH;  // kernels are built for sm_100a only
+    int minor = 0;
+    if ((e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device)) != cudaSuccess) return PFAC_status_t(e);
+    if (major != 10 || minor != 0) return PFAC_STATUS_ARCH_MISMATCH;  // kernels are built for sm_100a only
     PFAC_context* h = new (std::nothrow) PFAC_context();
     if (!h) return PFAC_STATUS_ALLOC_FAILED;
     h->device = device;

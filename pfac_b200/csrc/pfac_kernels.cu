@@ -40,9 +40,8 @@ constexpr int kDenseWarps = 32;
 constexpr int kDenseThreads = kDenseWarps * 32;
 constexpr int kDenseMaxHalo = 64;              // staged halo cap; walks that run further read global memory
 
-// look-back descriptor: [63:62] status, [61:0] value
+// CTA-tile aggregate word: [63:62] != 0 once published, [61:0] match count
 constexpr unsigned long long kStatusAgg = 1ull << 62;
-constexpr unsigned long long kStatusIncl = 2ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
 struct KParams {
