@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""Runs one BASELINE.json config end to end: generate the synthetic workload, check the CUDA
+"""Parity + timing runner for the BASELINE.json configs (lives under tests/ because it loads the
+oracle).  Runs one config end to end: generate the synthetic workload, check the CUDA
 path bit-exactly against the oracle (chunked, so inputs >= 2^31 bytes work), time it, and print
 one JSON line (also appended to gpurun_out/configs.jsonl).
 
-    python tools/run_configs.py --config c2|c3|c4|c4dense|c5 [--bytes N] [--check-bytes M] [--steps K]
-    python -m torch.distributed.run --nproc-per-node 8 ... tools/run_configs.py --config c5
+    python tests/run_configs.py --config c2|c3|c4|c4dense|c5 [--bytes N] [--check-bytes M] [--steps K]
+    python -m torch.distributed.run --nproc-per-node 8 ... tests/run_configs.py --config c5
 
 Configs:
   c2       1,000 patterns len 4-32 (255-symbol alphabet), 1 GiB planted random text, dense
