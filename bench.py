@@ -327,7 +327,23 @@ def main():
         if world == 1:
             # the shard ends at the end of the stream, so the host call and the shard call agree
             assert bool((torch.from_numpy(h_out.numpy()).to(dev) == d_out).all().item()), "e2e result differs"
-        del h_in, h_out
+        del h_out
+        # the same host-buffer input through the reduced API: 8 bytes per match come back instead of
+        # 4 bytes per input byte (extra information; the contract's e2e is the dense call above)
+        if owned < 2 ** 31:
+            r_id = np.empty(owned, dtype=np.int32)    # pageable: only the first M entries are touched
+            r_pos = np.empty(owned, dtype=np.int32)
+            ids, pos = pf.matchFromHostReduce(h_in, r_id, r_pos, size=owned)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                ids, pos = pf.matchFromHostReduce(h_in, r_id, r_pos, size=owned)
+            dt = max_over_ranks(time.perf_counter() - t0)
+            e2e["reduce_api"] = {"value": owned * world * args.e2e_steps / dt / 1e9, "unit": UNIT,
+                                 "h2d_bytes_per_step": int(owned), "d2h_bytes_per_step": int(ids.size) * 8,
+                                 "api": "PFAC_matchFromHostReduce", "matches": int(ids.size)}
+            del r_id, r_pos
+        del h_in
 
     # ---- fused reduce path on the same shard, with the cross-GPU count scan --------------------------
     reduce_info = None

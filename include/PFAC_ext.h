@@ -33,6 +33,13 @@ PFAC_status_t PFAC_setStream(PFAC_handle_t handle, void *cuda_stream);
  * src/PFAC_reorder_Table.cpp:121-231), image = the bytes the file would hold. */
 PFAC_status_t PFAC_readPatternFromMemory(PFAC_handle_t handle, const char *image, size_t size);
 
+/* ---- patterns from arrays: explicit lengths, so any byte may occur in a pattern (the file
+ * grammar cannot express 0x0A, user guide r1.2 p.26).  Pattern i gets ID i+1; order, state
+ * numbering and longest-match semantics are those of the file form.  Zero-length patterns are
+ * rejected (PFAC_STATUS_INVALID_PARAMETER). */
+PFAC_status_t PFAC_readPatternFromArrays(PFAC_handle_t handle, const char *const *patterns,
+                                         const size_t *lengths, size_t num_patterns);
+
 /* ---- shard form of PFAC_matchFromDevice: results for positions [0,n_owned); walks may read
  * input[0,n_total), n_total >= n_owned (owned bytes followed by the tail halo, which must be
  * the real following bytes; >= maxPatternLen-1 of them unless the stream ends).  This is the
@@ -91,6 +98,9 @@ PFAC_status_t PFAC_tableCompile(const char *image, size_t size, size_t hot_budge
                                 PFAC_table_t *table);
 PFAC_status_t PFAC_tableCompileFile(const char *filename, size_t hot_budget_bytes,
                                     PFAC_table_t *table);
+PFAC_status_t PFAC_tableCompileArrays(const char *const *patterns, const size_t *lengths,
+                                      size_t num_patterns, size_t hot_budget_bytes,
+                                      PFAC_table_t *table);
 PFAC_status_t PFAC_tableDestroy(PFAC_table_t table);
 PFAC_status_t PFAC_tableDump(PFAC_table_t table, FILE *fp);
 PFAC_status_t PFAC_tableDumpToFile(PFAC_table_t table, const char *filename);

@@ -104,6 +104,8 @@ def load_library():
         "PFAC_dumpTransitionTableToFile": [vp, cp],
         "PFAC_readPatternFromFile": [vp, cp],
         "PFAC_readPatternFromMemory": [vp, cp, sz],
+        "PFAC_readPatternFromArrays": [vp, vp, vp, sz],
+        "PFAC_tableCompileArrays": [vp, vp, sz, sz, ctypes.POINTER(vp)],
         "PFAC_matchFromDevice": [vp, vp, sz, vp],
         "PFAC_matchFromHost": [vp, vp, sz, vp],
         "PFAC_matchFromDeviceReduce": [vp, vp, sz, vp, vp, ip],
@@ -219,6 +221,13 @@ class PFAC:
         image = bytes(image)
         _check(self._L.PFAC_readPatternFromMemory(self._h, image, len(image)),
                "PFAC_readPatternFromMemory")
+
+    def readPatternFromArrays(self, patterns):
+        """patterns: list of bytes; any byte value allowed, ID = index + 1."""
+        ptrs, lens, keep = _pattern_arrays(patterns)
+        _check(self._L.PFAC_readPatternFromArrays(self._h, ptrs, lens, len(patterns)),
+               "PFAC_readPatternFromArrays")
+        del keep
 
     def dumpTransitionTable(self, filename):
         _check(self._L.PFAC_dumpTransitionTableToFile(self._h, os.fsencode(filename)),
@@ -336,6 +345,13 @@ class PFACMultiGPU:
         return ids[:m.value], pos[:m.value]
 
 
+def _pattern_arrays(patterns):
+    keep = [ctypes.create_string_buffer(bytes(p), len(p)) for p in patterns]
+    ptrs = (ctypes.c_void_p * len(keep))(*[ctypes.addressof(b) for b in keep])
+    lens = (ctypes.c_size_t * len(keep))(*[len(p) for p in patterns])
+    return ptrs, lens, keep
+
+
 def _host_u8(x):
     if isinstance(x, (bytes, bytearray)):
         return np.frombuffer(bytes(x), dtype=np.uint8)
@@ -353,10 +369,15 @@ def _host_len(x):
 class TableCompiler:
     """Host-only table compiler (no GPU needed): PFAC_tableCompile* in include/PFAC_ext.h."""
 
-    def __init__(self, pattern_file=None, image=None, hot_budget_bytes=24 * 1024):
+    def __init__(self, pattern_file=None, image=None, hot_budget_bytes=24 * 1024, patterns=None):
         self._L = load_library()
         self._t = ctypes.c_void_p()
-        if pattern_file is not None:
+        if patterns is not None:
+            ptrs, lens, keep = _pattern_arrays(patterns)
+            st = self._L.PFAC_tableCompileArrays(ptrs, lens, len(patterns), hot_budget_bytes,
+                                                 ctypes.byref(self._t))
+            del keep
+        elif pattern_file is not None:
             st = self._L.PFAC_tableCompileFile(os.fsencode(pattern_file), hot_budget_bytes,
                                                ctypes.byref(self._t))
         else:

@@ -396,6 +396,23 @@ PFAC_status_t PFAC_readPatternFromMemory(PFAC_handle_t handle, const char* image
     return loadImage(handle, image, size);
 }
 
+PFAC_status_t PFAC_readPatternFromArrays(PFAC_handle_t handle, const char* const* patterns, const size_t* lengths,
+                                         size_t num_patterns) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    std::lock_guard<std::mutex> lock(handle->mu);
+    if (handle->patternsReady) {
+        cudaDeviceSynchronize();
+        freePatterns(handle);
+    }
+    handle->patternFile[0] = 0;
+    int st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, handle->machine);
+    if (st != PFAC_STATUS_SUCCESS) { freePatterns(handle); return PFAC_status_t(st); }
+    handle->patternsReady = true;
+    PFAC_status_t bs = bindTable(handle);
+    if (bs != PFAC_STATUS_SUCCESS) { freePatterns(handle); return bs; }
+    return PFAC_STATUS_SUCCESS;
+}
+
 PFAC_status_t PFAC_setStream(PFAC_handle_t handle, void* cuda_stream) {
     if (!handle) return PFAC_STATUS_INVALID_HANDLE;
     handle->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -777,6 +794,19 @@ PFAC_status_t PFAC_tableCompile(const char* image, size_t size, size_t hot_budge
     PFAC_table* t = new (std::nothrow) PFAC_table();
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
     int st = pfac::buildMachine(image, size, t->machine);
+    if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
+    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout);
+    *table = t;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableCompileArrays(const char* const* patterns, const size_t* lengths, size_t num_patterns,
+                                      size_t hot_budget_bytes, PFAC_table_t* table) {
+    if (!table) return PFAC_STATUS_INVALID_PARAMETER;
+    *table = nullptr;
+    PFAC_table* t = new (std::nothrow) PFAC_table();
+    if (!t) return PFAC_STATUS_ALLOC_FAILED;
+    int st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, t->machine);
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
     pfac::compileLayout(t->machine, hot_budget_bytes, t->layout);
     *table = t;

@@ -23,16 +23,17 @@ struct Pat {
 // later ID wins in the matching table.
 struct PatLess {
     const char* base;
+    const int* len;  // by id
     bool operator()(const Pat& a, const Pat& b) const {
         const signed char* s = reinterpret_cast<const signed char*>(base + a.off);
         const signed char* t = reinterpret_cast<const signed char*>(base + b.off);
-        for (;;) {
-            signed char sc = *s++, tc = *t++;
-            bool se = (sc == '\n'), te = (tc == '\n');
-            if (se || te) return se && !te;
-            if (sc < tc) return true;
-            if (sc > tc) return false;
+        const int ls = len[a.id], lt = len[b.id];
+        const int n = ls < lt ? ls : lt;
+        for (int i = 0; i < n; i++) {
+            if (s[i] < t[i]) return true;
+            if (s[i] > t[i]) return false;
         }
+        return ls < lt;  // proper prefix first; equal strings: not less (stable sort keeps file order)
     }
 };
 
@@ -76,6 +77,8 @@ int fillBuckets(const std::vector<FlatEdge>& edges, size_t begin, size_t end, ui
     return std::max(maxProbe, longest + 1);
 }
 
+int finishMachine(Machine& m, std::vector<Pat>& pats, const std::vector<int>& lens);
+
 }  // namespace
 
 int buildMachine(const char* image, size_t size, Machine& m) {
@@ -105,6 +108,15 @@ int buildMachine(const char* image, size_t size, Machine& m) {
         }
         lineStart = i + 1;
     }
+    return finishMachine(m, pats, lens);
+}
+
+namespace {
+
+// patterns given as (offset into m.image, id) + lengths: order, trie, numbering
+int finishMachine(Machine& m, std::vector<Pat>& pats, const std::vector<int>& lens) {
+    const char* buf = m.image.data();
+    const size_t size = m.image.size();
     const int k = int(pats.size());
     m.numPatterns = m.numFinal = k;
     m.initialState = k + 1;
@@ -115,7 +127,7 @@ int buildMachine(const char* image, size_t size, Machine& m) {
         m.offById[size_t(i) + 1] = pats[size_t(i)].off;
         m.maxPatternLen = std::max(m.maxPatternLen, lens[size_t(i)]);
     }
-    std::stable_sort(pats.begin(), pats.end(), PatLess{buf});
+    std::stable_sort(pats.begin(), pats.end(), PatLess{buf, m.lenById.data()});
     m.sortedOff.resize(size_t(k));
     m.sortedId.resize(size_t(k));
     for (int i = 0; i < k; i++) {
@@ -161,6 +173,31 @@ int buildMachine(const char* image, size_t size, Machine& m) {
     for (int i = 1; i <= k; i++)
         if (m.rows[size_t(i)].empty()) m.numLeaves++;  // reference PFAC.cpp:716-722
     return PFAC_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+// Patterns from arrays: any byte may occur (the file grammar cannot express 0x0A), lengths are
+// explicit, IDs are 1-based array order.  Same order / numbering rules as the file form.
+int buildMachineFromArrays(const char* const* ptrs, const size_t* lens, size_t n, Machine& m) {
+    m = Machine();
+    if ((!ptrs || !lens) && n != 0) return PFAC_STATUS_INVALID_PARAMETER;
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (lens[i] == 0 || !ptrs[i]) return PFAC_STATUS_INVALID_PARAMETER;  // empty patterns match nothing
+        total += lens[i] + 1;
+    }
+    if (total >= size_t(kMaxStates)) return PFAC_STATUS_INTERNAL_ERROR;
+    std::vector<Pat> pats;
+    std::vector<int> plens;
+    m.image.reserve(total + 1);
+    for (size_t i = 0; i < n; i++) {
+        pats.push_back(Pat{m.image.size(), int(i) + 1});
+        plens.push_back(int(lens[i]));
+        m.image.append(ptrs[i], lens[i]);
+        m.image.push_back('\n');  // storage separator only; lengths are authoritative
+    }
+    return finishMachine(m, pats, plens);
 }
 
 void dumpMachine(const Machine& m, FILE* fp) {

@@ -41,6 +41,7 @@ struct Machine {
 
 // Returns a PFAC_status_t value (0 = success).
 int buildMachine(const char* image, size_t size, Machine& m);
+int buildMachineFromArrays(const char* const* ptrs, const size_t* lens, size_t n, Machine& m);
 
 // Text dump, byte-identical to reference PFAC_dumpTransitionTable (PFAC.cpp:1188-1246).
 void dumpMachine(const Machine& m, FILE* fp);

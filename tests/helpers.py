@@ -102,3 +102,23 @@ def probe(tab, mul, key):
             return -1  # trap
         b = 0 if b + 1 == nb else b + 1
     raise AssertionError("probe did not terminate: table has no empty slot")
+
+
+def brute_force_match(patterns, text):
+    """Reference semantics restated without the file grammar (needed for patterns that contain 0x0A):
+    result[i] = ID (index + 1) of the longest pattern that is a prefix of text[i:], else 0; of two
+    identical patterns the later ID wins."""
+    text = bytes(text)
+    by_len = {}
+    for i, p in enumerate(patterns):
+        by_len.setdefault(len(p), {})[bytes(p)] = i + 1
+    lens = sorted(by_len, reverse=True)
+    out = np.zeros(len(text), dtype=np.int32)
+    for i in range(len(text)):
+        for L in lens:
+            if i + L <= len(text):
+                pid = by_len[L].get(text[i:i + L])
+                if pid:
+                    out[i] = pid
+                    break
+    return out

@@ -456,3 +456,23 @@ def test_threads_sharing_one_handle_and_private_streams(cuda, tmp_path):
         assert np.array_equal(host.numpy(), wants[0])
         pf.setStream(None)
         assert np.array_equal(_dev_match(pf, texts[1], cuda), wants[1])
+
+
+def test_patterns_from_arrays_with_newlines(cuda):
+    """PFAC_readPatternFromArrays: patterns may contain 0x0A, which the reference's file grammar cannot
+    express (user guide r1.2 p.26); checked against a brute-force restatement of the semantics."""
+    from pfac_b200 import PFAC
+    from tests.helpers import brute_force_match
+    rng = np.random.default_rng(12)
+    pats = [b"a\nb", b"\n", b"\n\n\x00", b"line1\nline2\n", b"xyz", b"xy", b"\x00\n\xff", b"q", b"GET /\r\n\r\n"]
+    text = rng.integers(0, 256, size=40_000, dtype=np.uint8)
+    for p in pats * 40:
+        at = int(rng.integers(0, text.size - len(p)))
+        text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    want = brute_force_match(pats, text)
+    with PFAC() as pf:
+        pf.readPatternFromArrays(pats)
+        assert np.array_equal(_dev_match(pf, text, cuda), want)
+        m, ids, pos = _dev_reduce(pf, text, cuda)
+        nz = np.flatnonzero(want)
+        assert m == nz.size and np.array_equal(pos[:m], nz) and np.array_equal(ids[:m], want[nz])

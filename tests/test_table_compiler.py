@@ -14,7 +14,7 @@ import pytest
 
 from oracle import Oracle
 from pfac_b200 import PFACError, Status, TableCompiler, synth
-from tests.helpers import emulate_layout_walk, read_patterns
+from tests.helpers import brute_force_match, emulate_layout_walk, read_patterns
 
 
 def _layout(tc):
@@ -197,3 +197,33 @@ def test_symbol_coded_prefilter_small_alphabets(which, hot_kb):
     bad = np.flatnonzero(got != want)
     assert bad.size == 0, "%s: first mismatch at %d: got %d want %d" % (name, bad[0], got[bad[0]], want[bad[0]])
     assert (want > 0).sum() > 100
+
+
+def test_patterns_from_arrays_any_byte():
+    """PFAC_tableCompileArrays: explicit lengths, so 0x0A (and everything else) may occur in a pattern.
+    For newline-free sets the result is the file form's, including the dump."""
+    rng = np.random.default_rng(9)
+    pats = [b"a\nb", b"\n", b"\n\n\x00", b"line1\nline2\n", b"xyz", b"xy", b"\x00\n\xff", b"q"]
+    tc = TableCompiler(patterns=pats)
+    L = tc.layout()
+    text = np.frombuffer(b"a\nbxyz\n\n\x00line1\nline2\nq\x00\n\xffxy\n", dtype=np.uint8)
+    want = brute_force_match(pats, text)
+    got = np.array([emulate_layout_walk(L, len(pats), text, i) for i in range(text.size)], dtype=np.int32)
+    assert np.array_equal(got, want) and set(want) >= {1, 2, 3, 4, 5, 7, 8}
+    big = rng.integers(0, 256, size=3000, dtype=np.uint8)
+    for p in pats * 5:
+        at = int(rng.integers(0, big.size - len(p)))
+        big[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    want = brute_force_match(pats, big)
+    got = np.array([emulate_layout_walk(L, len(pats), big, i) for i in range(big.size)], dtype=np.int32)
+    assert np.array_equal(got, want)
+    # same machine as the file form when no pattern holds a newline
+    plain = synth.patterns_c2(120, seed=3, min_len=1, max_len=9, prefix_pairs=20)
+    a = TableCompiler(patterns=plain)
+    b = TableCompiler(image=synth.pattern_file_image(plain))
+    assert a.info() == b.info()
+    for k, v in a.layout().items():
+        assert np.array_equal(v, b.layout()[k]), k
+    with pytest.raises(PFACError) as e:
+        TableCompiler(patterns=[b"ab", b""])
+    assert e.value.status == Status.INVALID_PARAMETER
