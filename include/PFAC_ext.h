@@ -143,6 +143,19 @@ PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char *h_inputString
                                              int *h_matched_result, long long *h_pos,
                                              unsigned long long *h_num_matched);
 
+/*
+ * Pageable (malloc'ed) host buffers -- what the reference's callers pass (reference
+ * test/simple_example.cpp) -- are moved through library-owned pinned staging buffers by a small
+ * pool of host threads, overlapped with the DMA and the kernel of the neighbouring chunks.
+ * Pinned (cudaHostAlloc / cudaHostRegister) buffers are DMA'd directly.  Environment:
+ *   PFAC_B200_COPY_THREADS   host threads per process that copy, caller included (default min(8, cores/2))
+ *   PFAC_B200_STAGE_CHUNK_MB bytes of input per staged chunk (default 8)
+ *   PFAC_B200_STAGE=0        no staging: pageable pointers go straight to cudaMemcpyAsync
+ * PFAC_hostCopy is that pool's memcpy (host only, no GPU needed; exported for tests and for callers
+ * that fill their own pinned buffers).
+ */
+PFAC_status_t PFAC_hostCopy(void *dst, const void *src, size_t bytes);
+
 /* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
 unsigned long long PFAC_kernelLaunchCount(void);
 

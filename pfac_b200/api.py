@@ -127,6 +127,7 @@ def load_library():
         "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 3,
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_memoryUsage": [vp],
+        "PFAC_hostCopy": [vp, vp, sz],
         "PFAC_mgpuCreate": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int],
         "PFAC_mgpuDestroy": [vp],
         "PFAC_mgpuReadPatternFromFile": [vp, cp],
@@ -143,6 +144,14 @@ def load_library():
     L.PFAC_kernelLaunchCount.restype = ull
     _lib = L
     return L
+
+
+def host_copy(dst, src):
+    """PFAC_hostCopy: the staging pool's multi-threaded memcpy (host only).  dst, src: ndarrays."""
+    if dst.nbytes != src.nbytes:
+        raise ValueError("size mismatch")
+    _check(load_library().PFAC_hostCopy(dst.ctypes.data, src.ctypes.data, src.nbytes), "PFAC_hostCopy")
+    return dst
 
 
 def kernel_launch_count():

@@ -3,9 +3,14 @@
 //
 // Mirrors the behaviour of reference PFAC/src/PFAC.cpp (each entry point cites its lines);
 // the implementation is new.  There is no CPU matcher in this library.
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <new>
@@ -13,6 +18,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <emmintrin.h>  // SSE2 streaming stores (x86-64 baseline)
 
 #include "PFAC.h"
 #include "PFAC_ext.h"
@@ -33,6 +39,156 @@ size_t envBytes(const char* name, size_t dflt, size_t unit) {
     return size_t(x) * unit;
 }
 
+// ---- pageable host buffers -------------------------------------------------------------------
+// Callers of the reference pass malloc'ed memory (reference test/simple_example.cpp).  cudaMemcpyAsync
+// on pageable memory goes through the driver's small bounce buffers and does not overlap: measured
+// 3.3 GB/s through PFAC_matchFromHost on 1 GiB, against 13.2 GB/s with pinned buffers.  So the
+// library owns pinned staging buffers and moves user memory to/from them with a few host threads
+// while the DMA and the kernel of the neighbouring chunks run.
+class CopyPool {
+public:
+    struct Job {  // one memcpy split over the pool; finish() before the job or its buffers go away
+        std::atomic<int> left{0};
+    };
+
+    explicit CopyPool(int workers) {
+        for (int i = 0; i < workers; i++) threads_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread& t : threads_) t.join();
+    }
+
+    void start(Job& job, void* dst, const void* src, size_t bytes) {
+        if (!bytes) return;
+        const size_t kMinSlice = size_t(1) << 20;
+        const size_t parts = std::min(threads_.size() + 1, (bytes + kMinSlice - 1) / kMinSlice);
+        const size_t per = (((bytes + parts - 1) / parts) + 63) & ~size_t(63);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            for (size_t o = 0; o < bytes; o += per) {
+                job.left.fetch_add(1, std::memory_order_relaxed);
+                q_.push_back(Task{static_cast<char*>(dst) + o, static_cast<const char*>(src) + o,
+                                  std::min(per, bytes - o), &job});
+            }
+        }
+        cv_.notify_all();
+    }
+
+    void finish(Job& job) {  // the calling thread copies too, then waits for the stragglers
+        while (job.left.load(std::memory_order_acquire) > 0) {
+            Task t{};
+            bool have = false;
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                if (!q_.empty()) {
+                    t = q_.front();
+                    q_.pop_front();
+                    have = true;
+                }
+            }
+            if (have) exec(t);
+            else std::this_thread::yield();
+        }
+    }
+
+    void copy(void* dst, const void* src, size_t bytes) {
+        Job job;
+        start(job, dst, src, bytes);
+        finish(job);
+    }
+
+private:
+    struct Task {
+        char* dst;
+        const char* src;
+        size_t bytes;
+        Job* job;
+    };
+    // Staging copies are large, one-shot and never re-read by the copying core: streaming stores
+    // skip the read-for-ownership of the destination lines (a third of the memory traffic).
+    static void streamCopy(char* dst, const char* src, size_t n) {
+        if (n < (size_t(64) << 10)) {
+            memcpy(dst, src, n);
+            return;
+        }
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+        memcpy(dst, src, head);
+        dst += head;
+        src += head;
+        n -= head;
+        const size_t blocks = n / 64;
+        for (size_t i = 0; i < blocks; i++, src += 64, dst += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 48), d);
+        }
+        _mm_sfence();
+        memcpy(dst, src, n - blocks * 64);
+    }
+    static void exec(const Task& t) {
+        if (streamingStores()) streamCopy(t.dst, t.src, t.bytes);
+        else memcpy(t.dst, t.src, t.bytes);
+        t.job->left.fetch_sub(1, std::memory_order_release);
+    }
+    static bool streamingStores() {
+        static const bool on = envBytes("PFAC_B200_COPY_STREAM", 0, 1) != 0;
+        return on;
+    }
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;  // stop_
+                t = q_.front();
+                q_.pop_front();
+            }
+            exec(t);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Task> q_;
+    bool stop_ = false;
+};
+
+// one pool per process, shared by the handles that stage; joined when the last of them goes
+std::shared_ptr<CopyPool> acquireCopyPool() {
+    static std::mutex m;
+    static std::weak_ptr<CopyPool> weak;
+    std::lock_guard<std::mutex> lock(m);
+    std::shared_ptr<CopyPool> sp = weak.lock();
+    if (!sp) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const size_t dflt = std::min<size_t>(8, std::max<size_t>(1, hw / 2));
+        const size_t n = std::max<size_t>(1, envBytes("PFAC_B200_COPY_THREADS", dflt, 1));
+        sp = std::make_shared<CopyPool>(int(n) - 1);  // the caller is the n-th copier
+        weak = sp;
+    }
+    return sp;
+}
+
+bool isPageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 struct HostPipe {  // cached buffers of the matchFromHost* pipelines
     cudaStream_t stream[2] = {nullptr, nullptr};
     unsigned char* d_in[2] = {nullptr, nullptr};
@@ -41,6 +197,12 @@ struct HostPipe {  // cached buffers of the matchFromHost* pipelines
     size_t chunk = 0;                    // owned bytes per chunk
     size_t inCap = 0;
     bool hasPos = false;
+    // pinned staging for pageable user buffers (allocated on first use)
+    unsigned char* s_in[3] = {nullptr, nullptr, nullptr};
+    int* s_out[2] = {nullptr, nullptr};
+    size_t stageChunk = 0;               // owned bytes per staged chunk (<= chunk)
+    size_t stageInCap = 0;
+    std::shared_ptr<CopyPool> pool;
 };
 
 }  // namespace
@@ -89,7 +251,20 @@ void freePatterns(PFAC_handle_t h) {  // reference PFAC_freeResource, PFAC.cpp:2
     h->patternsReady = false;
 }
 
+void freeStage(HostPipe& p) {
+    for (int i = 0; i < 3; i++) {
+        if (p.s_in[i]) cudaFreeHost(p.s_in[i]);
+        p.s_in[i] = nullptr;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (p.s_out[i]) cudaFreeHost(p.s_out[i]);
+        p.s_out[i] = nullptr;
+    }
+    p.stageChunk = p.stageInCap = 0;
+}
+
 void freePipe(HostPipe& p) {
+    freeStage(p);
     for (int i = 0; i < 2; i++) {
         if (p.d_in[i]) cudaFree(p.d_in[i]);
         if (p.d_out[i]) cudaFree(p.d_out[i]);
@@ -251,6 +426,31 @@ PFAC_status_t ensurePipe(PFAC_handle_t h, bool needPos) {
     p.chunk = chunk;
     p.inCap = inCap;
     p.hasPos = needPos;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// PFAC_B200_STAGE=0 hands pageable pointers straight to cudaMemcpyAsync (for A/B measurements)
+bool stagingEnabled() { return envBytes("PFAC_B200_STAGE", 1, 1) != 0; }
+
+// pinned staging buffers of the pageable paths; after ensurePipe, caller holds h->pipeMu
+PFAC_status_t ensureStage(PFAC_handle_t h, bool needIn, bool needOut) {
+    HostPipe& p = h->pipe;
+    size_t sc = envBytes("PFAC_B200_STAGE_CHUNK_MB", 8, size_t(1) << 20);
+    if (sc == 0 || sc > p.chunk) sc = p.chunk;
+    const size_t halo = size_t(h->machine.maxPatternLen > 1 ? h->machine.maxPatternLen - 1 : 0);
+    const size_t inCap = ((sc + halo + 255) / 256) * 256;
+    if (p.stageChunk != sc || p.stageInCap < inCap) {
+        freeStage(p);
+        p.stageChunk = sc;
+        p.stageInCap = inCap;
+    }
+    if (!p.pool) p.pool = acquireCopyPool();
+    if (needIn && !p.s_in[0])
+        for (int i = 0; i < 3; i++)
+            if (cudaMallocHost(reinterpret_cast<void**>(&p.s_in[i]), inCap) != cudaSuccess) { freeStage(p); return PFAC_STATUS_ALLOC_FAILED; }
+    if (needOut && !p.s_out[0])
+        for (int i = 0; i < 2; i++)
+            if (cudaMallocHost(reinterpret_cast<void**>(&p.s_out[i]), sc * 4) != cudaSuccess) { freeStage(p); return PFAC_STATUS_ALLOC_FAILED; }
     return PFAC_STATUS_SUCCESS;
 }
 
@@ -445,7 +645,9 @@ PFAC_status_t PFAC_matchFromDevice(PFAC_handle_t handle, char* d_in, size_t size
 
 // reference PFAC.cpp:879-961.  Chunks of the host input (+ tail halo) go H2D on two private
 // streams, each followed by its kernel and the D2H of its 4-byte-per-position results, so
-// copy-in, match and copy-out of neighbouring chunks overlap.  Synchronous, like the reference.
+// copy-in, match and copy-out of neighbouring chunks overlap.  Pinned user buffers are DMA'd
+// directly; pageable ones go through the pinned staging buffers, copied by the CopyPool while the
+// other slot's chunk is on the GPU.  Synchronous, like the reference.
 // host shard: results for [0,n_owned), input bytes [0,n_total) (owned + tail halo), both on the host
 static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size_t n_owned, size_t n_total,
                                     int* h_out) {
@@ -453,21 +655,51 @@ static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size
     PFAC_status_t st = ensurePipe(handle, false);
     if (st != PFAC_STATUS_SUCCESS) return st;
     HostPipe& p = handle->pipe;
+    const bool stIn = stagingEnabled() && isPageable(h_in);
+    const bool stOut = stagingEnabled() && isPageable(h_out);
+    const bool staged = stIn || stOut;
+    if (staged && (st = ensureStage(handle, stIn, stOut)) != PFAC_STATUS_SUCCESS) return st;
+    const size_t chunk = staged ? p.stageChunk : p.chunk;
     const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
+    struct Pending {
+        size_t off = 0, owned = 0;
+        bool live = false;
+    } pend[2];
+    // wait for a slot's chunk; staged results then move from the pinned buffer to the caller's
+    auto drain = [&](int sl) -> cudaError_t {
+        if (!pend[sl].live) return cudaSuccess;
+        pend[sl].live = false;
+        cudaError_t r = cudaStreamSynchronize(p.stream[sl]);
+        if (r == cudaSuccess && stOut) p.pool->copy(h_out + pend[sl].off, p.s_out[sl], pend[sl].owned * sizeof(int));
+        return r;
+    };
     cudaError_t e = cudaSuccess;
     int slot = 0;
-    for (size_t off = 0; off < n_owned && e == cudaSuccess; off += p.chunk, slot ^= 1) {
-        const size_t owned = (n_owned - off < p.chunk) ? n_owned - off : p.chunk;
+    for (size_t off = 0; off < n_owned && e == cudaSuccess; off += chunk, slot ^= 1) {
+        const size_t owned = (n_owned - off < chunk) ? n_owned - off : chunk;
         const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
         cudaStream_t s = p.stream[slot];
-        e = cudaMemcpyAsync(p.d_in[slot], h_in + off, total, cudaMemcpyHostToDevice, s);
+        const void* src = h_in + off;
+        if (stIn) {  // this slot's previous chunk was drained one iteration ago
+            p.pool->copy(p.s_in[slot], h_in + off, total);
+            src = p.s_in[slot];
+        }
+        e = cudaMemcpyAsync(p.d_in[slot], src, total, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) break;
         e = pfac::launchMatchDense(handle->table, handle->launch, p.d_in[slot], owned, total, p.d_out[slot], s);
         if (e != cudaSuccess) break;
-        e = cudaMemcpyAsync(h_out + off, p.d_out[slot], owned * sizeof(int), cudaMemcpyDeviceToHost, s);
+        e = cudaMemcpyAsync(stOut ? p.s_out[slot] : h_out + off, p.d_out[slot], owned * sizeof(int),
+                            cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) break;
+        pend[slot].off = off;
+        pend[slot].owned = owned;
+        pend[slot].live = true;
+        if (staged) e = drain(slot ^ 1);  // the chunk queued just now keeps the GPU busy meanwhile
     }
-    cudaError_t e0 = cudaStreamSynchronize(p.stream[0]);
-    cudaError_t e1 = cudaStreamSynchronize(p.stream[1]);
+    cudaError_t e0 = drain(slot);  // older chunk first
+    cudaError_t e1 = drain(slot ^ 1);
+    cudaStreamSynchronize(p.stream[0]);
+    cudaStreamSynchronize(p.stream[1]);
     if (e != cudaSuccess) return cudaToStatus(e);
     if (e0 != cudaSuccess) return cudaToStatus(e0);
     return cudaToStatus(e1);
@@ -545,36 +777,61 @@ static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, siz
         if (st != PFAC_STATUS_SUCCESS) return st;
     }
     HostPipe& p = handle->pipe;
+    const bool stIn = stagingEnabled() && isPageable(h_in);
+    if (stIn) {
+        PFAC_status_t st = ensureStage(handle, true, false);
+        if (st != PFAC_STATUS_SUCCESS) return st;
+    }
+    const size_t chunk = stIn ? p.stageChunk : p.chunk;
+    const size_t nchunks = (n_owned + chunk - 1) / chunk;
     const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
     const size_t posBytes = pos64 ? 8 : 4;
     size_t written = 0;
-    int slot = 0;
-    // prefetch the first chunk, then: [H2D next chunk on the other stream] || [reduce this chunk]
-    auto stageIn = [&](size_t off, int sl) -> cudaError_t {
-        const size_t owned = (n_owned - off < p.chunk) ? n_owned - off : p.chunk;
-        const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
-        return cudaMemcpyAsync(p.d_in[sl], h_in + off, total, cudaMemcpyHostToDevice, p.stream[sl]);
+    auto ownedOf = [&](size_t c) { return (n_owned - c * chunk < chunk) ? n_owned - c * chunk : chunk; };
+    auto totalOf = [&](size_t c) {
+        const size_t off = c * chunk, owned = ownedOf(c);
+        return (n_total - off < owned + halo) ? n_total - off : owned + halo;
     };
-    if (stageIn(0, 0) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
-    for (size_t off = 0; off < n_owned; off += p.chunk, slot ^= 1) {
-        const size_t owned = (n_owned - off < p.chunk) ? n_owned - off : p.chunk;
-        const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
-        if (off + p.chunk < n_owned && stageIn(off + p.chunk, slot ^ 1) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    // three stages in flight: [host copy of chunk c+2 into pinned staging] || [H2D of chunk c+1] ||
+    // [fused match+compaction of chunk c].  Pinned input skips the first.
+    CopyPool::Job jobs[3];
+    auto hostStage = [&](size_t c) {
+        if (stIn && c < nchunks) p.pool->start(jobs[c % 3], p.s_in[c % 3], h_in + c * chunk, totalOf(c));
+    };
+    auto h2d = [&](size_t c) -> cudaError_t {
+        const void* src = h_in + c * chunk;
+        if (stIn) {
+            p.pool->finish(jobs[c % 3]);
+            src = p.s_in[c % 3];
+        }
+        return cudaMemcpyAsync(p.d_in[c % 2], src, totalOf(c), cudaMemcpyHostToDevice, p.stream[c % 2]);
+    };
+    auto bail = [&](PFAC_status_t st) {
+        if (stIn) for (int j = 0; j < 3; j++) p.pool->finish(jobs[j]);
+        cudaDeviceSynchronize();
+        return st;
+    };
+    hostStage(0);
+    hostStage(1);
+    if (h2d(0) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+    for (size_t c = 0; c < nchunks; c++) {
+        const int slot = int(c % 2);
+        // slot^1's previous chunk (c-1) has been reduced and read back: its buffers are free
+        if (c + 1 < nchunks && h2d(c + 1) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+        hostStage(c + 2);  // staging slot of chunk c-1, whose H2D finished before its reduce did
         unsigned long long count = 0;
-        PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, total, pos_base + (long long)off, p.d_out[slot],
-                                       p.d_pos[slot], pos64, p.stream[slot], &count);
-        if (st != PFAC_STATUS_SUCCESS) { cudaDeviceSynchronize(); return st; }
+        PFAC_status_t st = reduceShard(handle, p.d_in[slot], ownedOf(c), totalOf(c), pos_base + (long long)(c * chunk),
+                                       p.d_out[slot], p.d_pos[slot], pos64, p.stream[slot], &count);
+        if (st != PFAC_STATUS_SUCCESS) return bail(st);
         if (count) {
             if (cudaMemcpyAsync(h_id + written, p.d_out[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess ||
                 cudaMemcpyAsync(static_cast<char*>(h_pos) + written * posBytes, p.d_pos[slot], count * posBytes,
-                                cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess) {
-                cudaDeviceSynchronize();
-                return PFAC_STATUS_INTERNAL_ERROR;
-            }
+                                cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess)
+                return bail(PFAC_STATUS_INTERNAL_ERROR);
             written += count;
         }
         // the slot is reused two chunks later: its D2H must have drained before the next H2D into it
-        if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
     }
     if (cudaStreamSynchronize(p.stream[0]) != cudaSuccess || cudaStreamSynchronize(p.stream[1]) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
@@ -884,6 +1141,12 @@ PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
 }
 
 // bench.py reports how many of this library's kernels ran inside its timed region
+PFAC_status_t PFAC_hostCopy(void* dst, const void* src, size_t bytes) {
+    if (bytes && (!dst || !src)) return PFAC_STATUS_INVALID_PARAMETER;
+    acquireCopyPool()->copy(dst, src, bytes);
+    return PFAC_STATUS_SUCCESS;
+}
+
 unsigned long long PFAC_kernelLaunchCount(void) { return pfac::kernelLaunchCount(); }
 
 }  // extern "C"

@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 from pfac_b200 import PFAC, PFACError, Status, load_library, library_path
@@ -84,3 +85,25 @@ def test_create_fails_loudly_without_gpu():
     with pytest.raises(PFACError) as e:
         PFAC()
     assert 0 < e.value.status < Status.BASE
+
+
+def test_host_copy_pool_is_exact_and_thread_safe():
+    """PFAC_hostCopy = the copy pool behind the pageable-buffer pipelines (pfac_api.cu CopyPool): odd
+    sizes and alignments, zero bytes, and several caller threads sharing the one pool."""
+    import threading
+    from pfac_b200.api import host_copy, load_library
+    L = load_library()
+    assert L.PFAC_hostCopy(None, None, 0) == 0
+    assert L.PFAC_hostCopy(None, None, 8) == Status.INVALID_PARAMETER
+    rng = np.random.default_rng(9)
+    for n in (1, 63, 64, 65, (1 << 20) - 1, (1 << 20) + 1, 9_437_189):
+        src = rng.integers(0, 256, size=n + 3, dtype=np.uint8)[3:]      # misaligned source
+        dst = np.zeros(n + 5, dtype=np.uint8)
+        host_copy(dst[5:], src)
+        assert np.array_equal(dst[5:], src) and not dst[:5].any()
+    srcs = [rng.integers(0, 256, size=6_000_000 + 4097 * i, dtype=np.uint8) for i in range(4)]
+    dsts = [np.zeros_like(x) for x in srcs]
+    ts = [threading.Thread(target=lambda d=d, x=x: [host_copy(d, x) for _ in range(3)]) for d, x in zip(dsts, srcs)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(np.array_equal(d, x) for d, x in zip(dsts, srcs))

@@ -377,6 +377,52 @@ def test_host_apis_across_pipeline_chunks(cuda, tmp_path, monkeypatch):
             assert np.array_equal(ids, wi) and np.array_equal(pos.astype(np.int64), wp)
 
 
+def test_pageable_and_pinned_host_buffers_agree(cuda, tmp_path, monkeypatch):
+    """Pageable (malloc-style) buffers go through pinned staging + the host copy pool, pinned ones are
+    DMA'd directly (pfac_api.cu hostDenseShard / hostReduceShard): every mix of the two, staging switched
+    off, one copy thread, and sizes around the staged chunk give the oracle's result."""
+    from pfac_b200 import PFAC
+    monkeypatch.setenv("PFAC_B200_STAGE_CHUNK_MB", "1")
+    pats = synth.patterns_snort_like(1500, seed=61)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = (1 << 20) * 7 + 4321
+    text = synth.make_text("ascii", 6161, 0, n, n, pats, 900)
+    synth.plant(text, 0, n, pats, 78, every=1 << 30, boundary=1 << 20)   # straddle every staged chunk edge
+    want = orc.match(text)
+    wid, wpos = orc.reduce(want)
+    p_in = torch.from_numpy(text).pin_memory()
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        for pin_in in (False, True):
+            for pin_out in (False, True):
+                h_in = p_in if pin_in else text
+                h_out = torch.zeros(n, dtype=torch.int32)
+                h_out = h_out.pin_memory() if pin_out else h_out.numpy()
+                pf.matchFromHost(h_in, h_out, size=n)
+                got = h_out.numpy() if pin_out else h_out
+                assert np.array_equal(got, want), (pin_in, pin_out)
+            ids, pos = pf.matchFromHostReduce(h_in, size=n)
+            assert np.array_equal(ids, wid) and np.array_equal(pos.astype(np.int64), wpos), pin_in
+        for cut in (1, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, (2 << 20) + 7, 3 << 20):
+            w = orc.match(text[:cut])
+            assert np.array_equal(pf.matchFromHost(text[:cut].copy()), w), cut
+            ids, pos = pf.matchFromHostReduce(text[:cut].copy())
+            wi, wp = orc.reduce(w)
+            assert np.array_equal(ids, wi) and np.array_equal(pos.astype(np.int64), wp), cut
+        monkeypatch.setenv("PFAC_B200_STAGE", "0")
+        assert np.array_equal(pf.matchFromHost(text), want)
+        ids, pos = pf.matchFromHostReduce(text)
+        assert np.array_equal(ids, wid) and np.array_equal(pos.astype(np.int64), wpos)
+    monkeypatch.delenv("PFAC_B200_STAGE")
+    monkeypatch.setenv("PFAC_B200_STAGE_CHUNK_MB", "3")
+    with PFAC() as pf:                                                   # other chunk size, fresh buffers
+        pf.readPatternFromFile(pfile)
+        assert np.array_equal(pf.matchFromHost(text), want)
+        ids, pos = pf.matchFromHostReduce(text)
+        assert np.array_equal(ids, wid) and np.array_equal(pos.astype(np.int64), wpos)
+
+
 def test_multi_gpu_driver_one_process(cuda, tmp_path, monkeypatch):
     """PFAC_mgpu_* (the library-level replacement of reference test/omp_PFAC.cpp): shards + halo, one
     host thread per handle, runs placed at the exclusive scan of the per-GPU counts.  Uses every
