@@ -91,6 +91,8 @@ typedef struct {
     int hot_max_probe, cold_max_probe;
     int pre2_bits_set;     /* of 65536: (c0,c1) pairs that survive the prefilter */
     int root_fanout;       /* valid first bytes */
+    int hashed_filter;     /* 1: the per-position test is the hashed 4-gram filter (8192 words) */
+    int hfilt_bits_set;    /* of 262144 */
     size_t device_bytes;   /* total bytes uploaded */
 } PFAC_tableInfo_t;
 
@@ -119,6 +121,13 @@ PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int **root, const un
  * has_best2 == 0; chk2: parallel to next2 (16-bit set of next byte & 15), NULL when has_chk2 == 0 */
 PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut,
                                    const unsigned **best2, const unsigned short **chk2);
+
+/* hashed 4-gram first stage, used instead of pre2 as the per-position test for byte alphabets
+ * (b = 8) whenever the shared-memory budget holds its 32 KB: 8192 unsigned, NULL when
+ * hashed_filter == 0.  x = c0|c1<<8|c2<<16|c3<<24, h = x * 0x9E3779B1, word (h>>3)&8191, bit
+ * 31-(h>>27); survivors are re-checked exactly against pre2 / chk2 by the walker.
+ * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
+PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);
 
 /* info / dump-to-path for a live handle */
 PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);

@@ -62,7 +62,8 @@ class TableInfo(ctypes.Structure):
                 ("hot_buckets", ctypes.c_uint), ("cold_buckets", ctypes.c_uint),
                 ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
                 ("cold_max_probe", ctypes.c_int), ("pre2_bits_set", ctypes.c_int),
-                ("root_fanout", ctypes.c_int), ("device_bytes", ctypes.c_size_t)]
+                ("root_fanout", ctypes.c_int), ("hashed_filter", ctypes.c_int),
+                ("hfilt_bits_set", ctypes.c_int), ("device_bytes", ctypes.c_size_t)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -125,6 +126,7 @@ def load_library():
         "PFAC_tableGetInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_tableGetLayout": [vp] + [ctypes.POINTER(vp)] * 8,
         "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 3,
+        "PFAC_tableGetFilter": [vp, ctypes.POINTER(vp)],
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_memoryUsage": [vp],
         "PFAC_hostCopy": [vp, vp, sz],
@@ -415,6 +417,8 @@ class TableCompiler:
                "PFAC_tableGetLayout")
         p2 = [ctypes.c_void_p() for _ in range(3)]
         _check(self._L.PFAC_tableGetLayout2(self._t, *[ctypes.byref(p) for p in p2]), "PFAC_tableGetLayout2")
+        pf = ctypes.c_void_p()
+        _check(self._L.PFAC_tableGetFilter(self._t, ctypes.byref(pf)), "PFAC_tableGetFilter")
         info = self.info()
 
         def arr(p, nbytes, dt):
@@ -434,6 +438,7 @@ class TableCompiler:
             "lut": arr(p2[0], 256, np.uint8),
             "best2": arr(p2[1], max(info["pre2_bits_set"], 1) * 4 if info["has_best2"] else 0, np.uint32),
             "chk2": arr(p2[2], max(info["pre2_bits_set"], 1) * 2 if info["has_chk2"] else 0, np.uint16),
+            "hfilt": arr(pf, 32768 if info["hashed_filter"] else 0, np.uint32),
             "code_bits": info["code_bits"], "gram_len": info["gram_len"],
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
         }

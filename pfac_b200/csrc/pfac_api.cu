@@ -27,6 +27,10 @@
 
 namespace {
 
+static_assert(pfac::kKernelHashFilterMul == pfac::kHashFilterMul &&
+                  pfac::kKernelHashFilterWords == pfac::kHashFilterWords,
+              "kernels and table compiler disagree on the hashed filter");
+
 constexpr size_t kFilenameLen = 256;            // reference PFAC_P.h FILENAME_LEN
 constexpr size_t kInt32Limit = size_t(1) << 31;
 
@@ -308,6 +312,8 @@ PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::D
     PFAC_UP(next2, const uint32_t*, L.next2.data(), L.next2.size() * 4)
     PFAC_UP(best2, const uint32_t*, L.best2.data(), L.best2.size() * 4)
     PFAC_UP(chk2, const unsigned short*, L.chk2.data(), L.chk2.size() * 2)
+    PFAC_UP(hfilt, const uint32_t*, L.hfilt.data(), L.hfilt.size() * 4)
+    t.hfiltBytes = uint32_t(L.hfilt.size() * 4);
     t.chk2Bytes = uint32_t(((L.chk2.size() * 2 + 15) / 16) * 16);
     t.hasBest2 = !L.best2.empty();
     t.codeBits = L.codeBits;
@@ -331,12 +337,20 @@ PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::D
     return PFAC_STATUS_SUCCESS;
 }
 
+// PFAC_B200_FILTER=exact|hash overrides the table compiler's choice of first prefilter stage
+int filterPolicy() {
+    const char* v = getenv("PFAC_B200_FILTER");
+    if (v && !strcmp(v, "exact")) return pfac::kFilterExact;
+    if (v && !strcmp(v, "hash")) return pfac::kFilterHashed;
+    return pfac::kFilterAuto;
+}
+
 // compile the device layouts for the current perf mode and upload them (reference
 // PFAC_bindTable, PFAC.cpp:321-343, which picks the dense 2-D table or the hash table)
 PFAC_status_t bindTable(PFAC_handle_t h) {
     freeDeviceTable(h);
-    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout);
-    pfac::compileLayout(h->machine, hotBudget(h, true), h->layoutReduce);
+    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, filterPolicy());
+    pfac::compileLayout(h->machine, hotBudget(h, true), h->layoutReduce, filterPolicy());
     PFAC_status_t st = uploadLayout(h, h->layout, h->table);
     if (st != PFAC_STATUS_SUCCESS) return st;
     return uploadLayout(h, h->layoutReduce, h->tableReduce);
@@ -1042,6 +1056,8 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->cold_max_probe = L.coldMaxProbe;
     info->pre2_bits_set = L.pre2BitsSet;
     info->root_fanout = L.rootFanout;
+    info->hashed_filter = L.hfilt.empty() ? 0 : 1;
+    info->hfilt_bits_set = L.hfiltBitsSet;
     info->device_bytes = L.deviceBytes();
 }
 
@@ -1052,7 +1068,7 @@ PFAC_status_t PFAC_tableCompile(const char* image, size_t size, size_t hot_budge
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
     int st = pfac::buildMachine(image, size, t->machine);
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
-    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout);
+    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, filterPolicy());
     *table = t;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1065,7 +1081,7 @@ PFAC_status_t PFAC_tableCompileArrays(const char* const* patterns, const size_t*
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
     int st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, t->machine);
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
-    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout);
+    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, filterPolicy());
     *table = t;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1120,6 +1136,13 @@ PFAC_status_t PFAC_tableGetLayout(PFAC_table_t table, const int** root, const un
     if (cold) *cold = table->layout.cold.data();
     if (chains) *chains = table->layout.chains.data();
     if (tails) *tails = table->layout.tails.data();
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned** hfilt) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    if (!hfilt) return PFAC_STATUS_INVALID_PARAMETER;
+    *hfilt = table->layout.hfilt.empty() ? nullptr : table->layout.hfilt.data();
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -32,6 +32,8 @@ constexpr uint32_t kChainBit = 0x80000000u;
 constexpr int kChainByteShift = 23;               // chain reference: bits 23..30 = first tail byte
 constexpr uint32_t kChainIndexMask = (1u << kChainByteShift) - 1u;
 constexpr uint32_t kLeafPlainBit = 0x40000000u;  // plain state without out-edges
+constexpr uint32_t kHashFilterMul = kKernelHashFilterMul;
+constexpr int kHashFilterWords = kKernelHashFilterWords;
 constexpr unsigned kSlowFlag = 0x8000u;           // queue entry: walk from the root row (generic path)
 constexpr int kMaxSmem = 232448;               // 227 KB opt-in dynamic shared memory per CTA
 
@@ -62,10 +64,12 @@ struct KParams {
     const uint32_t* next2;
     const uint32_t* best2;
     const unsigned short* chk2;
+    const uint32_t* hfilt;
     const uint4* hot;
     const uint4* cold;
     const uint4* chains;
     const unsigned char* tails;
+    uint32_t hfilt_bytes;       // 0 or kHashFilterWords * 4 (hashed 4-gram first stage, always staged in smem)
     uint32_t chk2_bytes;        // multiple of 16, 0 = no second prefilter stage (always staged in smem)
     uint32_t next2_bytes;       // multiple of 16 (copied to smem when next2_hot; best2 has the same size)
     int has_best2;
@@ -93,6 +97,7 @@ struct Tables {
     const uint32_t* next2;      // smem or global
     const uint32_t* best2;      // smem or global; nullptr when no pattern is shorter than K
     const unsigned short* chk2; // smem; nullptr when the second prefilter stage is off
+    const uint32_t* hfilt;      // smem; nullptr unless the first stage is the hashed 4-gram filter
     const uint4* hot;           // smem
     const uint4* cold;          // global
     const uint4* chains;        // smem or global
@@ -181,7 +186,7 @@ __device__ __forceinline__ uint32_t probe_cold(const uint4* __restrict__ tab, ui
 }
 
 // copy the compiled tables into shared memory (whole CTA), returns the walker's view.
-// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB | lut 256 B;  s_var: [chk2][next2][best2][hot buckets][chains][tails]
+// s_fixed: root 1 KB | pre2 8 KB | rank2 4 KB | lut 256 B;  s_var: [hfilt][chk2][next2][best2][hot buckets][chains][tails]
 constexpr int kFixedTableBytes = 1024 + 8192 + 4096 + 256;
 __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* s_fixed, unsigned char* s_var,
                                                int tid, int nthreads) {
@@ -201,6 +206,13 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     t.next2 = p.next2;
     t.best2 = p.has_best2 ? p.best2 : nullptr;
     uint4* var = reinterpret_cast<uint4*>(s_var);
+    t.hfilt = nullptr;
+    if (p.hfilt_bytes) {
+        for (uint32_t i = tid; i < p.hfilt_bytes / 16; i += nthreads)
+            var[i] = reinterpret_cast<const uint4*>(p.hfilt)[i];
+        t.hfilt = reinterpret_cast<const uint32_t*>(var);
+        var += p.hfilt_bytes / 16;
+    }
     t.chk2 = nullptr;
     if (p.chk2_bytes) {
         for (uint32_t i = tid; i < p.chk2_bytes / 16; i += nthreads)
@@ -256,12 +268,14 @@ __device__ __forceinline__ bool second_stage(const Tables& T, uint32_t idx, uint
     return (T.chk2[rank] >> (next_byte & 15u)) & 1u;
 }
 
-template <int CODE, bool TWO>
+// FILT: 0 = exact K-gram set only, 1 = + inline second stage (chk2), 2 = hashed 4-gram filter
+// (byte alphabets; pfac_table.h) whose survivors the walker re-checks exactly
+template <int CODE, int FILT>
 __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const Tables& T, uint32_t& cand,
                                             uint32_t& slow) {
     constexpr int K = 16 / CODE;
     const uint32_t* s_pre2 = T.pre2;
-    constexpr bool two_stage = TWO;  // second stage compiled in only for the tables that use it
+    constexpr bool two_stage = FILT == 1;  // second stage compiled in only for the tables that use it
     cand = 0;
     slow = 0;
     if (CODE == 8) {
@@ -274,6 +288,13 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
 #pragma unroll
             for (int j = 3; j >= 0; j--) {
                 const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
+                if (FILT == 2) {
+                    // word picked by (c0,c1) -- the low 16 bits of the product -- bit by all four bytes
+                    const uint32_t h = x * kHashFilterMul;
+                    const uint32_t hw = T.hfilt[(h >> 3) & static_cast<uint32_t>(kHashFilterWords - 1)];
+                    cand = __funnelshift_l(hw << (h >> 27), cand, 1);
+                    continue;
+                }
                 const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];
                 // the table stores bit idx at position 31-(idx&31): one shift brings it to bit 31,
                 // one funnel shift moves it into cand from the right
@@ -352,7 +373,7 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, uint32_t slow, int 
 // Per survivor: root row (is c0 alone a match?) -> next2[rank of (c0,c1)] (the walk after two
 // bytes, no hashing) -> then per step either a chain (tail compared 4 bytes at a time) or a
 // hash probe (hot rows in shared memory below hot_depth, cold rows through L1/L2).
-template <bool DENSE, int CODE>
+template <bool DENSE, int CODE, bool HASHED>
 __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
                                            const unsigned char* __restrict__ gin, int tile_rem,
                                            const unsigned short* q16, int wtotal, int* wres, int lane) {
@@ -394,13 +415,19 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
                 }
                 const uint32_t word = T.pre2[idx >> 5];
                 const uint32_t rank = T.rank2[idx >> 5] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
+                // survivors of the hashed filter may hold any bytes: the exact 2-gram bit comes first
+                // (unset: c0 starts no pattern at all, or (c0,c1) leads nowhere and c0 alone is none)
+                bool viable = !HASHED || static_cast<int>(word << (idx & 31u)) < 0;
                 if (CODE == 8) {  // K-1 = 1 symbol: the root row tells whether c0 alone is a pattern
-                    const int r = T.root[idx & 0xFFu];
+                    const int r = viable ? T.root[idx & 0xFFu] : 0;
                     best = (r <= T.num_final) ? r : 0;
                 } else {
                     best = T.best2 ? static_cast<int>(T.best2[rank]) : 0;  // longest pattern inside K-1 symbols
                 }
-                v = (limit >= K) ? T.next2[rank] : kEmpty;             // CODE 8: last byte of the input
+                // ... then the chk2 set of byte 2 (pl+2 is staged; a byte past the input can only fail
+                // a walk that needs it)
+                if (HASHED && viable && T.chk2) viable = (T.chk2[rank] >> (inb[pl + 2] & 15u)) & 1u;
+                v = (viable && limit >= K) ? T.next2[rank] : kEmpty;   // CODE 8: last byte of the input
                 d = K - 1;
             } else {
                 // generic path: from the root row, hash rows for every further step
@@ -518,7 +545,7 @@ __device__ __forceinline__ void clip_windows(int tile_rem, int lb, uint32_t& can
     }
 }
 
-template <int NSTAGE, int CODE, bool TWO>
+template <int NSTAGE, int CODE, int FILT>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int stage = kWarpTile + p.halo;
@@ -589,7 +616,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 
         const int lb = lane * kPosPerThread;
         uint32_t cand, slow;
-        prefilter16<CODE, TWO>(inb, lb, T, cand, slow);
+        prefilter16<CODE, FILT>(inb, lb, T, cand, slow);
         clip_windows<CODE>(tile_rem, lb, cand, slow);
         int valid = kWarpTile;
         if (!full) {  // tail tile: drop positions we do not own
@@ -611,7 +638,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
             __syncwarp();
         }
         dirty = __any_sync(0xffffffffu,
-                           walk_queue<true, CODE>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
+                           walk_queue<true, CODE, FILT == 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
 
         int* gout = p.out + start;
         if (p.out_aligned && full) {
@@ -702,7 +729,7 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
 #define PFAC_SPIN_GUARD(n, what, a, b_, c)
 #endif
 
-template <bool POS64, int CODE, bool TWO>
+template <bool POS64, int CODE, int FILT>
 __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KParams p) {
     constexpr int NSTAGE = kRedStages;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -907,7 +934,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
             const int lb = lane * kPosPerThread;
             uint32_t cand, slow;
-            prefilter16<CODE, TWO>(inb, lb, T, cand, slow);
+            prefilter16<CODE, FILT>(inb, lb, T, cand, slow);
             clip_windows<CODE>(tile_rem, lb, cand, slow);
             if (tile >= full_tiles) {
                 const int valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
@@ -919,7 +946,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             const int wtotal = push_survivors(cand, slow, lb, q16, lane);
             __syncwarp();
             const bool any_match = __any_sync(
-                0xffffffffu, walk_queue<false, CODE>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
+                0xffffffffu, walk_queue<false, CODE, FILT == 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
             __syncwarp();
             // in-place ordered compaction of (position, id) to the front of q16 / wids
             for (int base = 0; any_match && base < wtotal; base += 32) {
@@ -1014,7 +1041,7 @@ size_t reduceFixedBytes(int halo) {
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
-    return size_t(t.chk2Bytes) + (t.next2Hot ? size_t(t.next2Bytes) * (t.hasBest2 ? 2 : 1) : 0) +
+    return size_t(t.hfiltBytes) + size_t(t.chk2Bytes) + (t.next2Hot ? size_t(t.next2Bytes) * (t.hasBest2 ? 2 : 1) : 0) +
            size_t(t.hotBuckets) * 16 +
            (t.chainsHot ? size_t(t.chainBytes) + t.tailBytes : 0);
 }
@@ -1034,6 +1061,8 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
     p.best2 = t.best2;
     p.chk2 = t.chk2;
     p.chk2_bytes = t.chk2Bytes;
+    p.hfilt = t.hfilt;
+    p.hfilt_bytes = t.hfiltBytes;
     p.has_best2 = t.hasBest2 ? 1 : 0;
     p.next2_bytes = t.next2Bytes;
     p.next2_hot = t.next2Hot ? 1 : 0;
@@ -1090,17 +1119,19 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const int nst = denseStages(halo);
     void (*kernel)(KParams) = nullptr;
-    const bool two = t.chk2Bytes != 0;  // the table compiler only emits chk2 for byte alphabets
+    // the table compiler emits hfilt / chk2 for byte alphabets only
+    const int filt = t.hfiltBytes ? 2 : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (two) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, true> : pfac_dense_kernel<2, 8, true>;
-            else kernel = (nst == 3) ? pfac_dense_kernel<3, 8, false> : pfac_dense_kernel<2, 8, false>;
+            if (filt == 2) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 2> : pfac_dense_kernel<2, 8, 2>;
+            else if (filt == 1) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 1> : pfac_dense_kernel<2, 8, 1>;
+            else kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 0> : pfac_dense_kernel<2, 8, 0>;
             break;
-        case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4, false> : pfac_dense_kernel<2, 4, false>; break;
-        case 2: kernel = (nst == 3) ? pfac_dense_kernel<3, 2, false> : pfac_dense_kernel<2, 2, false>; break;
+        case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4, 0> : pfac_dense_kernel<2, 4, 0>; break;
+        case 2: kernel = (nst == 3) ? pfac_dense_kernel<3, 2, 0> : pfac_dense_kernel<2, 2, 0>; break;
         default: return cudaErrorInvalidValue;
     }
-    if (two && t.codeBits != 8) return cudaErrorInvalidValue;
+    if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
@@ -1134,17 +1165,18 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     const size_t smem = reduceFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const void* kernel = nullptr;
-    const bool two = t.chk2Bytes != 0;
+    const int filt = t.hfiltBytes ? 2 : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (two) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, true> : (const void*)pfac_reduce_kernel<false, 8, true>;
-            else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, false> : (const void*)pfac_reduce_kernel<false, 8, false>;
+            if (filt == 2) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 2> : (const void*)pfac_reduce_kernel<false, 8, 2>;
+            else if (filt == 1) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 1> : (const void*)pfac_reduce_kernel<false, 8, 1>;
+            else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 0> : (const void*)pfac_reduce_kernel<false, 8, 0>;
             break;
-        case 4: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 4, false> : (const void*)pfac_reduce_kernel<false, 4, false>; break;
-        case 2: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, false> : (const void*)pfac_reduce_kernel<false, 2, false>; break;
+        case 4: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 4, 0> : (const void*)pfac_reduce_kernel<false, 4, 0>; break;
+        case 2: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, 0> : (const void*)pfac_reduce_kernel<false, 2, 0>; break;
         default: return cudaErrorInvalidValue;
     }
-    if (two && t.codeBits != 8) return cudaErrorInvalidValue;
+    if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kRedMatchers - 1) / kRedMatchers;

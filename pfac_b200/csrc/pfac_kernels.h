@@ -7,6 +7,11 @@
 
 namespace pfac {
 
+// hashed 4-gram filter parameters the kernels are built with (pfac_api.cu checks them against
+// the table compiler's, pfac_table.h)
+constexpr uint32_t kKernelHashFilterMul = 0x9E3779B1u;
+constexpr int kKernelHashFilterWords = 8192;
+
 // Device-resident compiled table (uploaded by the handle).
 struct DeviceTable {
     const int32_t* root = nullptr;    // 256
@@ -17,6 +22,8 @@ struct DeviceTable {
     const uint32_t* best2 = nullptr;  // parallel to next2 (valid when hasBest2)
     const unsigned short* chk2 = nullptr;  // second prefilter stage (chk2Bytes > 0), always staged in smem
     uint32_t chk2Bytes = 0;           // multiple of 16; 0 = stage off
+    const uint32_t* hfilt = nullptr;  // hashed 4-gram first stage (hfiltBytes > 0), always staged in smem
+    uint32_t hfiltBytes = 0;          // 0 or kHashFilterWords * 4
     uint32_t next2Bytes = 0;
     bool next2Hot = false;            // kernels copy next2 (+ best2) into shared memory
     bool hasBest2 = false;

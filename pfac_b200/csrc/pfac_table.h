@@ -77,6 +77,18 @@ constexpr int kMinChain = 2;          // compress runs of at least this many sin
 constexpr uint32_t kTrap = 0xFFFFFFFFu;
 constexpr uint32_t kLeafPlain = 0x40000000u;  // plain state value: no out-edges, stop after it
 
+//   hfilt (byte alphabets, when the shared-memory budget holds it): with tens of thousands of
+//     patterns the exact 2-gram set passes a third of all text positions, and even with 1,000 it
+//     passes 1.5 %.  A hashed 4-gram filter takes its place as the per-position test: x = c0|c1<<8|c2<<16|c3<<24, h = x * kHashFilterMul, word (h>>3) & 8191,
+//     bit 31-(h>>27).  The low 16 bits of h depend on c0,c1 only, so the word is chosen by the
+//     2-gram and the bit by all four bytes: a 4-byte prefix of a pattern sets one bit, a 3-byte
+//     pattern its 256 possible bits, a 2-byte pattern its whole word, a 1-byte pattern the 256
+//     words of (c0,*).  Bytes past the end of the input therefore never hide a short match.  The
+//     walker re-checks survivors against pre2 (+ chk2) exactly.
+constexpr uint32_t kHashFilterMul = 0x9E3779B1u;
+constexpr int kHashFilterWords = 8192;           // 32 KB of shared memory
+enum FilterPolicy { kFilterAuto = 0, kFilterExact = 1, kFilterHashed = 2 };
+
 struct DeviceLayout {
     int32_t root[kCharSet];          // next state from the initial state, -1 = trap
     uint8_t lut[kCharSet];           // symbol code | 0x80 if the byte occurs in no pattern
@@ -90,6 +102,8 @@ struct DeviceLayout {
     // when the K-gram alone already yields a result.  Used as a second prefilter stage (in shared
     // memory) when the first one lets many positions through; empty = stage off.
     std::vector<uint16_t> chk2;
+    std::vector<uint32_t> hfilt;     // kHashFilterWords words, or empty (exact 2-gram first stage)
+    int hfiltBitsSet = 0;
     bool next2Hot = false;           // next2 (+ best2) fit the shared-memory budget
     std::vector<uint32_t> hot;       // edges with source depth in [K,hotDepth)  -> smem
     std::vector<uint32_t> cold;      // edges with source depth >= hotDepth      -> global/L2
@@ -107,7 +121,7 @@ struct DeviceLayout {
     int pre2BitsSet = 0;
     int rootFanout = 0;
     size_t deviceBytes() const {
-        return sizeof(root) + sizeof(lut) + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 + chk2.size() * 2 +
+        return sizeof(root) + sizeof(lut) + hfilt.size() * 4 + pre2.size() * 4 + rank2.size() * 2 + next2.size() * 4 + chk2.size() * 2 +
                best2.size() * 4 + hot.size() * 4 +
                cold.size() * 4 + chains.size() * 4 + tails.size();
     }
@@ -115,6 +129,8 @@ struct DeviceLayout {
 
 // hotBudgetBytes: shared-memory bytes the kernels may spend on hash rows (+ chains and tails
 // when everything fits).
-void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L);
+// filterPolicy: kFilterAuto / kFilterHashed use the hashed 4-gram filter for byte alphabets when the
+// budget holds it; kFilterExact keeps the exact K-gram stage (A/B measurements, tests).
+void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int filterPolicy = kFilterAuto);
 
 }  // namespace pfac

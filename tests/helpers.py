@@ -9,12 +9,14 @@ def read_patterns(path):
     return [p for p in parts[:-1] if p]  # the unterminated tail is dropped by the parser
 
 
-def emulate_layout_walk(L, num_final, text, start, n_total=None):
+def emulate_layout_walk(L, num_final, text, start, n_total=None, pad=0):
     """Python restatement of the lookup sequence the CUDA kernels run on the compiled device
     layout (pfac_b200/csrc/pfac_kernels.cu): symbol codes -> K-gram prefilter bit -> rank ->
     next2/best2 (or, for K-grams with a byte outside the alphabet / cut off by the end of the
     input, the generic path from the root row) -> bucketed hash rows (hot for K <= depth <
-    hot_depth, else cold) -> chain records with tail compare.
+    hot_depth, else cold) -> chain records with tail compare.  With the hashed 4-gram first stage
+    (L["hfilt"]) a position must pass that filter before anything else; `pad` stands for whatever
+    bytes the kernel finds past the end of the input (they must never hide a match).
     Test-only; checks the table compiler without a GPU.  L = TableCompiler.layout()."""
     n_total = len(text) if n_total is None else n_total
     avail = n_total - start
@@ -24,6 +26,13 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None):
     lut = L["lut"]
     syms = [int(text[start + i]) if i < avail else 0 for i in range(K)]
     fast = B == 8 or (avail >= K and all(not (int(lut[c]) & 0x80) for c in syms))
+    if L["hfilt"].size:
+        assert B == 8
+        x = sum((int(text[start + i]) if i < avail else pad) << (8 * i) for i in range(4))
+        h = (x * 0x9E3779B1) & 0xFFFFFFFF
+        w = int(L["hfilt"][(h >> 3) & 8191])
+        if not ((w << (h >> 27)) >> 31) & 1:       # bit 31-(h>>27) of the word picked by (c0,c1)
+            return 0
     if fast:
         idx = 0
         for i, c in enumerate(syms):

@@ -174,6 +174,36 @@ def test_edge_sizes_tail_tiles_and_shards(cuda, tmp_path):
         assert (d_out == -7).all()
 
 
+@pytest.mark.parametrize("policy", ["hash", "exact"])
+def test_first_stage_filters_agree(cuda, tmp_path, monkeypatch, policy):
+    """The hashed 4-gram first stage (large byte-alphabet dictionaries, pfac_table.h hfilt) and the exact
+    2-gram stage must both give the oracle's result: 1-, 2- and 3-byte patterns, matches in the last
+    bytes of the input, ragged sizes, the shard form, SPACE_DRIVEN (no room for the filter)."""
+    from pfac_b200 import PFAC, PerfMode
+    monkeypatch.setenv("PFAC_B200_FILTER", policy)
+    pats = synth.patterns_snort_like(2500, seed=71)
+    pats += [b"q", b"zq", b"~z", b"xyz", b"e", b"th", b"the", b"them", b"\xff", b"\x00\x01\x02"]
+    pats = list(dict.fromkeys(pats))
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        assert pf.tableInfo()["hashed_filter"] == (1 if policy == "hash" else 0)
+        for n in [1, 2, 3, 4, 5, 17, 511, 512, 513, 515, 1024, 4099, 70001, 300_000]:
+            text = synth.make_text("ascii", 700 + n, 0, n, n, pats, 80)
+            _check_all(pf, orc, text, cuda)
+            for tail in (b"q", b"zq", b"xyz", b"the", b"them", b"\xff"):
+                if len(tail) <= n:
+                    text[n - len(tail):] = np.frombuffer(tail, dtype=np.uint8)
+                    _check_all(pf, orc, text, cuda)
+        text = synth.make_text("ascii", 7171, 0, 200_000, 200_000, pats, 64)
+        for owned in [1, 511, 512, 513, 100_000, 199_990, 199_999, 200_000]:
+            _check_all(pf, orc, text, cuda, n_owned=owned)
+        pf.setPerfMode(PerfMode.SPACE_DRIVEN)
+        assert pf.tableInfo()["hashed_filter"] == 0
+        _check_all(pf, orc, text, cuda)
+
+
 def test_unaligned_device_pointers(cuda, tmp_path):
     """Any pointer alignment is accepted (the reference needs 4-byte aligned input and reads up to
     3 bytes past the end, PFAC.cpp:838-841; this library does neither)."""

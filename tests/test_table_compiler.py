@@ -227,3 +227,49 @@ def test_patterns_from_arrays_any_byte():
     with pytest.raises(PFACError) as e:
         TableCompiler(patterns=[b"ab", b""])
     assert e.value.status == Status.INVALID_PARAMETER
+
+
+@pytest.mark.parametrize("policy", ["hash", "auto"])
+def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
+    """Large byte-alphabet dictionaries get a hashed 4-gram filter as the per-position test
+    (pfac_table.h hfilt).  It may pass too much, never too little: patterns of 1, 2 and 3 bytes,
+    matches at the very end of the input whatever bytes lie behind it, duplicates and prefixes."""
+    monkeypatch.setenv("PFAC_B200_FILTER", policy)
+    rng = np.random.default_rng(17)
+    n_pat = 300 if policy == "hash" else 4000      # auto: the 2-gram set must be unselective
+    pats = synth.patterns_snort_like(n_pat, seed=23)
+    pats += [b"q", b"zq", b"~z", b"xyz", b"\x00\x01\x02", b"e", b"th", b"the", b"them", b"\xff"]
+    pats = list(dict.fromkeys(pats))
+    tc = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
+    info = tc.info()
+    assert info["hashed_filter"] == 1 and 0 < info["hfilt_bits_set"] < 262144 * 0.6
+    L = tc.layout()
+    assert L["hfilt"].size == 8192
+    n = 20000
+    text = synth.make_text("ascii", 99, 0, n, n, pats, 64)
+    for p in (b"q", b"zq", b"xyz", b"th", b"the", b"them", b"\xff", b"\x00\x01\x02"):   # shorts at the end
+        text[n - len(p):] = np.frombuffer(p, dtype=np.uint8)
+        want = brute_force_match(pats, text[n - 8:])
+        for pad in (0, 0xA5, 0xFF):
+            got = [emulate_layout_walk(L, len(pats), text[n - 8:], i, pad=pad) for i in range(8)]
+            assert got == want.tolist(), (p, pad)
+    want = brute_force_match(pats, text)
+    got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=0x5A) for i in range(n)], dtype=np.int32)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "first mismatch at %d: got %d want %d" % (bad[0], got[bad[0]], want[bad[0]])
+    assert (want > 0).sum() > 300
+    # the filter does reject: most positions never reach the exact tables
+    t = text.astype(np.uint64)
+    x = t[:-3] | (t[1:-2] << 8) | (t[2:-1] << 16) | (t[3:] << 24)
+    h = (x * 0x9E3779B1) & 0xFFFFFFFF
+    w = L["hfilt"][((h >> 3) & 8191).astype(np.int64)].astype(np.uint64)
+    passed = ((w << (h >> 27)) >> 31) & 1
+    assert passed.mean() < 0.5
+    assert np.all(passed[np.flatnonzero(want[:-3] > 0)] == 1)
+    # exact policy: no filter, same results
+    monkeypatch.setenv("PFAC_B200_FILTER", "exact")
+    tc2 = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
+    assert tc2.info()["hashed_filter"] == 0 and tc2.layout()["hfilt"].size == 0
+    # no room for the filter: falls back to the exact stage
+    monkeypatch.setenv("PFAC_B200_FILTER", policy)
+    assert TableCompiler(patterns=pats, hot_budget_bytes=16 * 1024).info()["hashed_filter"] == 0
