@@ -124,8 +124,8 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
 
 /* hashed 4-gram first stage, used instead of pre2 as the per-position test for byte alphabets
  * (b = 8) whenever the shared-memory budget holds its 32 KB: 8192 unsigned, NULL when
- * hashed_filter == 0.  x = c0|c1<<8|c2<<16|c3<<24, h = x * 0x9E3779B1, word (h>>3)&8191, bit
- * 31-(h>>27); survivors are re-checked exactly against pre2 / chk2 by the walker.
+ * hashed_filter == 0.  x = c0|c1<<8|c2<<16|c3<<24, word ((x * 0x9E3779B1) >> 2) & 8191, bit
+ * 31 - (umulhi(x, 0x85EBCA6B) & 31); survivors are re-checked exactly against pre2 / chk2 by the walker.
  * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
 PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);
 

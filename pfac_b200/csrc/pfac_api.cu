@@ -28,6 +28,7 @@
 namespace {
 
 static_assert(pfac::kKernelHashFilterMul == pfac::kHashFilterMul &&
+                  pfac::kKernelHashFilterMul2 == pfac::kHashFilterMul2 &&
                   pfac::kKernelHashFilterWords == pfac::kHashFilterWords,
               "kernels and table compiler disagree on the hashed filter");
 

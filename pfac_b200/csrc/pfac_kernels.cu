@@ -33,6 +33,7 @@ constexpr int kChainByteShift = 23;               // chain reference: bits 23..3
 constexpr uint32_t kChainIndexMask = (1u << kChainByteShift) - 1u;
 constexpr uint32_t kLeafPlainBit = 0x40000000u;  // plain state without out-edges
 constexpr uint32_t kHashFilterMul = kKernelHashFilterMul;
+constexpr uint32_t kHashFilterMul2 = kKernelHashFilterMul2;
 constexpr int kHashFilterWords = kKernelHashFilterWords;
 constexpr unsigned kSlowFlag = 0x8000u;           // queue entry: walk from the root row (generic path)
 constexpr int kMaxSmem = 232448;               // 227 KB opt-in dynamic shared memory per CTA
@@ -289,10 +290,13 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
             for (int j = 3; j >= 0; j--) {
                 const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
                 if (FILT == 2) {
-                    // word picked by (c0,c1) -- the low 16 bits of the product -- bit by all four bytes
+                    // word picked by (c0,c1) -- bits 2..14 of the product are its byte offset -- bit
+                    // by all four bytes; both multiplies run on the FMA pipe, the ALU pipe is the busy one
                     const uint32_t h = x * kHashFilterMul;
-                    const uint32_t hw = T.hfilt[(h >> 3) & static_cast<uint32_t>(kHashFilterWords - 1)];
-                    cand = __funnelshift_l(hw << (h >> 27), cand, 1);
+                    const uint32_t hw = *reinterpret_cast<const uint32_t*>(
+                        reinterpret_cast<const unsigned char*>(T.hfilt) + (h & static_cast<uint32_t>(kHashFilterWords * 4 - 4)));
+                    const uint32_t rot = __funnelshift_l(hw, hw, __umulhi(x, kHashFilterMul2));  // bit 31-(amt&31) on top
+                    cand = __funnelshift_l(rot, cand, 1);
                     continue;
                 }
                 const uint32_t word = s_pre2[(x >> 5) & 0x7FFu];

@@ -10,6 +10,7 @@ namespace pfac {
 // hashed 4-gram filter parameters the kernels are built with (pfac_api.cu checks them against
 // the table compiler's, pfac_table.h)
 constexpr uint32_t kKernelHashFilterMul = 0x9E3779B1u;
+constexpr uint32_t kKernelHashFilterMul2 = 0x85EBCA6Bu;
 constexpr int kKernelHashFilterWords = 8192;
 
 // Device-resident compiled table (uploaded by the handle).

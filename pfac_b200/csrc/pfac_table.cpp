@@ -440,9 +440,12 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
     if (B == 8 && !frontier.empty() && hotBudgetBytes >= hfiltBytes && filterPolicy != kFilterExact) {
         L.hfilt.assign(size_t(kHashFilterWords), 0u);
         auto word = [&](uint32_t x) -> uint32_t& {
-            return L.hfilt[((x * kHashFilterMul) >> 3) & uint32_t(kHashFilterWords - 1)];
+            return L.hfilt[((x * kHashFilterMul) >> 2) & uint32_t(kHashFilterWords - 1)];
         };
-        auto setGram = [&](uint32_t x) { word(x) |= 0x80000000u >> ((x * kHashFilterMul) >> 27); };
+        auto setGram = [&](uint32_t x) {
+            const uint32_t bit = uint32_t((uint64_t(x) * kHashFilterMul2) >> 32) & 31u;
+            word(x) |= 0x80000000u >> bit;
+        };
         struct Node { int state; uint32_t x; int d; };
         std::vector<Node> todo;
         todo.push_back(Node{m.initialState, 0u, 0});

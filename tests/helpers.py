@@ -29,9 +29,8 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None, pad=0):
     if L["hfilt"].size:
         assert B == 8
         x = sum((int(text[start + i]) if i < avail else pad) << (8 * i) for i in range(4))
-        h = (x * 0x9E3779B1) & 0xFFFFFFFF
-        w = int(L["hfilt"][(h >> 3) & 8191])
-        if not ((w << (h >> 27)) >> 31) & 1:       # bit 31-(h>>27) of the word picked by (c0,c1)
+        w = int(L["hfilt"][(((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191])   # word picked by (c0,c1)
+        if not ((w << (((x * 0x85EBCA6B) >> 32) & 31)) >> 31) & 1:           # bit by all four bytes
             return 0
     if fast:
         idx = 0

@@ -261,9 +261,8 @@ def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
     # the filter does reject: most positions never reach the exact tables
     t = text.astype(np.uint64)
     x = t[:-3] | (t[1:-2] << 8) | (t[2:-1] << 16) | (t[3:] << 24)
-    h = (x * 0x9E3779B1) & 0xFFFFFFFF
-    w = L["hfilt"][((h >> 3) & 8191).astype(np.int64)].astype(np.uint64)
-    passed = ((w << (h >> 27)) >> 31) & 1
+    w = L["hfilt"][((((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191).astype(np.int64)].astype(np.uint64)
+    passed = ((w << (((x * 0x85EBCA6B) >> 32) & 31)) >> 31) & 1
     assert passed.mean() < 0.5
     assert np.all(passed[np.flatnonzero(want[:-3] > 0)] == 1)
     # exact policy: no filter, same results

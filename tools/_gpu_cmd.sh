@@ -1,8 +1,4 @@
-set -x
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 200 python tests/run_configs.py --config c3 --bytes 1073741824 --check-bytes 268435456 --steps 5 2>&1 | tail -1 | cut -c1-900
-PFAC_B200_FILTER=exact timeout 200 python tests/run_configs.py --config c3 --bytes 1073741824 --check-bytes 0 --steps 5 2>&1 | tail -1 | cut -c1-400
-timeout 200 python tests/run_configs.py --config c5 --bytes 1073741824 --check-bytes 268435456 --steps 5 2>&1 | tail -1 | cut -c1-900
-PFAC_B200_FILTER=exact timeout 200 python tests/run_configs.py --config c5 --bytes 1073741824 --check-bytes 0 --steps 5 2>&1 | tail -1 | cut -c1-400
-PFAC_B200_FILTER=hash timeout 200 python tests/run_configs.py --config c2 --check-bytes 268435456 --steps 10 2>&1 | tail -1 | cut -c1-900
-timeout 200 python tests/run_configs.py --config c2 --check-bytes 0 --steps 10 2>&1 | tail -1 | cut -c1-400
+timeout 300 python bench.py 2>gpurun_out/bench.err | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('bench', d['value'], d['roofline']['frac'], 'e2e', d['e2e']['value'], 'reduce', d['reduce']['call_only_value'], d['reduce']['ms_per_call'])"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:pfac_reduce -c 1 -s 2 -o gpurun_out/c2_reduce_h -f python tools/reduce_stress.py 256 > gpurun_out/c2r_ncu.log 2>&1; tail -2 gpurun_out/c2r_ncu.log
