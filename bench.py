@@ -411,7 +411,10 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": dict(workload_config(args.bytes, world), states=info["num_states"],
                            hot_depth=info["hot_depth"], hot_buckets=info["hot_buckets"],
-                           prefilter_pass_rate=info["pre2_bits_set"] / 65536.0, matches_per_gpu=n_matches),
+                           first_stage=("hashed 4-gram filter, %d of 262144 bits set" % info["hfilt_bits_set"]
+                                        if info["hashed_filter"] else
+                                        "exact 2-gram set, %d of 65536 bits set" % info["pre2_bits_set"]),
+                           matches_per_gpu=n_matches),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reduce": reduce_info,
             "gpu_launches": int(launches), "clocks": clocks,
             "gbps_reference_unit": value * 8.0,

@@ -68,7 +68,10 @@ public:
         for (std::thread& t : threads_) t.join();
     }
 
-    void start(Job& job, void* dst, const void* src, size_t bytes) {
+    // streamDst: write the destination with streaming stores (results going to user memory that no
+    // core reads again soon; measured 8.0 -> 9.0 GB/s on the dense path).  Staging copies that the
+    // DMA engine reads next are better off in the cache hierarchy (40 vs 35 GB/s on the reduce path).
+    void start(Job& job, void* dst, const void* src, size_t bytes, bool streamDst = false) {
         if (!bytes) return;
         const size_t kMinSlice = size_t(1) << 20;
         const size_t parts = std::min(threads_.size() + 1, (bytes + kMinSlice - 1) / kMinSlice);
@@ -78,7 +81,7 @@ public:
             for (size_t o = 0; o < bytes; o += per) {
                 job.left.fetch_add(1, std::memory_order_relaxed);
                 q_.push_back(Task{static_cast<char*>(dst) + o, static_cast<const char*>(src) + o,
-                                  std::min(per, bytes - o), &job});
+                                  std::min(per, bytes - o), &job, streamDst});
             }
         }
         cv_.notify_all();
@@ -101,9 +104,9 @@ public:
         }
     }
 
-    void copy(void* dst, const void* src, size_t bytes) {
+    void copy(void* dst, const void* src, size_t bytes, bool streamDst = false) {
         Job job;
-        start(job, dst, src, bytes);
+        start(job, dst, src, bytes, streamDst);
         finish(job);
     }
 
@@ -113,9 +116,9 @@ private:
         const char* src;
         size_t bytes;
         Job* job;
+        bool stream;
     };
-    // Staging copies are large, one-shot and never re-read by the copying core: streaming stores
-    // skip the read-for-ownership of the destination lines (a third of the memory traffic).
+    // streaming stores skip the read-for-ownership of the destination lines
     static void streamCopy(char* dst, const char* src, size_t n) {
         if (n < (size_t(64) << 10)) {
             memcpy(dst, src, n);
@@ -141,12 +144,12 @@ private:
         memcpy(dst, src, n - blocks * 64);
     }
     static void exec(const Task& t) {
-        if (streamingStores()) streamCopy(t.dst, t.src, t.bytes);
+        if (t.stream && streamingStores()) streamCopy(t.dst, t.src, t.bytes);
         else memcpy(t.dst, t.src, t.bytes);
         t.job->left.fetch_sub(1, std::memory_order_release);
     }
     static bool streamingStores() {
-        static const bool on = envBytes("PFAC_B200_COPY_STREAM", 0, 1) != 0;
+        static const bool on = envBytes("PFAC_B200_COPY_STREAM", 1, 1) != 0;
         return on;
     }
     void run() {
@@ -685,7 +688,7 @@ static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size
         if (!pend[sl].live) return cudaSuccess;
         pend[sl].live = false;
         cudaError_t r = cudaStreamSynchronize(p.stream[sl]);
-        if (r == cudaSuccess && stOut) p.pool->copy(h_out + pend[sl].off, p.s_out[sl], pend[sl].owned * sizeof(int));
+        if (r == cudaSuccess && stOut) p.pool->copy(h_out + pend[sl].off, p.s_out[sl], pend[sl].owned * sizeof(int), true);
         return r;
     };
     cudaError_t e = cudaSuccess;
@@ -1167,7 +1170,7 @@ PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
 // bench.py reports how many of this library's kernels ran inside its timed region
 PFAC_status_t PFAC_hostCopy(void* dst, const void* src, size_t bytes) {
     if (bytes && (!dst || !src)) return PFAC_STATUS_INVALID_PARAMETER;
-    acquireCopyPool()->copy(dst, src, bytes);
+    acquireCopyPool()->copy(dst, src, bytes, true);  // destination written with streaming stores
     return PFAC_STATUS_SUCCESS;
 }
 

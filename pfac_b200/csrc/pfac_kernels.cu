@@ -4,8 +4,9 @@
 // (reference PFAC/src/PFAC_CPU.cpp:60-100 is the spec; PFAC_kernel.cu:377-458 and
 // PFAC_reduce_kernel.cu:639-867 are the 2012 GPU forms being replaced).  How it is computed
 // is new -- see DESIGN.md:
-//   * a 64-Kbit two-byte prefilter in shared memory rejects most start positions with one
-//     LDS; survivors are compacted into a per-warp queue;
+//   * a prefilter in shared memory rejects most start positions with one LDS -- a 256-Kbit hashed
+//     4-gram filter for byte alphabets, an exact 64-Kbit K-gram set for symbol-coded small
+//     alphabets; survivors are compacted into a per-warp queue;
 //   * survivors are walked 32 at a time (one per lane, until the batch's longest walk ends): root row and
 //     shallow ("hot") hash rows in shared memory, deep ("cold") rows through L1/L2, and
 //     path-compressed chains whose tail bytes are compared directly against the text;
