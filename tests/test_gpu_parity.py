@@ -204,6 +204,45 @@ def test_first_stage_filters_agree(cuda, tmp_path, monkeypatch, policy):
         _check_all(pf, orc, text, cuda)
 
 
+@pytest.mark.parametrize("policy", ["auto", "exact"])
+def test_random_dictionaries_vs_oracle(cuda, tmp_path, monkeypatch, policy):
+    """Random alphabets (all three symbol codings), pattern lengths 1..40 with shared prefixes, texts
+    with foreign bytes, a match ending at the last byte: dense, reduce and shard forms against the
+    oracle, for both first stages."""
+    from pfac_b200 import PFAC
+    if policy != "auto":
+        monkeypatch.setenv("PFAC_B200_FILTER", policy)
+    rng = np.random.default_rng(4242)
+    with PFAC() as pf:
+        for trial in range(14):
+            asize = int(rng.choice([2, 4, 5, 16, 17, 64, 255]))
+            alpha = rng.choice(np.setdiff1d(np.arange(256), [10]), size=asize, replace=False).astype(np.uint8)
+            pats = []
+            for _ in range(int(rng.integers(1, 400))):
+                body = alpha[rng.integers(0, asize, size=int(rng.integers(1, 41)))].tobytes()
+                if pats and rng.random() < 0.4:
+                    body = (pats[int(rng.integers(0, len(pats)))] + body)[:60]
+                pats.append(body)
+            pats = list(dict.fromkeys(pats))
+            pfile = synth.write_pattern_file(str(tmp_path / ("p%d.txt" % trial)), pats)
+            orc = _oracle(pfile)
+            pf.readPatternFromFile(pfile)
+            n = int(rng.choice([1, 7, 513, 4097, 50_001, 131_072]))
+            text = alpha[rng.integers(0, asize, size=n)].copy()
+            k = max(1, n // 40)
+            text[rng.integers(0, n, size=k)] = rng.integers(0, 256, size=k).astype(np.uint8)
+            for p in pats[:50]:
+                if len(p) <= n:
+                    at = int(rng.integers(0, n - len(p) + 1))
+                    text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+            tail = pats[int(rng.integers(0, len(pats)))]
+            if len(tail) <= n:
+                text[n - len(tail):] = np.frombuffer(tail, dtype=np.uint8)
+            _check_all(pf, orc, text, cuda)
+            if n > 600:
+                _check_all(pf, orc, text, cuda, n_owned=n - 37)
+
+
 def test_unaligned_device_pointers(cuda, tmp_path):
     """Any pointer alignment is accepted (the reference needs 4-byte aligned input and reads up to
     3 bytes past the end, PFAC.cpp:838-841; this library does neither)."""

@@ -272,3 +272,44 @@ def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
     # no room for the filter: falls back to the exact stage
     monkeypatch.setenv("PFAC_B200_FILTER", policy)
     assert TableCompiler(patterns=pats, hot_budget_bytes=16 * 1024).info()["hashed_filter"] == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_dictionaries_both_first_stages(monkeypatch, seed):
+    """Property check of the compiled layout against the brute-force semantics on random dictionaries:
+    random alphabets (2..256 symbols, so all three symbol codings occur), pattern lengths 1..12 with
+    shared prefixes, texts drawn from the same alphabet plus foreign bytes; exact and hashed first
+    stage; every budget from nothing to everything in shared memory."""
+    rng = np.random.default_rng(1000 + seed)
+    for trial in range(8):
+        asize = int(rng.choice([2, 3, 4, 5, 9, 16, 17, 40, 256]))
+        alpha = rng.choice(256, size=asize, replace=False).astype(np.uint8)
+        npat = int(rng.integers(1, 60))
+        pats = []
+        for _ in range(npat):
+            ln = int(rng.integers(1, 13))
+            body = alpha[rng.integers(0, asize, size=ln)].tobytes()
+            if pats and rng.random() < 0.4:
+                body = (pats[int(rng.integers(0, len(pats)))] + body)[:14]
+            pats.append(body)
+        pats = list(dict.fromkeys(pats))
+        n = 700
+        text = alpha[rng.integers(0, asize, size=n)].copy()
+        text[rng.integers(0, n, size=25)] = rng.integers(0, 256, size=25).astype(np.uint8)
+        for p in pats[:12]:
+            at = int(rng.integers(0, n - len(p) + 1))
+            text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+        tail = pats[int(rng.integers(0, len(pats)))]
+        text[n - len(tail):] = np.frombuffer(tail, dtype=np.uint8)        # a match ending at the last byte
+        want = brute_force_match(pats, text)
+        for policy in ("exact", "hash"):
+            monkeypatch.setenv("PFAC_B200_FILTER", policy)
+            for budget in (0, 40 * 1024, 512 * 1024):
+                tc = TableCompiler(patterns=pats, hot_budget_bytes=budget)
+                L = tc.layout()
+                info = tc.info()
+                assert info["hashed_filter"] == int(policy == "hash" and info["code_bits"] == 8 and budget >= 32768)
+                got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=int(rng.integers(0, 256)))
+                                for i in range(n)], dtype=np.int32)
+                bad = np.flatnonzero(got != want)
+                assert bad.size == 0, (seed, trial, policy, budget, int(bad[0]), int(got[bad[0]]), int(want[bad[0]]))
