@@ -411,7 +411,7 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": dict(workload_config(args.bytes, world), states=info["num_states"],
                            hot_depth=info["hot_depth"], hot_buckets=info["hot_buckets"],
-                           first_stage=("hashed 4-gram filter, %d of 262144 bits set" % info["hfilt_bits_set"]
+                           first_stage=("hashed 4-gram filter, %d bit(s) per lookup, %d of 262144 bits set" % (info["hashed_filter"], info["hfilt_bits_set"])
                                         if info["hashed_filter"] else
                                         "exact 2-gram set, %d of 65536 bits set" % info["pre2_bits_set"]),
                            matches_per_gpu=n_matches),

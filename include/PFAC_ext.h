@@ -91,7 +91,7 @@ typedef struct {
     int hot_max_probe, cold_max_probe;
     int pre2_bits_set;     /* of 65536: (c0,c1) pairs that survive the prefilter */
     int root_fanout;       /* valid first bytes */
-    int hashed_filter;     /* 1: the per-position test is the hashed 4-gram filter (8192 words) */
+    int hashed_filter;     /* 1 / 2: the per-position test is the hashed 4-gram filter (8192 words), 1 or 2 bits per lookup */
     int hfilt_bits_set;    /* of 262144 */
     size_t device_bytes;   /* total bytes uploaded */
 } PFAC_tableInfo_t;
@@ -125,7 +125,8 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
 /* hashed 4-gram first stage, used instead of pre2 as the per-position test for byte alphabets
  * (b = 8) whenever the shared-memory budget holds its 32 KB: 8192 unsigned, NULL when
  * hashed_filter == 0.  x = c0|c1<<8|c2<<16|c3<<24, word ((x * 0x9E3779B1) >> 2) & 8191, bit
- * 31 - (umulhi(x, 0x85EBCA6B) & 31); survivors are re-checked exactly against pre2 / chk2 by the walker.
+ * 31 - (umulhi(x, 0x85EBCA6B) & 31) and, when hashed_filter == 2 (dense tables), also bit
+ * 31 - (umulhi(x, 0xC2B2AE35) & 31); survivors are re-checked exactly against pre2 / chk2 by the walker.
  * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
 PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);
 

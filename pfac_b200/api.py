@@ -439,6 +439,7 @@ class TableCompiler:
             "best2": arr(p2[1], max(info["pre2_bits_set"], 1) * 4 if info["has_best2"] else 0, np.uint32),
             "chk2": arr(p2[2], max(info["pre2_bits_set"], 1) * 2 if info["has_chk2"] else 0, np.uint16),
             "hfilt": arr(pf, 32768 if info["hashed_filter"] else 0, np.uint32),
+            "hfilt_k": info["hashed_filter"],
             "code_bits": info["code_bits"], "gram_len": info["gram_len"],
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
         }

@@ -29,6 +29,7 @@ namespace {
 
 static_assert(pfac::kKernelHashFilterMul == pfac::kHashFilterMul &&
                   pfac::kKernelHashFilterMul2 == pfac::kHashFilterMul2 &&
+                  pfac::kKernelHashFilterMul3 == pfac::kHashFilterMul3 &&
                   pfac::kKernelHashFilterWords == pfac::kHashFilterWords,
               "kernels and table compiler disagree on the hashed filter");
 
@@ -318,6 +319,7 @@ PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::D
     PFAC_UP(chk2, const unsigned short*, L.chk2.data(), L.chk2.size() * 2)
     PFAC_UP(hfilt, const uint32_t*, L.hfilt.data(), L.hfilt.size() * 4)
     t.hfiltBytes = uint32_t(L.hfilt.size() * 4);
+    t.hfiltK = L.hfiltK;
     t.chk2Bytes = uint32_t(((L.chk2.size() * 2 + 15) / 16) * 16);
     t.hasBest2 = !L.best2.empty();
     t.codeBits = L.codeBits;
@@ -497,7 +499,6 @@ PFAC_status_t PFAC_create(PFAC_handle_t* handle) {
     if (!h) return PFAC_STATUS_ALLOC_FAILED;
     h->device = device;
     h->launch.numSMs = sms;
-    h->launch.ctasPerSM = int(envBytes("PFAC_B200_CTAS_PER_SM", 0, 1));
     *handle = h;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1060,7 +1061,7 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->cold_max_probe = L.coldMaxProbe;
     info->pre2_bits_set = L.pre2BitsSet;
     info->root_fanout = L.rootFanout;
-    info->hashed_filter = L.hfilt.empty() ? 0 : 1;
+    info->hashed_filter = L.hfilt.empty() ? 0 : L.hfiltK;
     info->hfilt_bits_set = L.hfiltBitsSet;
     info->device_bytes = L.deviceBytes();
 }

@@ -35,6 +35,7 @@ constexpr uint32_t kChainIndexMask = (1u << kChainByteShift) - 1u;
 constexpr uint32_t kLeafPlainBit = 0x40000000u;  // plain state without out-edges
 constexpr uint32_t kHashFilterMul = kKernelHashFilterMul;
 constexpr uint32_t kHashFilterMul2 = kKernelHashFilterMul2;
+constexpr uint32_t kHashFilterMul3 = kKernelHashFilterMul3;
 constexpr int kHashFilterWords = kKernelHashFilterWords;
 constexpr unsigned kSlowFlag = 0x8000u;           // queue entry: walk from the root row (generic path)
 constexpr int kMaxSmem = 232448;               // 227 KB opt-in dynamic shared memory per CTA
@@ -270,8 +271,8 @@ __device__ __forceinline__ bool second_stage(const Tables& T, uint32_t idx, uint
     return (T.chk2[rank] >> (next_byte & 15u)) & 1u;
 }
 
-// FILT: 0 = exact K-gram set only, 1 = + inline second stage (chk2), 2 = hashed 4-gram filter
-// (byte alphabets; pfac_table.h) whose survivors the walker re-checks exactly
+// FILT: 0 = exact K-gram set only, 1 = + inline second stage (chk2), 2 / 3 = hashed 4-gram filter
+// testing one / two bits (byte alphabets; pfac_table.h) whose survivors the walker re-checks exactly
 template <int CODE, int FILT>
 __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const Tables& T, uint32_t& cand,
                                             uint32_t& slow) {
@@ -290,13 +291,15 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
 #pragma unroll
             for (int j = 3; j >= 0; j--) {
                 const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
-                if (FILT == 2) {
-                    // word picked by (c0,c1) -- bits 2..14 of the product are its byte offset -- bit
-                    // by all four bytes; both multiplies run on the FMA pipe, the ALU pipe is the busy one
+                if (FILT >= 2) {
+                    // word picked by (c0,c1) -- bits 2..14 of the product are its byte offset -- two bits
+                    // by all four bytes; the multiplies run on the FMA pipe, the ALU pipe is the busy one
                     const uint32_t h = x * kHashFilterMul;
                     const uint32_t hw = *reinterpret_cast<const uint32_t*>(
                         reinterpret_cast<const unsigned char*>(T.hfilt) + (h & static_cast<uint32_t>(kHashFilterWords * 4 - 4)));
-                    const uint32_t rot = __funnelshift_l(hw, hw, __umulhi(x, kHashFilterMul2));  // bit 31-(amt&31) on top
+                    // rotate the bit to the top; dense tables (FILT 3) test a second one
+                    uint32_t rot = __funnelshift_l(hw, hw, __umulhi(x, kHashFilterMul2));
+                    if (FILT == 3) rot &= __funnelshift_l(hw, hw, __umulhi(x, kHashFilterMul3));
                     cand = __funnelshift_l(rot, cand, 1);
                     continue;
                 }
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
             __syncwarp();
         }
         dirty = __any_sync(0xffffffffu,
-                           walk_queue<true, CODE, FILT == 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
+                           walk_queue<true, CODE, FILT >= 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
 
         int* gout = p.out + start;
         if (p.out_aligned && full) {
@@ -951,7 +954,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             const int wtotal = push_survivors(cand, slow, lb, q16, lane);
             __syncwarp();
             const bool any_match = __any_sync(
-                0xffffffffu, walk_queue<false, CODE, FILT == 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
+                0xffffffffu, walk_queue<false, CODE, FILT >= 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
             __syncwarp();
             // in-place ordered compaction of (position, id) to the front of q16 / wids
             for (int base = 0; any_match && base < wtotal; base += 32) {
@@ -1125,10 +1128,11 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
     const int nst = denseStages(halo);
     void (*kernel)(KParams) = nullptr;
     // the table compiler emits hfilt / chk2 for byte alphabets only
-    const int filt = t.hfiltBytes ? 2 : (t.chk2Bytes ? 1 : 0);
+    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (filt == 2) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 2> : pfac_dense_kernel<2, 8, 2>;
+            if (filt == 3) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 3> : pfac_dense_kernel<2, 8, 3>;
+            else if (filt == 2) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 2> : pfac_dense_kernel<2, 8, 2>;
             else if (filt == 1) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 1> : pfac_dense_kernel<2, 8, 1>;
             else kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 0> : pfac_dense_kernel<2, 8, 0>;
             break;
@@ -1170,10 +1174,11 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     const size_t smem = reduceFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const void* kernel = nullptr;
-    const int filt = t.hfiltBytes ? 2 : (t.chk2Bytes ? 1 : 0);
+    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (filt == 2) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 2> : (const void*)pfac_reduce_kernel<false, 8, 2>;
+            if (filt == 3) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 3> : (const void*)pfac_reduce_kernel<false, 8, 3>;
+            else if (filt == 2) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 2> : (const void*)pfac_reduce_kernel<false, 8, 2>;
             else if (filt == 1) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 1> : (const void*)pfac_reduce_kernel<false, 8, 1>;
             else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 0> : (const void*)pfac_reduce_kernel<false, 8, 0>;
             break;

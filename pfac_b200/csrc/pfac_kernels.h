@@ -11,6 +11,7 @@ namespace pfac {
 // the table compiler's, pfac_table.h)
 constexpr uint32_t kKernelHashFilterMul = 0x9E3779B1u;
 constexpr uint32_t kKernelHashFilterMul2 = 0x85EBCA6Bu;
+constexpr uint32_t kKernelHashFilterMul3 = 0xC2B2AE35u;
 constexpr int kKernelHashFilterWords = 8192;
 
 // Device-resident compiled table (uploaded by the handle).
@@ -25,6 +26,7 @@ struct DeviceTable {
     uint32_t chk2Bytes = 0;           // multiple of 16; 0 = stage off
     const uint32_t* hfilt = nullptr;  // hashed 4-gram first stage (hfiltBytes > 0), always staged in smem
     uint32_t hfiltBytes = 0;          // 0 or kHashFilterWords * 4
+    int hfiltK = 0;                   // bits tested per lookup (1 or 2)
     uint32_t next2Bytes = 0;
     bool next2Hot = false;            // kernels copy next2 (+ best2) into shared memory
     bool hasBest2 = false;
@@ -47,7 +49,6 @@ struct DeviceTable {
 
 struct LaunchConfig {
     int numSMs = 148;
-    int ctasPerSM = 0;   // 0 = ask the occupancy API
 };
 
 // Shared-memory bytes the dense (or reduce) kernel can spare for next2 / hash rows / chains /

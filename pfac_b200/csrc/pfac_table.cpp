@@ -438,33 +438,44 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
     // random patterns (+11 %) to 20,000 Snort-like ones (+29 %)
     const size_t hfiltBytes = size_t(kHashFilterWords) * 4;
     if (B == 8 && !frontier.empty() && hotBudgetBytes >= hfiltBytes && filterPolicy != kFilterExact) {
-        L.hfilt.assign(size_t(kHashFilterWords), 0u);
-        auto word = [&](uint32_t x) -> uint32_t& {
-            return L.hfilt[((x * kHashFilterMul) >> 2) & uint32_t(kHashFilterWords - 1)];
-        };
-        auto setGram = [&](uint32_t x) {
-            const uint32_t bit = uint32_t((uint64_t(x) * kHashFilterMul2) >> 32) & 31u;
-            word(x) |= 0x80000000u >> bit;
-        };
-        struct Node { int state; uint32_t x; int d; };
-        std::vector<Node> todo;
-        todo.push_back(Node{m.initialState, 0u, 0});
-        while (!todo.empty()) {
-            const Node f = todo.back();
-            todo.pop_back();
-            for (const Edge& e : out[size_t(f.state)]) {
-                const uint32_t x = f.x | (uint32_t(e.ch) << (8 * f.d));
-                const int d = f.d + 1;
-                if (d == 4) { setGram(x); continue; }
-                if (isFinal(e.next)) {  // a pattern shorter than the gram: whatever follows must pass
-                    if (d == 1) for (uint32_t c = 0; c < 256; c++) word(x | (c << 8)) = 0xFFFFFFFFu;
-                    else if (d == 2) word(x) = 0xFFFFFFFFu;
-                    else for (uint32_t c = 0; c < 256; c++) setGram(x | (c << 24));
+        // one bit per 4-gram first; a table that comes out dense (> 2 % of its bits, whole words of short
+        // patterns aside) is rebuilt with two
+        for (L.hfiltK = 1; L.hfiltK <= 2; L.hfiltK++) {
+            L.hfilt.assign(size_t(kHashFilterWords), 0u);
+            L.hfiltBitsSet = 0;
+            auto word = [&](uint32_t x) -> uint32_t& {
+                return L.hfilt[((x * kHashFilterMul) >> 2) & uint32_t(kHashFilterWords - 1)];
+            };
+            auto setGram = [&](uint32_t x) {
+                const uint32_t b1 = uint32_t((uint64_t(x) * kHashFilterMul2) >> 32) & 31u;
+                const uint32_t b2 = uint32_t((uint64_t(x) * kHashFilterMul3) >> 32) & 31u;
+                word(x) |= (0x80000000u >> b1) | (L.hfiltK == 2 ? 0x80000000u >> b2 : 0u);
+            };
+            struct Node { int state; uint32_t x; int d; };
+            std::vector<Node> todo;
+            todo.push_back(Node{m.initialState, 0u, 0});
+            while (!todo.empty()) {
+                const Node f = todo.back();
+                todo.pop_back();
+                for (const Edge& e : out[size_t(f.state)]) {
+                    const uint32_t x = f.x | (uint32_t(e.ch) << (8 * f.d));
+                    const int d = f.d + 1;
+                    if (d == 4) { setGram(x); continue; }
+                    if (isFinal(e.next)) {  // a pattern shorter than the gram: whatever follows must pass
+                        if (d == 1) for (uint32_t c = 0; c < 256; c++) word(x | (c << 8)) = 0xFFFFFFFFu;
+                        else if (d == 2) word(x) = 0xFFFFFFFFu;
+                        else for (uint32_t c = 0; c < 256; c++) setGram(x | (c << 24));
+                    }
+                    if (!out[size_t(e.next)].empty()) todo.push_back(Node{e.next, x, d});
                 }
-                if (!out[size_t(e.next)].empty()) todo.push_back(Node{e.next, x, d});
             }
+            int gramBits = 0;  // all-ones words (1- and 2-byte patterns) pass whatever the number of bits
+            for (uint32_t w : L.hfilt) {
+                L.hfiltBitsSet += __builtin_popcount(w);
+                if (w != 0xFFFFFFFFu) gramBits += __builtin_popcount(w);
+            }
+            if (L.hfiltK == 2 || gramBits <= kHashFilterWords * 32 / 50) break;
         }
-        for (uint32_t w : L.hfilt) L.hfiltBitsSet += __builtin_popcount(w);
         hotBudgetBytes -= hfiltBytes;
     }
 

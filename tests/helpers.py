@@ -30,8 +30,9 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None, pad=0):
         assert B == 8
         x = sum((int(text[start + i]) if i < avail else pad) << (8 * i) for i in range(4))
         w = int(L["hfilt"][(((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191])   # word picked by (c0,c1)
-        if not ((w << (((x * 0x85EBCA6B) >> 32) & 31)) >> 31) & 1:           # bit by all four bytes
-            return 0
+        for m in (0x85EBCA6B, 0xC2B2AE35)[:L["hfilt_k"]]:                     # one or two bits by all four bytes
+            if not ((w << (((x * m) >> 32) & 31)) >> 31) & 1:
+                return 0
     if fast:
         idx = 0
         for i, c in enumerate(syms):
