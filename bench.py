@@ -314,19 +314,35 @@ def main():
         h_in = torch.empty(owned, dtype=torch.uint8, pin_memory=True)
         h_in.numpy()[:] = shard[:owned]
         h_out = torch.empty(owned, dtype=torch.int32, pin_memory=True)
-        pf.matchFromHost(h_in, h_out, size=owned)  # warm-up: allocates the pipeline buffers
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            pf.matchFromHost(h_in, h_out, size=owned)
-        dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt)
+        def time_host_calls():
+            pf.matchFromHost(h_in, h_out, size=owned)  # warm-up: allocates the pipeline buffers
+            h_out.fill_(-1)                            # every timed call must rewrite the whole array
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                pf.matchFromHost(h_in, h_out, size=owned)
+            return max_over_ranks(time.perf_counter() - t0)
+
+        dt = time_host_calls()
+        h2d_b, d2h_b = pf.lastHostTransfer()           # counted by the library around its cudaMemcpyAsync calls
         e2e = {"value": owned * world * args.e2e_steps / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(owned), "d2h_bytes_per_step": int(owned) * 4,
-               "steps": args.e2e_steps, "api": "PFAC_matchFromHost (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
+               "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+               "steps": args.e2e_steps,
+               "api": "PFAC_matchFromHost (pinned host buffers; chunked H2D / fused match+compaction / D2H of the "
+                      "(id, position) pairs; the host zero-fills and scatters the dense int32 array it returns)"}
         if world == 1:
             # the shard ends at the end of the stream, so the host call and the shard call agree
             assert bool((torch.from_numpy(h_out.numpy()).to(dev) == d_out).all().item()), "e2e result differs"
+        # the same call with the dense array itself crossing PCIe (the reference's data movement)
+        os.environ["PFAC_B200_HOST_RESULT"] = "dense"
+        dt = time_host_calls()
+        del os.environ["PFAC_B200_HOST_RESULT"]
+        h2d_b, d2h_b = pf.lastHostTransfer()
+        e2e["dense_d2h"] = {"value": owned * world * args.e2e_steps / dt / 1e9, "unit": UNIT,
+                            "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+                            "api": "PFAC_matchFromHost with PFAC_B200_HOST_RESULT=dense"}
+        if world == 1:
+            assert bool((torch.from_numpy(h_out.numpy()).to(dev) == d_out).all().item()), "e2e (dense D2H) result differs"
         del h_out
         # the same host-buffer input through the reduced API: 8 bytes per match come back instead of
         # 4 bytes per input byte (extra information; the contract's e2e is the dense call above)

@@ -164,7 +164,20 @@ PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char *h_inputString
  * PFAC_hostCopy is that pool's memcpy (host only, no GPU needed; exported for tests and for callers
  * that fill their own pinned buffers).
  */
+/*
+ * PFAC_matchFromHost returns 4 bytes per input byte, almost all of them zero.  By default only the
+ * (id, position) pairs of each chunk cross PCIe (the fused match + compaction kernel produces
+ * them) and the host writes the dense array: zero fill by the copy pool while the chunk is on the
+ * GPU, then a scatter of the pairs.  Chunks with more than one match per 16 positions use the dense
+ * kernel and a plain D2H.  The result is the same array either way.
+ *   PFAC_B200_HOST_RESULT=dense   always return the dense array over PCIe
+ * PFAC_lastHostTransfer: bytes the handle's last PFAC_matchFromHost* call moved over PCIe.
+ */
+PFAC_status_t PFAC_lastHostTransfer(PFAC_handle_t handle, size_t *h2d_bytes, size_t *d2h_bytes);
+
 PFAC_status_t PFAC_hostCopy(void *dst, const void *src, size_t bytes);
+/* the same pool's zero fill (streaming stores); PFAC_matchFromHost uses it for the sparse result path */
+PFAC_status_t PFAC_hostZero(void *dst, size_t bytes);
 
 /* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
 unsigned long long PFAC_kernelLaunchCount(void);

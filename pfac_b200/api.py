@@ -130,6 +130,8 @@ def load_library():
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_memoryUsage": [vp],
         "PFAC_hostCopy": [vp, vp, sz],
+        "PFAC_hostZero": [vp, sz],
+        "PFAC_lastHostTransfer": [vp, ctypes.POINTER(sz), ctypes.POINTER(sz)],
         "PFAC_mgpuCreate": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int],
         "PFAC_mgpuDestroy": [vp],
         "PFAC_mgpuReadPatternFromFile": [vp, cp],
@@ -292,6 +294,12 @@ class PFAC:
             h_result = np.zeros(n, dtype=np.int32)
         _check(self._L.PFAC_matchFromHost(self._h, _ptr(src), n, _ptr(h_result)), "PFAC_matchFromHost")
         return h_result
+
+    def lastHostTransfer(self):
+        """(h2d_bytes, d2h_bytes) the last matchFromHost* call of this handle moved over PCIe."""
+        a, b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _check(self._L.PFAC_lastHostTransfer(self._h, ctypes.byref(a), ctypes.byref(b)), "PFAC_lastHostTransfer")
+        return a.value, b.value
 
     def matchFromHostReduce(self, h_input, h_result=None, h_pos=None, size=None):
         """Returns (ids[:M], pos[:M]) as int32 arrays (views of the supplied buffers)."""

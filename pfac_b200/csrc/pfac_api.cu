@@ -105,6 +105,22 @@ public:
         }
     }
 
+    // zero `bytes` bytes at dst with streaming stores, split over the pool (src == nullptr marks a fill)
+    void startZero(Job& job, void* dst, size_t bytes) {
+        if (!bytes) return;
+        const size_t kMinSlice = size_t(1) << 20;
+        const size_t parts = std::min(threads_.size() + 1, (bytes + kMinSlice - 1) / kMinSlice);
+        const size_t per = (((bytes + parts - 1) / parts) + 63) & ~size_t(63);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            for (size_t o = 0; o < bytes; o += per) {
+                job.left.fetch_add(1, std::memory_order_relaxed);
+                q_.push_back(Task{static_cast<char*>(dst) + o, nullptr, std::min(per, bytes - o), &job, true});
+            }
+        }
+        cv_.notify_all();
+    }
+
     void copy(void* dst, const void* src, size_t bytes, bool streamDst = false) {
         Job job;
         start(job, dst, src, bytes, streamDst);
@@ -144,8 +160,31 @@ private:
         _mm_sfence();
         memcpy(dst, src, n - blocks * 64);
     }
+    static void streamZero(char* dst, size_t n) {
+        if (n < (size_t(64) << 10)) {
+            memset(dst, 0, n);
+            return;
+        }
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+        memset(dst, 0, head);
+        dst += head;
+        n -= head;
+        const size_t blocks = n / 64;
+        const __m128i z = _mm_setzero_si128();
+        for (size_t i = 0; i < blocks; i++, dst += 64) {
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst), z);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 16), z);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 32), z);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 48), z);
+        }
+        _mm_sfence();
+        memset(dst, 0, n - blocks * 64);
+    }
     static void exec(const Task& t) {
-        if (t.stream && streamingStores()) streamCopy(t.dst, t.src, t.bytes);
+        if (!t.src) {
+            if (streamingStores()) streamZero(t.dst, t.bytes);
+            else memset(t.dst, 0, t.bytes);
+        } else if (t.stream && streamingStores()) streamCopy(t.dst, t.src, t.bytes);
         else memcpy(t.dst, t.src, t.bytes);
         t.job->left.fetch_sub(1, std::memory_order_release);
     }
@@ -211,7 +250,10 @@ struct HostPipe {  // cached buffers of the matchFromHost* pipelines
     int* s_out[2] = {nullptr, nullptr};
     size_t stageChunk = 0;               // owned bytes per staged chunk (<= chunk)
     size_t stageInCap = 0;
+    int* s_list[2] = {nullptr, nullptr};  // pinned (ids | positions) of the sparse result path
+    size_t listCap = 0;                   // entries per slot
     std::shared_ptr<CopyPool> pool;
+    size_t lastH2D = 0, lastD2H = 0;      // bytes the last matchFromHost* call moved over PCIe
 };
 
 }  // namespace
@@ -268,8 +310,10 @@ void freeStage(HostPipe& p) {
     for (int i = 0; i < 2; i++) {
         if (p.s_out[i]) cudaFreeHost(p.s_out[i]);
         p.s_out[i] = nullptr;
+        if (p.s_list[i]) cudaFreeHost(p.s_list[i]);
+        p.s_list[i] = nullptr;
     }
-    p.stageChunk = p.stageInCap = 0;
+    p.stageChunk = p.stageInCap = p.listCap = 0;
 }
 
 void freePipe(HostPipe& p) {
@@ -662,6 +706,120 @@ PFAC_status_t PFAC_matchFromDevice(PFAC_handle_t handle, char* d_in, size_t size
                                                d_out, handle->stream));
 }
 
+// PFAC_B200_HOST_RESULT=dense: always bring the 4-byte-per-position array back over PCIe
+static bool sparseHostResult() {
+    const char* v = getenv("PFAC_B200_HOST_RESULT");
+    return !(v && !strcmp(v, "dense"));
+}
+
+// PFAC_matchFromHost, sparse result path.  The dense result is almost all zeros, and returning it
+// costs 4 bytes of PCIe per input byte (13.7 GB/s of input at best).  Instead every chunk goes
+// through the fused match + compaction kernel, only its (id, position) pairs come back, and the
+// host writes the dense array itself: the copy pool zero-fills the chunk's slice of h_out with
+// streaming stores (about 200 GB/s on the 16-core boxes) while the chunk is on the GPU, then the
+// pairs are scattered into it.  A chunk with more than one match per 16 positions falls back to the
+// dense kernel + a plain D2H of its slice.  Works the same for pinned and pageable h_out.
+static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, size_t n_owned, size_t n_total,
+                                     int* h_out) {
+    std::lock_guard<std::mutex> lock(handle->pipeMu);
+    {
+        PFAC_status_t st = ensurePipe(handle, true);
+        if (st != PFAC_STATUS_SUCCESS) return st;
+    }
+    HostPipe& p = handle->pipe;
+    const bool stIn = stagingEnabled() && isPageable(h_in);
+    {
+        PFAC_status_t st = ensureStage(handle, stIn, false);
+        if (st != PFAC_STATUS_SUCCESS) return st;
+    }
+    const size_t chunk = stIn ? p.stageChunk : p.chunk;
+    const size_t cap = std::max<size_t>(chunk / 16, 1024);  // pairs a chunk may return before it goes dense
+    if (p.listCap < cap) {
+        for (int i = 0; i < 2; i++) {
+            if (p.s_list[i]) cudaFreeHost(p.s_list[i]);
+            p.s_list[i] = nullptr;
+            if (cudaMallocHost(reinterpret_cast<void**>(&p.s_list[i]), cap * 8) != cudaSuccess) {
+                p.listCap = 0;
+                return PFAC_STATUS_ALLOC_FAILED;
+            }
+        }
+        p.listCap = cap;
+    }
+    const size_t nchunks = (n_owned + chunk - 1) / chunk;
+    const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
+    auto ownedOf = [&](size_t c) { return (n_owned - c * chunk < chunk) ? n_owned - c * chunk : chunk; };
+    auto totalOf = [&](size_t c) {
+        const size_t off = c * chunk, owned = ownedOf(c);
+        return (n_total - off < owned + halo) ? n_total - off : owned + halo;
+    };
+    // in flight: [host copy of chunk c+2 into pinned staging (pageable input only)] || [H2D of chunk
+    // c+1] || [match + compaction of chunk c on the GPU, zero fill of its h_out slice on the host]
+    CopyPool::Job jobs[3];
+    CopyPool::Job zero;
+    auto hostStage = [&](size_t c) {
+        if (stIn && c < nchunks) p.pool->start(jobs[c % 3], p.s_in[c % 3], h_in + c * chunk, totalOf(c));
+    };
+    auto h2d = [&](size_t c) -> cudaError_t {
+        const void* src = h_in + c * chunk;
+        if (stIn) {
+            p.pool->finish(jobs[c % 3]);
+            src = p.s_in[c % 3];
+        }
+        p.lastH2D += totalOf(c);
+        return cudaMemcpyAsync(p.d_in[c % 2], src, totalOf(c), cudaMemcpyHostToDevice, p.stream[c % 2]);
+    };
+    auto bail = [&](PFAC_status_t st) {
+        if (stIn) for (int j = 0; j < 3; j++) p.pool->finish(jobs[j]);
+        p.pool->finish(zero);
+        cudaDeviceSynchronize();
+        return st;
+    };
+    p.lastH2D = p.lastD2H = 0;
+    hostStage(0);
+    hostStage(1);
+    if (h2d(0) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+    for (size_t c = 0; c < nchunks; c++) {
+        const int slot = int(c % 2);
+        const size_t off = c * chunk, owned = ownedOf(c);
+        if (c + 1 < nchunks && h2d(c + 1) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+        hostStage(c + 2);
+        p.pool->startZero(zero, h_out + off, owned * sizeof(int));  // the workers fill while the GPU matches
+        unsigned long long count = 0;
+        PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, totalOf(c), 0, p.d_out[slot], p.d_pos[slot],
+                                       false, p.stream[slot], &count);
+        if (st != PFAC_STATUS_SUCCESS) return bail(st);
+        p.lastD2H += 8;
+        if (count <= cap) {
+            int* ids = p.s_list[slot];
+            int* pos = p.s_list[slot] + cap;
+            if (count) {
+                if (cudaMemcpyAsync(ids, p.d_out[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess ||
+                    cudaMemcpyAsync(pos, p.d_pos[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess)
+                    return bail(PFAC_STATUS_INTERNAL_ERROR);
+                p.lastD2H += count * 8;
+            }
+            p.pool->finish(zero);
+            if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+            int* dst = h_out + off;
+            for (unsigned long long i = 0; i < count; i++) dst[pos[i]] = ids[i];
+        } else {
+            // dense chunk: the position buffer (8 bytes per position) doubles as the dense result
+            p.pool->finish(zero);
+            int* d_dense = p.d_pos[slot];
+            cudaError_t e = pfac::launchMatchDense(handle->table, handle->launch, p.d_in[slot], owned, totalOf(c),
+                                                   d_dense, p.stream[slot]);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(h_out + off, d_dense, owned * sizeof(int), cudaMemcpyDeviceToHost, p.stream[slot]);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(p.stream[slot]);
+            if (e != cudaSuccess) return bail(cudaToStatus(e));
+            p.lastD2H += owned * sizeof(int);
+        }
+    }
+    if (cudaStreamSynchronize(p.stream[0]) != cudaSuccess || cudaStreamSynchronize(p.stream[1]) != cudaSuccess)
+        return PFAC_STATUS_INTERNAL_ERROR;
+    return PFAC_STATUS_SUCCESS;
+}
+
 // reference PFAC.cpp:879-961.  Chunks of the host input (+ tail halo) go H2D on two private
 // streams, each followed by its kernel and the D2H of its 4-byte-per-position results, so
 // copy-in, match and copy-out of neighbouring chunks overlap.  Pinned user buffers are DMA'd
@@ -670,6 +828,7 @@ PFAC_status_t PFAC_matchFromDevice(PFAC_handle_t handle, char* d_in, size_t size
 // host shard: results for [0,n_owned), input bytes [0,n_total) (owned + tail halo), both on the host
 static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size_t n_owned, size_t n_total,
                                     int* h_out) {
+    if (sparseHostResult()) return hostDenseSparse(handle, h_in, n_owned, n_total, h_out);
     std::lock_guard<std::mutex> lock(handle->pipeMu);
     PFAC_status_t st = ensurePipe(handle, false);
     if (st != PFAC_STATUS_SUCCESS) return st;
@@ -694,6 +853,7 @@ static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size
     };
     cudaError_t e = cudaSuccess;
     int slot = 0;
+    p.lastH2D = p.lastD2H = 0;
     for (size_t off = 0; off < n_owned && e == cudaSuccess; off += chunk, slot ^= 1) {
         const size_t owned = (n_owned - off < chunk) ? n_owned - off : chunk;
         const size_t total = (n_total - off < owned + halo) ? n_total - off : owned + halo;
@@ -705,6 +865,8 @@ static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size
         }
         e = cudaMemcpyAsync(p.d_in[slot], src, total, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) break;
+        p.lastH2D += total;
+        p.lastD2H += owned * sizeof(int);
         e = pfac::launchMatchDense(handle->table, handle->launch, p.d_in[slot], owned, total, p.d_out[slot], s);
         if (e != cudaSuccess) break;
         e = cudaMemcpyAsync(stOut ? p.s_out[slot] : h_out + off, p.d_out[slot], owned * sizeof(int),
@@ -806,6 +968,7 @@ static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, siz
     const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
     const size_t posBytes = pos64 ? 8 : 4;
     size_t written = 0;
+    p.lastH2D = p.lastD2H = 0;
     auto ownedOf = [&](size_t c) { return (n_owned - c * chunk < chunk) ? n_owned - c * chunk : chunk; };
     auto totalOf = [&](size_t c) {
         const size_t off = c * chunk, owned = ownedOf(c);
@@ -823,6 +986,7 @@ static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, siz
             p.pool->finish(jobs[c % 3]);
             src = p.s_in[c % 3];
         }
+        p.lastH2D += totalOf(c);
         return cudaMemcpyAsync(p.d_in[c % 2], src, totalOf(c), cudaMemcpyHostToDevice, p.stream[c % 2]);
     };
     auto bail = [&](PFAC_status_t st) {
@@ -849,6 +1013,7 @@ static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, siz
                 return bail(PFAC_STATUS_INTERNAL_ERROR);
             written += count;
         }
+        p.lastD2H += 8 + count * (4 + posBytes);
         // the slot is reused two chunks later: its D2H must have drained before the next H2D into it
         if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
     }
@@ -1172,6 +1337,23 @@ PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
 PFAC_status_t PFAC_hostCopy(void* dst, const void* src, size_t bytes) {
     if (bytes && (!dst || !src)) return PFAC_STATUS_INVALID_PARAMETER;
     acquireCopyPool()->copy(dst, src, bytes, true);  // destination written with streaming stores
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_lastHostTransfer(PFAC_handle_t handle, size_t* h2d_bytes, size_t* d2h_bytes) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    std::lock_guard<std::mutex> lock(handle->pipeMu);
+    if (h2d_bytes) *h2d_bytes = handle->pipe.lastH2D;
+    if (d2h_bytes) *d2h_bytes = handle->pipe.lastD2H;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_hostZero(void* dst, size_t bytes) {
+    if (bytes && !dst) return PFAC_STATUS_INVALID_PARAMETER;
+    std::shared_ptr<CopyPool> pool = acquireCopyPool();
+    CopyPool::Job job;
+    pool->startZero(job, dst, bytes);
+    pool->finish(job);
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -101,6 +101,10 @@ def test_host_copy_pool_is_exact_and_thread_safe():
         dst = np.zeros(n + 5, dtype=np.uint8)
         host_copy(dst[5:], src)
         assert np.array_equal(dst[5:], src) and not dst[:5].any()
+    for n in (1, 63, 65, 70_001, (1 << 20) + 3, 5_000_011):                   # PFAC_hostZero: the pool's zero fill
+        buf = np.full(n + 9, 7, dtype=np.uint8)
+        assert L.PFAC_hostZero(buf[4:].ctypes.data, n) == 0
+        assert not buf[4:4 + n].any() and (buf[:4] == 7).all() and (buf[4 + n:] == 7).all()
     srcs = [rng.integers(0, 256, size=6_000_000 + 4097 * i, dtype=np.uint8) for i in range(4)]
     dsts = [np.zeros_like(x) for x in srcs]
     ts = [threading.Thread(target=lambda d=d, x=x: [host_copy(d, x) for _ in range(3)]) for d, x in zip(dsts, srcs)]

@@ -492,6 +492,48 @@ def test_pageable_and_pinned_host_buffers_agree(cuda, tmp_path, monkeypatch):
         assert np.array_equal(ids, wid) and np.array_equal(pos.astype(np.int64), wpos)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_result_sparse_and_dense_paths(cuda, tmp_path, monkeypatch, pinned):
+    """PFAC_matchFromHost returns the dense array either by shipping it over PCIe or (default) by
+    shipping the (id, position) pairs and letting the host zero-fill + scatter (pfac_api.cu
+    hostDenseSparse).  A text whose first third is match-dense (more than one match per 16 positions:
+    those chunks fall back to the dense kernel), the rest sparse; stale garbage in the output buffer;
+    both modes and the transfer counters."""
+    from pfac_b200 import PFAC
+    monkeypatch.setenv("PFAC_B200_HOST_CHUNK_MB", "1")
+    monkeypatch.setenv("PFAC_B200_STAGE_CHUNK_MB", "1")
+    pats = synth.patterns_snort_like(800, seed=91) + [b"zz", b"z"]
+    pats = list(dict.fromkeys(pats))
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = (1 << 20) * 6 + 777
+    text = synth.make_text("ascii", 9191, 0, n, n, pats, 700)
+    dense_part = (1 << 20) * 2 + 5000
+    rng = np.random.default_rng(3)
+    text[:dense_part][rng.random(dense_part) < 0.3] = ord("z")            # 30 % of the positions match
+    want = orc.match(text)
+    assert (want[:dense_part] > 0).mean() > 0.25 and (want[dense_part:] > 0).mean() < 0.05
+    h_in = torch.from_numpy(text).pin_memory() if pinned else text
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        moved = {}
+        for mode in ("sparse", "dense"):
+            if mode == "dense":
+                monkeypatch.setenv("PFAC_B200_HOST_RESULT", "dense")
+            h_out = torch.full((n,), -5, dtype=torch.int32)
+            h_out = h_out.pin_memory() if pinned else h_out.numpy()
+            pf.matchFromHost(h_in, h_out, size=n)
+            got = h_out.numpy() if pinned else h_out
+            bad = np.flatnonzero(got != want)
+            assert bad.size == 0, (mode, int(bad[0]), int(got[bad[0]]), int(want[bad[0]]))
+            moved[mode] = pf.lastHostTransfer()
+            for cut in (1, 15, (1 << 20) - 1, (1 << 20) + 1):
+                assert np.array_equal(pf.matchFromHost(text[:cut].copy()), orc.match(text[:cut])), (mode, cut)
+        assert moved["dense"][1] == 4 * n and moved["dense"][0] >= n
+        # sparse: the two dense chunks came back whole, the rest as pairs
+        assert 4 * (2 << 20) <= moved["sparse"][1] < 4 * (3 << 20) + 8 * int((want > 0).sum())
+
+
 def test_multi_gpu_driver_one_process(cuda, tmp_path, monkeypatch):
     """PFAC_mgpu_* (the library-level replacement of reference test/omp_PFAC.cpp): shards + halo, one
     host thread per handle, runs placed at the exclusive scan of the per-GPU counts.  Uses every
