@@ -755,9 +755,12 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
     // in flight: [host copy of chunk c+2 into pinned staging (pageable input only)] || [H2D of chunk
     // c+1] || [match + compaction of chunk c on the GPU, zero fill of its h_out slice on the host]
     CopyPool::Job jobs[3];
-    CopyPool::Job zero;
+    CopyPool::Job zero[2];  // the fill runs two chunks ahead, so the workers never wait for the GPU
     auto hostStage = [&](size_t c) {
         if (stIn && c < nchunks) p.pool->start(jobs[c % 3], p.s_in[c % 3], h_in + c * chunk, totalOf(c));
+    };
+    auto zeroFill = [&](size_t c) {
+        if (c < nchunks) p.pool->startZero(zero[c % 2], h_out + c * chunk, ownedOf(c) * sizeof(int));
     };
     auto h2d = [&](size_t c) -> cudaError_t {
         const void* src = h_in + c * chunk;
@@ -770,20 +773,22 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
     };
     auto bail = [&](PFAC_status_t st) {
         if (stIn) for (int j = 0; j < 3; j++) p.pool->finish(jobs[j]);
-        p.pool->finish(zero);
+        p.pool->finish(zero[0]);
+        p.pool->finish(zero[1]);
         cudaDeviceSynchronize();
         return st;
     };
     p.lastH2D = p.lastD2H = 0;
     hostStage(0);
     hostStage(1);
+    zeroFill(0);
+    zeroFill(1);
     if (h2d(0) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
     for (size_t c = 0; c < nchunks; c++) {
         const int slot = int(c % 2);
         const size_t off = c * chunk, owned = ownedOf(c);
         if (c + 1 < nchunks && h2d(c + 1) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
         hostStage(c + 2);
-        p.pool->startZero(zero, h_out + off, owned * sizeof(int));  // the workers fill while the GPU matches
         unsigned long long count = 0;
         PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, totalOf(c), 0, p.d_out[slot], p.d_pos[slot],
                                        false, p.stream[slot], &count);
@@ -798,13 +803,13 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
                     return bail(PFAC_STATUS_INTERNAL_ERROR);
                 p.lastD2H += count * 8;
             }
-            p.pool->finish(zero);
+            p.pool->finish(zero[slot]);
             if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
             int* dst = h_out + off;
             for (unsigned long long i = 0; i < count; i++) dst[pos[i]] = ids[i];
         } else {
             // dense chunk: the position buffer (8 bytes per position) doubles as the dense result
-            p.pool->finish(zero);
+            p.pool->finish(zero[slot]);
             int* d_dense = p.d_pos[slot];
             cudaError_t e = pfac::launchMatchDense(handle->table, handle->launch, p.d_in[slot], owned, totalOf(c),
                                                    d_dense, p.stream[slot]);
@@ -814,6 +819,7 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
             if (e != cudaSuccess) return bail(cudaToStatus(e));
             p.lastD2H += owned * sizeof(int);
         }
+        zeroFill(c + 2);
     }
     if (cudaStreamSynchronize(p.stream[0]) != cudaSuccess || cudaStreamSynchronize(p.stream[1]) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
