@@ -130,6 +130,18 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
  * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
 PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);
 
+/* ---- compiled-table files: parse, sort, number and lay out a large dictionary once (20,000
+ * patterns: ~0.5 s), later processes read the result back.  Versioned and checksummed; a file that
+ * is not recognised gives PFAC_STATUS_INVALID_PARAMETER (compile from the pattern file instead), a
+ * missing one PFAC_STATUS_FILE_OPEN_ERROR.  PFAC_loadCompiledPatterns leaves the handle exactly as
+ * PFAC_readPatternFromFile on the original pattern file would (same IDs, same dump, same results);
+ * layouts stored for another shared-memory budget / filter policy are recompiled from the stored
+ * automaton. */
+PFAC_status_t PFAC_saveCompiledPatterns(PFAC_handle_t handle, const char *filename);
+PFAC_status_t PFAC_loadCompiledPatterns(PFAC_handle_t handle, const char *filename);
+PFAC_status_t PFAC_tableSave(PFAC_table_t table, const char *filename);      /* host only */
+PFAC_status_t PFAC_tableLoad(const char *filename, PFAC_table_t *table);     /* host only */
+
 /* info / dump-to-path for a live handle */
 PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);
 PFAC_status_t PFAC_dumpTransitionTableToFile(PFAC_handle_t handle, const char *filename);

@@ -127,6 +127,10 @@ def load_library():
         "PFAC_tableGetLayout": [vp] + [ctypes.POINTER(vp)] * 8,
         "PFAC_tableGetLayout2": [vp] + [ctypes.POINTER(vp)] * 3,
         "PFAC_tableGetFilter": [vp, ctypes.POINTER(vp)],
+        "PFAC_tableSave": [vp, cp],
+        "PFAC_tableLoad": [cp, ctypes.POINTER(vp)],
+        "PFAC_saveCompiledPatterns": [vp, cp],
+        "PFAC_loadCompiledPatterns": [vp, cp],
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_memoryUsage": [vp],
         "PFAC_hostCopy": [vp, vp, sz],
@@ -241,6 +245,12 @@ class PFAC:
         _check(self._L.PFAC_readPatternFromArrays(self._h, ptrs, lens, len(patterns)),
                "PFAC_readPatternFromArrays")
         del keep
+
+    def saveCompiledPatterns(self, filename):
+        _check(self._L.PFAC_saveCompiledPatterns(self._h, os.fsencode(filename)), "PFAC_saveCompiledPatterns")
+
+    def loadCompiledPatterns(self, filename):
+        _check(self._L.PFAC_loadCompiledPatterns(self._h, os.fsencode(filename)), "PFAC_loadCompiledPatterns")
 
     def dumpTransitionTable(self, filename):
         _check(self._L.PFAC_dumpTransitionTableToFile(self._h, os.fsencode(filename)),
@@ -388,10 +398,13 @@ def _host_len(x):
 class TableCompiler:
     """Host-only table compiler (no GPU needed): PFAC_tableCompile* in include/PFAC_ext.h."""
 
-    def __init__(self, pattern_file=None, image=None, hot_budget_bytes=24 * 1024, patterns=None):
+    def __init__(self, pattern_file=None, image=None, hot_budget_bytes=24 * 1024, patterns=None,
+                 compiled_file=None):
         self._L = load_library()
         self._t = ctypes.c_void_p()
-        if patterns is not None:
+        if compiled_file is not None:
+            st = self._L.PFAC_tableLoad(os.fsencode(compiled_file), ctypes.byref(self._t))
+        elif patterns is not None:
             ptrs, lens, keep = _pattern_arrays(patterns)
             st = self._L.PFAC_tableCompileArrays(ptrs, lens, len(patterns), hot_budget_bytes,
                                                  ctypes.byref(self._t))
@@ -416,6 +429,10 @@ class TableCompiler:
 
     def dump(self, filename):
         _check(self._L.PFAC_tableDumpToFile(self._t, os.fsencode(filename)), "PFAC_tableDumpToFile")
+
+    def save(self, filename):
+        """Write the compiled-table file (PFAC_tableSave); TableCompiler(compiled_file=...) reads it back."""
+        _check(self._L.PFAC_tableSave(self._t, os.fsencode(filename)), "PFAC_tableSave")
 
     def layout(self):
         """Copies of the device layout arrays as a dict: root[256] i32, pre2[2048] u32 (bit-reversed words), rank2[2048] u16, next2 u32, hot/cold

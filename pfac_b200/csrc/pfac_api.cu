@@ -397,13 +397,17 @@ int filterPolicy() {
 
 // compile the device layouts for the current perf mode and upload them (reference
 // PFAC_bindTable, PFAC.cpp:321-343, which picks the dense 2-D table or the hash table)
-PFAC_status_t bindTable(PFAC_handle_t h) {
+PFAC_status_t uploadTables(PFAC_handle_t h) {
     freeDeviceTable(h);
-    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, filterPolicy());
-    pfac::compileLayout(h->machine, hotBudget(h, true), h->layoutReduce, filterPolicy());
     PFAC_status_t st = uploadLayout(h, h->layout, h->table);
     if (st != PFAC_STATUS_SUCCESS) return st;
     return uploadLayout(h, h->layoutReduce, h->tableReduce);
+}
+
+PFAC_status_t bindTable(PFAC_handle_t h) {
+    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, filterPolicy());
+    pfac::compileLayout(h->machine, hotBudget(h, true), h->layoutReduce, filterPolicy());
+    return uploadTables(h);
 }
 
 PFAC_status_t loadImage(PFAC_handle_t h, const char* image, size_t size) {
@@ -1205,6 +1209,8 @@ PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char* h_in, size_t 
 struct PFAC_table {
     pfac::Machine machine;
     pfac::DeviceLayout layout;
+    size_t budget = 0;   // what the layout was compiled for (stored in compiled-table files)
+    int policy = pfac::kFilterAuto;
 };
 
 static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_tableInfo_t* info) {
@@ -1244,7 +1250,9 @@ PFAC_status_t PFAC_tableCompile(const char* image, size_t size, size_t hot_budge
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
     int st = pfac::buildMachine(image, size, t->machine);
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
-    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, filterPolicy());
+    t->budget = hot_budget_bytes;
+    t->policy = filterPolicy();
+    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, t->policy);
     *table = t;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1257,7 +1265,9 @@ PFAC_status_t PFAC_tableCompileArrays(const char* const* patterns, const size_t*
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
     int st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, t->machine);
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
-    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, filterPolicy());
+    t->budget = hot_budget_bytes;
+    t->policy = filterPolicy();
+    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, t->policy);
     *table = t;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1268,6 +1278,86 @@ PFAC_status_t PFAC_tableCompileFile(const char* filename, size_t hot_budget_byte
     PFAC_status_t st = readWholeFile(filename, image);
     if (st != PFAC_STATUS_SUCCESS) return st;
     return PFAC_tableCompile(image.data(), image.size(), hot_budget_bytes, table);
+}
+
+// ---- compiled-table files (pfac_table.h saveCompiled / loadCompiled) ------------------------------
+PFAC_status_t PFAC_tableSave(PFAC_table_t table, const char* filename) {
+    if (!table) return PFAC_STATUS_INVALID_HANDLE;
+    if (!filename) return PFAC_STATUS_INVALID_PARAMETER;
+    pfac::CompiledLayout c;
+    c.budget = table->budget;
+    c.policy = table->policy;
+    c.layout = table->layout;
+    return pfac::saveCompiled(filename, table->machine, {&c}) ? PFAC_STATUS_SUCCESS : PFAC_STATUS_FILE_OPEN_ERROR;
+}
+
+PFAC_status_t PFAC_tableLoad(const char* filename, PFAC_table_t* table) {
+    if (!filename || !table) return PFAC_STATUS_INVALID_PARAMETER;
+    *table = nullptr;
+    FILE* fp = fopen(filename, "rb");
+    if (!fp) return PFAC_STATUS_FILE_OPEN_ERROR;
+    fclose(fp);
+    PFAC_table* t = new (std::nothrow) PFAC_table();
+    if (!t) return PFAC_STATUS_ALLOC_FAILED;
+    std::vector<pfac::CompiledLayout> ls;
+    if (!pfac::loadCompiled(filename, t->machine, ls) || ls.empty()) { delete t; return PFAC_STATUS_INVALID_PARAMETER; }
+    t->layout = std::move(ls[0].layout);
+    t->budget = size_t(ls[0].budget);
+    t->policy = ls[0].policy;
+    *table = t;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_saveCompiledPatterns(PFAC_handle_t handle, const char* filename) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!filename) return PFAC_STATUS_INVALID_PARAMETER;
+    std::lock_guard<std::mutex> lock(handle->mu);
+    pfac::CompiledLayout a, b;
+    a.budget = hotBudget(handle, false);
+    b.budget = hotBudget(handle, true);
+    a.policy = b.policy = filterPolicy();
+    a.layout = handle->layout;
+    b.layout = handle->layoutReduce;
+    return pfac::saveCompiled(filename, handle->machine, {&a, &b}) ? PFAC_STATUS_SUCCESS
+                                                                    : PFAC_STATUS_FILE_OPEN_ERROR;
+}
+
+// Same end state as PFAC_readPatternFromFile on the pattern file the image was compiled from.  A
+// layout stored for another shared-memory budget or filter policy is not used: that one is
+// recompiled from the stored automaton.
+PFAC_status_t PFAC_loadCompiledPatterns(PFAC_handle_t handle, const char* filename) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!filename) return PFAC_STATUS_INVALID_PARAMETER;
+    FILE* fp = fopen(filename, "rb");
+    if (!fp) return PFAC_STATUS_FILE_OPEN_ERROR;
+    fclose(fp);
+    pfac::Machine m;
+    std::vector<pfac::CompiledLayout> ls;
+    if (!pfac::loadCompiled(filename, m, ls)) return PFAC_STATUS_INVALID_PARAMETER;
+    std::lock_guard<std::mutex> lock(handle->mu);
+    if (handle->patternsReady) {
+        cudaDeviceSynchronize();
+        freePatterns(handle);
+    }
+    handle->patternFile[0] = 0;
+    handle->machine = std::move(m);
+    handle->patternsReady = true;
+    const int policy = filterPolicy();
+    auto take = [&](bool reduceKernel, pfac::DeviceLayout& dst) {
+        const size_t budget = hotBudget(handle, reduceKernel);
+        for (pfac::CompiledLayout& c : ls)
+            if (c.budget == budget && c.policy == policy && !c.layout.pre2.empty()) {
+                dst = c.layout;
+                return;
+            }
+        pfac::compileLayout(handle->machine, budget, dst, policy);
+    };
+    take(false, handle->layout);
+    take(true, handle->layoutReduce);
+    PFAC_status_t st = uploadTables(handle);
+    if (st != PFAC_STATUS_SUCCESS) { freePatterns(handle); return st; }
+    return PFAC_STATUS_SUCCESS;
 }
 
 PFAC_status_t PFAC_tableDestroy(PFAC_table_t table) {

@@ -582,4 +582,190 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
     L.coldMaxProbe = bestCold;
 }
 
+// ---- compiled-table files -----------------------------------------------------------------------
+namespace {
+
+constexpr char kFileMagic[8] = {'P', 'F', 'A', 'C', 'B', '2', '0', '0'};
+constexpr uint32_t kFileVersion = 3;  // bump whenever Machine / DeviceLayout or their meaning change
+
+struct Writer {
+    std::string buf;
+    void raw(const void* p, size_t n) { buf.append(static_cast<const char*>(p), n); }
+    template <typename T> void pod(const T& v) { raw(&v, sizeof(T)); }
+    template <typename T> void vec(const std::vector<T>& v) {
+        pod<uint64_t>(v.size());
+        if (!v.empty()) raw(v.data(), v.size() * sizeof(T));
+    }
+};
+
+struct Reader {
+    const char* p;
+    const char* end;
+    bool ok = true;
+    void raw(void* dst, size_t n) {
+        if (!ok || size_t(end - p) < n) { ok = false; return; }
+        memcpy(dst, p, n);
+        p += n;
+    }
+    template <typename T> void pod(T& v) { raw(&v, sizeof(T)); }
+    template <typename T> void vec(std::vector<T>& v) {
+        uint64_t n = 0;
+        pod(n);
+        if (!ok || n > uint64_t(end - p) / sizeof(T)) { ok = false; return; }
+        v.resize(size_t(n));
+        if (n) raw(v.data(), size_t(n) * sizeof(T));
+    }
+};
+
+uint64_t checksum(const char* p, size_t n) {  // FNV-1a, 64 bit
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) h = (h ^ uint8_t(p[i])) * 1099511628211ull;
+    return h;
+}
+
+void putMachine(Writer& w, const Machine& m) {
+    w.pod<uint64_t>(m.image.size());
+    w.raw(m.image.data(), m.image.size());
+    w.pod(m.numPatterns); w.pod(m.numFinal); w.pod(m.initialState); w.pod(m.numStates);
+    w.pod(m.maxPatternLen); w.pod(m.numLeaves);
+    std::vector<uint64_t> off64(m.sortedOff.begin(), m.sortedOff.end());
+    w.vec(off64);
+    w.vec(m.sortedId);
+    w.vec(m.lenById);
+    std::vector<uint64_t> offById64(m.offById.begin(), m.offById.end());
+    w.vec(offById64);
+    // rows, flattened: per-state edge counts, then all edges in state order / insertion order
+    std::vector<uint32_t> counts(m.rows.size());
+    std::vector<Edge> flat;
+    for (size_t i = 0; i < m.rows.size(); i++) {
+        counts[i] = uint32_t(m.rows[i].size());
+        flat.insert(flat.end(), m.rows[i].begin(), m.rows[i].end());
+    }
+    w.vec(counts);
+    w.vec(flat);
+}
+
+void getMachine(Reader& r, Machine& m) {
+    uint64_t n = 0;
+    r.pod(n);
+    if (!r.ok || n > uint64_t(r.end - r.p)) { r.ok = false; return; }
+    m.image.assign(r.p, size_t(n));
+    r.p += n;
+    r.pod(m.numPatterns); r.pod(m.numFinal); r.pod(m.initialState); r.pod(m.numStates);
+    r.pod(m.maxPatternLen); r.pod(m.numLeaves);
+    std::vector<uint64_t> off64, offById64;
+    r.vec(off64);
+    r.vec(m.sortedId);
+    r.vec(m.lenById);
+    r.vec(offById64);
+    m.sortedOff.assign(off64.begin(), off64.end());
+    m.offById.assign(offById64.begin(), offById64.end());
+    std::vector<uint32_t> counts;
+    std::vector<Edge> flat;
+    r.vec(counts);
+    r.vec(flat);
+    if (!r.ok) return;
+    uint64_t total = 0;
+    for (uint32_t c : counts) total += c;
+    if (total != flat.size() || int64_t(counts.size()) < int64_t(m.numStates)) { r.ok = false; return; }
+    m.rows.assign(counts.size(), std::vector<Edge>());
+    size_t at = 0;
+    for (size_t i = 0; i < counts.size(); i++) {
+        m.rows[i].assign(flat.begin() + long(at), flat.begin() + long(at + counts[i]));
+        at += counts[i];
+    }
+}
+
+void putLayout(Writer& w, const DeviceLayout& L) {
+    w.raw(L.root, sizeof(L.root));
+    w.raw(L.lut, sizeof(L.lut));
+    w.pod(L.codeBits); w.pod(L.gramLen);
+    w.vec(L.pre2); w.vec(L.rank2); w.vec(L.next2); w.vec(L.best2); w.vec(L.chk2); w.vec(L.hfilt);
+    w.pod(L.hfiltK); w.pod(L.hfiltBitsSet);
+    w.pod<uint8_t>(L.next2Hot);
+    w.vec(L.hot); w.vec(L.cold); w.vec(L.chains); w.vec(L.tails);
+    w.pod(L.hotBuckets); w.pod(L.coldBuckets); w.pod(L.mul); w.pod(L.hotDepth);
+    w.pod<uint8_t>(L.chainsHot);
+    w.pod(L.maxDepth); w.pod(L.numEdges); w.pod(L.hashEdges); w.pod(L.numChains);
+    w.pod(L.hotMaxProbe); w.pod(L.coldMaxProbe); w.pod(L.pre2BitsSet); w.pod(L.rootFanout);
+}
+
+void getLayout(Reader& r, DeviceLayout& L) {
+    r.raw(L.root, sizeof(L.root));
+    r.raw(L.lut, sizeof(L.lut));
+    r.pod(L.codeBits); r.pod(L.gramLen);
+    r.vec(L.pre2); r.vec(L.rank2); r.vec(L.next2); r.vec(L.best2); r.vec(L.chk2); r.vec(L.hfilt);
+    r.pod(L.hfiltK); r.pod(L.hfiltBitsSet);
+    uint8_t b = 0;
+    r.pod(b); L.next2Hot = b != 0;
+    r.vec(L.hot); r.vec(L.cold); r.vec(L.chains); r.vec(L.tails);
+    r.pod(L.hotBuckets); r.pod(L.coldBuckets); r.pod(L.mul); r.pod(L.hotDepth);
+    r.pod(b); L.chainsHot = b != 0;
+    r.pod(L.maxDepth); r.pod(L.numEdges); r.pod(L.hashEdges); r.pod(L.numChains);
+    r.pod(L.hotMaxProbe); r.pod(L.coldMaxProbe); r.pod(L.pre2BitsSet); r.pod(L.rootFanout);
+    // sizes the kernels rely on
+    if (r.ok && (L.pre2.size() != 2048 || L.rank2.size() != 2048 || L.next2.empty() ||
+                 (!L.hfilt.empty() && L.hfilt.size() != size_t(kHashFilterWords)) ||
+                 L.hot.size() != size_t(L.hotBuckets) * 4 || L.cold.size() != size_t(L.coldBuckets) * 4 ||
+                 (L.chains.size() & 3) || (L.tails.size() & 15)))
+        r.ok = false;
+}
+
+}  // namespace
+
+bool saveCompiled(const char* filename, const Machine& m, const std::vector<const CompiledLayout*>& layouts) {
+    Writer w;
+    putMachine(w, m);
+    w.pod<uint32_t>(uint32_t(layouts.size()));
+    for (const CompiledLayout* c : layouts) {
+        w.pod(c->budget);
+        w.pod(c->policy);
+        putLayout(w, c->layout);
+    }
+    FILE* fp = fopen(filename, "wb");
+    if (!fp) return false;
+    const uint64_t size = w.buf.size(), sum = checksum(w.buf.data(), w.buf.size());
+    const uint32_t consts[3] = {kHashFilterMul, kHashFilterMul2, kHashFilterMul3};
+    bool ok = fwrite(kFileMagic, 1, 8, fp) == 8 && fwrite(&kFileVersion, 4, 1, fp) == 1 &&
+              fwrite(consts, 4, 3, fp) == 3 && fwrite(&size, 8, 1, fp) == 1 && fwrite(&sum, 8, 1, fp) == 1 &&
+              fwrite(w.buf.data(), 1, w.buf.size(), fp) == w.buf.size();
+    ok = (fclose(fp) == 0) && ok;
+    return ok;
+}
+
+bool loadCompiled(const char* filename, Machine& m, std::vector<CompiledLayout>& layouts) {
+    FILE* fp = fopen(filename, "rb");
+    if (!fp) return false;
+    char magic[8];
+    uint32_t version = 0, consts[3] = {0, 0, 0};
+    uint64_t size = 0, sum = 0;
+    bool ok = fread(magic, 1, 8, fp) == 8 && fread(&version, 4, 1, fp) == 1 && fread(consts, 4, 3, fp) == 3 &&
+              fread(&size, 8, 1, fp) == 1 && fread(&sum, 8, 1, fp) == 1;
+    ok = ok && !memcmp(magic, kFileMagic, 8) && version == kFileVersion && consts[0] == kHashFilterMul &&
+         consts[1] == kHashFilterMul2 && consts[2] == kHashFilterMul3 && size < (uint64_t(1) << 34);
+    std::string buf;
+    if (ok) {
+        buf.resize(size_t(size));
+        ok = fread(&buf[0], 1, buf.size(), fp) == buf.size() && fgetc(fp) == EOF;
+    }
+    fclose(fp);
+    if (!ok || checksum(buf.data(), buf.size()) != sum) return false;
+    Reader r{buf.data(), buf.data() + buf.size()};
+    Machine mm;
+    getMachine(r, mm);
+    uint32_t n = 0;
+    r.pod(n);
+    if (!r.ok || n > 16) return false;
+    std::vector<CompiledLayout> ls(n);
+    for (uint32_t i = 0; i < n && r.ok; i++) {
+        r.pod(ls[i].budget);
+        r.pod(ls[i].policy);
+        getLayout(r, ls[i].layout);
+    }
+    if (!r.ok || r.p != r.end) return false;
+    m = std::move(mm);
+    layouts = std::move(ls);
+    return true;
+}
+
 }  // namespace pfac

@@ -142,4 +142,18 @@ struct DeviceLayout {
 // budget holds it; kFilterExact keeps the exact K-gram stage (A/B measurements, tests).
 void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int filterPolicy = kFilterAuto);
 
+// ---- compiled-table files -----------------------------------------------------------------------
+// Binary image of a Machine plus any number of DeviceLayouts (each tagged with the shared-memory
+// budget and filter policy it was compiled for), so that a large dictionary is parsed, sorted,
+// numbered and laid out once and later processes only read it back.  Little-endian, versioned,
+// with a checksum; loadCompiled rejects anything it does not recognise (returns false), and the
+// caller then compiles from the pattern file as usual.
+struct CompiledLayout {
+    uint64_t budget = 0;
+    int32_t policy = kFilterAuto;
+    DeviceLayout layout;
+};
+bool saveCompiled(const char* filename, const Machine& m, const std::vector<const CompiledLayout*>& layouts);
+bool loadCompiled(const char* filename, Machine& m, std::vector<CompiledLayout>& layouts);
+
 }  // namespace pfac

@@ -534,6 +534,45 @@ def test_host_result_sparse_and_dense_paths(cuda, tmp_path, monkeypatch, pinned)
         assert 4 * (2 << 20) <= moved["sparse"][1] < 4 * (3 << 20) + 8 * int((want > 0).sum())
 
 
+def test_compiled_patterns_file(cuda, tmp_path, monkeypatch):
+    """PFAC_saveCompiledPatterns / PFAC_loadCompiledPatterns: a second handle loaded from the file is
+    indistinguishable from one that read the pattern file (table info, dump, results); a stored layout
+    for another filter policy is recompiled from the stored automaton; a bad file changes nothing."""
+    from pfac_b200 import PFAC, PFACError, Status
+    pats = synth.patterns_snort_like(3000, seed=101)
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    blob = str(tmp_path / "p.pfacb")
+    text = synth.make_text("ascii", 1011, 0, 300_000, 300_000, pats, 90)
+    with PFAC() as a, PFAC() as b:
+        a.readPatternFromFile(pfile)
+        a.saveCompiledPatterns(blob)
+        with pytest.raises(PFACError) as e:
+            b.saveCompiledPatterns(str(tmp_path / "none.pfacb"))
+        assert e.value.status == Status.PATTERNS_NOT_READY
+        b.loadCompiledPatterns(blob)
+        assert a.tableInfo() == b.tableInfo()
+        a.dumpTransitionTable(str(tmp_path / "a.txt"))
+        b.dumpTransitionTable(str(tmp_path / "b.txt"))
+        assert open(str(tmp_path / "a.txt"), "rb").read() == open(str(tmp_path / "b.txt"), "rb").read()
+        _check_all(b, orc, text, cuda)
+        # garbage: INVALID_PARAMETER, the loaded patterns stay
+        bad = str(tmp_path / "bad.pfacb")
+        open(bad, "wb").write(open(blob, "rb").read()[:-7])
+        with pytest.raises(PFACError) as e:
+            b.loadCompiledPatterns(bad)
+        assert e.value.status == Status.INVALID_PARAMETER
+        with pytest.raises(PFACError) as e:
+            b.loadCompiledPatterns(str(tmp_path / "missing.pfacb"))
+        assert e.value.status == Status.FILE_OPEN_ERROR
+        _check_all(b, orc, text, cuda)
+        # other policy than the file's: layouts are recompiled, results unchanged
+        monkeypatch.setenv("PFAC_B200_FILTER", "exact")
+        b.loadCompiledPatterns(blob)
+        assert b.tableInfo()["hashed_filter"] == 0
+        _check_all(b, orc, text, cuda)
+
+
 def test_multi_gpu_driver_one_process(cuda, tmp_path, monkeypatch):
     """PFAC_mgpu_* (the library-level replacement of reference test/omp_PFAC.cpp): shards + halo, one
     host thread per handle, runs placed at the exclusive scan of the per-GPU counts.  Uses every

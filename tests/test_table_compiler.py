@@ -316,3 +316,35 @@ def test_random_dictionaries_both_first_stages(monkeypatch, seed):
                                 for i in range(n)], dtype=np.int32)
                 bad = np.flatnonzero(got != want)
                 assert bad.size == 0, (seed, trial, policy, budget, int(bad[0]), int(got[bad[0]]), int(want[bad[0]]))
+
+
+def test_compiled_table_file_round_trip(tmp_path, golden_dir):
+    """PFAC_tableSave / PFAC_tableLoad: the automaton and the layout come back bit for bit (info, every
+    layout array, the text dump); truncated, corrupted and foreign files are rejected, a missing
+    file is FILE_OPEN_ERROR."""
+    for name, budget in (("synth_snort.pat", 64 * 1024), ("synth_dna.pat", 24 * 1024), ("example_pattern", 0)):
+        src = os.path.join(golden_dir, name)
+        a = TableCompiler(src, hot_budget_bytes=budget)
+        f = str(tmp_path / (name + ".pfacb"))
+        a.save(f)
+        b = TableCompiler(compiled_file=f)
+        assert a.info() == b.info()
+        la, lb = a.layout(), b.layout()
+        assert la.keys() == lb.keys()
+        for k in la:
+            assert np.array_equal(la[k], lb[k]), k
+        a.dump(str(tmp_path / "a.txt"))
+        b.dump(str(tmp_path / "b.txt"))
+        assert open(str(tmp_path / "a.txt"), "rb").read() == open(str(tmp_path / "b.txt"), "rb").read()
+    blob = open(f, "rb").read()
+    bad = str(tmp_path / "bad.pfacb")
+    for mutate in (lambda x: x[:-1], lambda x: x[:40], lambda x: x + b"\0",
+                   lambda x: x[:100] + bytes([x[100] ^ 1]) + x[101:], lambda x: b"NOTPFAC0" + x[8:],
+                   lambda x: x[:8] + b"\xff\xff\xff\xff" + x[12:], lambda x: b""):
+        open(bad, "wb").write(mutate(blob))
+        with pytest.raises(PFACError) as e:
+            TableCompiler(compiled_file=bad)
+        assert e.value.status == Status.INVALID_PARAMETER
+    with pytest.raises(PFACError) as e:
+        TableCompiler(compiled_file=str(tmp_path / "missing.pfacb"))
+    assert e.value.status == Status.FILE_OPEN_ERROR
