@@ -48,3 +48,36 @@ def allgather_count_offsets(count: int, device=None, group=None) -> Tuple[int, i
     counts = [int(x) for x in allc.cpu().tolist()]
     offs, total = exclusive_offsets(counts)
     return offs[rank], total, counts
+
+
+def place_runs(ids, pos, counts: List[int], dst: int = 0, group=None):
+    """Optional second step of SURVEY.md 8(e): one global (ID, position) list on rank `dst`.  Every
+    rank sends its run (the first counts[rank] entries of `ids` int32 / `pos` int64, positions
+    already global) point to point; `dst` receives each run directly at its scanned offset, so no
+    rank holds more than its own run plus, on `dst`, the final list.  NCCL send/recv over NVLink on
+    GPUs (tensors on the device), gloo in the CPU tests.  Returns (ids, pos) of length sum(counts)
+    on `dst`, (None, None) elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    offs, total = exclusive_offsets(counts)
+    n = int(counts[rank])
+    if rank != dst:
+        if n:
+            dist.send(ids[:n].contiguous(), dst, group=group)
+            dist.send(pos[:n].contiguous(), dst, group=group)
+        return None, None
+    g_ids = torch.empty(total, dtype=torch.int32, device=ids.device)
+    g_pos = torch.empty(total, dtype=torch.int64, device=pos.device)
+    for r in range(world):
+        c, o = int(counts[r]), offs[r]
+        if c == 0:
+            continue
+        if r == rank:
+            g_ids[o:o + c] = ids[:c]
+            g_pos[o:o + c] = pos[:c]
+        else:
+            dist.recv(g_ids[o:o + c], r, group=group)   # contiguous slices: received in place
+            dist.recv(g_pos[o:o + c], r, group=group)
+    return g_ids, g_pos

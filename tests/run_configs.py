@@ -71,6 +71,8 @@ def main():
                     help="bytes per rank to verify against the oracle (-1 = all, 0 = none)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--perf-mode", type=int, default=0)
+    ap.add_argument("--gather", action="store_true",
+                    help="multi-GPU reduce: also deliver every rank's run to rank 0 (sharding.place_runs) and time it")
     args = ap.parse_args()
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -78,7 +80,7 @@ def main():
     import torch.distributed as dist
     from oracle import Oracle
     from pfac_b200 import PFAC
-    from pfac_b200.sharding import allgather_count_offsets
+    from pfac_b200.sharding import allgather_count_offsets, place_runs
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -161,6 +163,20 @@ def main():
             res["count_scan_ms"] = (time.perf_counter() - t0) * 1e3
         else:
             off, total_m = 0, count
+        if world > 1 and args.gather and pos64:
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            g_ids, g_pos = place_runs(d_id, d_pos, counts, dst=0)
+            torch.cuda.synchronize()
+            dist.barrier()
+            res["gather_ms"] = (time.perf_counter() - t0) * 1e3
+            res["gather_bytes"] = 12 * total_m
+            if rank == 0:   # one global list, ascending positions, this rank's run at its offset
+                ok = bool((g_pos[1:] > g_pos[:-1]).all().item()) if total_m > 1 else True
+                ok = ok and g_ids.numel() == total_m and bool(torch.equal(g_ids[:count], d_id[:count]))
+                res["gather_ok"] = ok
+            del g_ids, g_pos
         res["matches_rank"] = count
         res["matches_total"] = total_m
         res["global_offset"] = off

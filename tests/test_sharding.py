@@ -92,7 +92,7 @@ sys.path.insert(0, %(root)r)
 import numpy as np, torch, torch.distributed as dist
 from oracle import Oracle
 from pfac_b200 import synth
-from pfac_b200.sharding import shard_bounds, allgather_count_offsets
+from pfac_b200.sharding import shard_bounds, allgather_count_offsets, place_runs
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 pats = synth.patterns_c2(300, seed=9, min_len=2, max_len=20)
@@ -109,6 +109,15 @@ off, total, counts = allgather_count_offsets(ids.size)
 g_ids = torch.zeros(total, dtype=torch.int32); g_pos = torch.zeros(total, dtype=torch.int64)
 g_ids[off:off + ids.size] = torch.from_numpy(ids); g_pos[off:off + pos.size] = torch.from_numpy(pos)
 dist.all_reduce(g_ids); dist.all_reduce(g_pos)
+# the same list delivered point to point to the last rank (place_runs)
+cap = ids.size + 5
+t_ids = torch.full((cap,), -1, dtype=torch.int32); t_ids[:ids.size] = torch.from_numpy(ids)
+t_pos = torch.full((cap,), -1, dtype=torch.int64); t_pos[:pos.size] = torch.from_numpy(pos)
+p_ids, p_pos = place_runs(t_ids, t_pos, counts, dst=world - 1)
+if rank == world - 1:
+    assert torch.equal(p_ids, g_ids) and torch.equal(p_pos, g_pos)
+else:
+    assert p_ids is None and p_pos is None
 if rank == 0:
     text = synth.make_text("random", 77, 0, n, n, pats, 256)
     w_ids, w_pos = o.reduce(o.match(text))
