@@ -479,7 +479,8 @@ PFAC_status_t reduceShard(PFAC_handle_t h, const unsigned char* d_in, size_t n_o
 // host pipeline buffers; caller holds h->pipeMu
 PFAC_status_t ensurePipe(PFAC_handle_t h, bool needPos) {
     HostPipe& p = h->pipe;
-    const size_t chunk = envBytes("PFAC_B200_HOST_CHUNK_MB", 32, size_t(1) << 20);
+    size_t chunk = envBytes("PFAC_B200_HOST_CHUNK_MB", 32, size_t(1) << 20);
+    chunk = std::min(std::max(chunk, size_t(1) << 16), size_t(1) << 30);  // 64 KB .. 1 GiB (int positions per chunk)
     const size_t halo = size_t(h->machine.maxPatternLen > 1 ? h->machine.maxPatternLen - 1 : 0);
     const size_t inCap = ((chunk + halo + 255) / 256) * 256;
     if (p.chunk == chunk && p.inCap >= inCap && (!needPos || p.hasPos)) return PFAC_STATUS_SUCCESS;

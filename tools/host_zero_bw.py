@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""Bandwidth of the library's host zero fill (PFAC_hostZero: the copy pool + streaming stores), which
+bounds the sparse result path of PFAC_matchFromHost at 4 bytes per input byte.  CPU only.
+
+    [PFAC_B200_COPY_THREADS=n] python tools/host_zero_bw.py
+"""
 import numpy as np, time, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pfac_b200.api import load_library
