@@ -74,6 +74,26 @@ def test_null_handle_is_invalid_handle_first():
     assert L.PFAC_matchFromDeviceReduce(None, None, 0, None, None, ctypes.byref(n)) == Status.INVALID_HANDLE
     assert L.PFAC_matchFromHostReduce(None, None, 0, None, None, ctypes.byref(n)) == Status.INVALID_HANDLE
     assert L.PFAC_dumpTransitionTable(None, None) == Status.INVALID_HANDLE
+    # additive entry points (include/PFAC_ext.h) follow the same rule
+    m = ctypes.c_ulonglong(0)
+    assert L.PFAC_reduceOnDevice(None, None, 0, None, None, ctypes.byref(n)) == Status.INVALID_HANDLE
+    assert L.PFAC_reduceInplaceOnDevice(None, None, 0, None, None, ctypes.byref(n)) == Status.INVALID_HANDLE
+    assert L.PFAC_setStream(None, None) == Status.INVALID_HANDLE
+    assert L.PFAC_readPatternFromMemory(None, b"x\n", 2) == Status.INVALID_HANDLE
+    assert L.PFAC_readPatternFromArrays(None, None, None, 0) == Status.INVALID_HANDLE
+    assert L.PFAC_matchShardFromDevice(None, None, 0, 0, None) == Status.INVALID_HANDLE
+    assert L.PFAC_matchFromDeviceReduce64(None, None, 0, None, None, ctypes.byref(m)) == Status.INVALID_HANDLE
+    assert L.PFAC_matchShardFromDeviceReduce64(None, None, 0, 0, 0, None, None, ctypes.byref(m)) == Status.INVALID_HANDLE
+    assert L.PFAC_getTableInfo(None, None) == Status.INVALID_HANDLE
+    assert L.PFAC_memoryUsage(None) == Status.INVALID_HANDLE
+    assert L.PFAC_dumpTransitionTableToFile(None, b"x") == Status.INVALID_HANDLE
+    assert L.PFAC_saveCompiledPatterns(None, b"x") == Status.INVALID_HANDLE
+    assert L.PFAC_loadCompiledPatterns(None, b"x") == Status.INVALID_HANDLE
+    assert L.PFAC_lastHostTransfer(None, None, None) == Status.INVALID_HANDLE
+    assert L.PFAC_tableSave(None, b"x") == Status.INVALID_HANDLE
+    assert L.PFAC_tableDestroy(None) == Status.INVALID_HANDLE
+    assert L.PFAC_mgpuDestroy(None) == Status.INVALID_HANDLE
+    assert L.PFAC_mgpuMatchFromHost(None, None, 0, None) == Status.INVALID_HANDLE
 
 
 def test_create_fails_loudly_without_gpu():
