@@ -476,7 +476,15 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
             }
             if (L.hfiltK == 2 || gramBits <= kHashFilterWords * 32 / 50) break;
         }
-        hotBudgetBytes -= hfiltBytes;
+        if (L.hfiltBitsSet > kHashFilterWords * 32 / 2 && filterPolicy != kFilterHashed) {
+            // saturated (e.g. dozens of 1-byte patterns, each filling 256 words): it would pass most
+            // positions to the walker; the exact 2-gram stage with its inline second stage does better
+            L.hfilt.clear();
+            L.hfiltK = 0;
+            L.hfiltBitsSet = 0;
+        } else {
+            hotBudgetBytes -= hfiltBytes;
+        }
     }
 
     // deeper transitions (source depth >= K): hash rows, hot by depth

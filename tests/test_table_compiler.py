@@ -348,3 +348,18 @@ def test_compiled_table_file_round_trip(tmp_path, golden_dir):
     with pytest.raises(PFACError) as e:
         TableCompiler(compiled_file=str(tmp_path / "missing.pfacb"))
     assert e.value.status == Status.FILE_OPEN_ERROR
+
+
+def test_saturated_hashed_filter_falls_back_to_exact_stage():
+    """Dozens of 1-byte patterns fill the hashed filter (256 words each): the compiler then keeps the
+    exact 2-gram stage; results are the brute-force ones either way."""
+    rng = np.random.default_rng(5)
+    pats = [bytes([c]) for c in range(0x30, 0x30 + 40)] + synth.patterns_snort_like(200, seed=7)
+    pats = list(dict.fromkeys(pats))
+    tc = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
+    assert tc.info()["hashed_filter"] == 0 and tc.info()["has_chk2"] == 1
+    L = tc.layout()
+    text = rng.integers(0, 256, size=4000, dtype=np.uint8)
+    want = brute_force_match(pats, text)
+    got = np.array([emulate_layout_walk(L, len(pats), text, i) for i in range(text.size)], dtype=np.int32)
+    assert np.array_equal(got, want) and (want > 0).mean() > 0.1
