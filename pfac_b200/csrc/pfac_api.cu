@@ -955,9 +955,11 @@ PFAC_status_t PFAC_reduceInplaceOnDevice(PFAC_handle_t handle, char* d_in, size_
     return PFAC_matchFromDeviceReduce(handle, d_in, size, d_id, d_pos, h_num);
 }
 
-// reference PFAC.cpp:1010-1128.  Chunked: H2D of chunk c+1 overlaps the fused match+compaction
-// of chunk c; only 8 bytes per match come back.  Positions are global (chunk offset added on
-// the device), lists are appended in chunk order, so the result is ascending in position.
+// Host buffers, reduced result (reference PFAC.cpp:1010-1128).  Chunked: the host copy of chunk
+// c+2 into pinned staging (pageable input only) and the H2D of chunk c+1 overlap the fused
+// match+compaction of chunk c; only 8 bytes per match come back.  Positions are global (chunk
+// offset added on the device), lists are appended in chunk order, so the result is ascending in
+// position.
 // host shard, reduced: appends (id, position) for owned positions; position = pos_base + local.
 // h_pos is int* (pos64 == false) or long long* (pos64 == true).
 static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, size_t n_owned, size_t n_total,
@@ -1034,9 +1036,7 @@ static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, siz
     return PFAC_STATUS_SUCCESS;
 }
 
-// reference PFAC.cpp:1010-1128.  Chunked: H2D of chunk c+1 overlaps the fused match+compaction
-// of chunk c; only 8 bytes per match come back.  Positions are global (chunk offset added on
-// the device), lists are appended in chunk order, so the result is ascending in position.
+// reference PFAC.cpp:1010-1128: same NULL checks; the work is hostReduceShard above
 PFAC_status_t PFAC_matchFromHostReduce(PFAC_handle_t handle, char* h_in, size_t size, int* h_id, int* h_pos,
                                        int* h_num) {
     if (!handle) return PFAC_STATUS_INVALID_HANDLE;
