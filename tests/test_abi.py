@@ -131,3 +131,25 @@ def test_host_copy_pool_is_exact_and_thread_safe():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert all(np.array_equal(d, x) for d, x in zip(dsts, srcs))
+
+
+def test_headers_are_plain_c_and_the_example_links(tmp_path):
+    """The boundary is a C ABI: include/PFAC.h + PFAC_ext.h compile as C89/C99 and as C++, and a C caller
+    links against libpfac.so with nothing but -lpfac (reference PFAC/test/Makefile:23)."""
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    src = tmp_path / "caller.c"
+    src.write_text('#include "PFAC.h"\n#include "PFAC_ext.h"\n#include <stdio.h>\n'
+                   "int main(void) {\n"
+                   "    PFAC_tableInfo_t info; (void)info;\n"
+                   "    if (PFAC_destroy(0) != PFAC_STATUS_INVALID_HANDLE) return 1;\n"
+                   '    printf("%s\\n", PFAC_getErrorString(PFAC_STATUS_INVALID_HANDLE));\n'
+                   "    return 0;\n}\n")
+    for cc, std in (("/usr/bin/gcc", "-std=c89"), ("/usr/bin/gcc", "-std=c99"), ("/usr/bin/g++", "-std=c++11")):
+        extra = ["-x", "c++"] if cc.endswith("g++") else []
+        subprocess.run([cc, std, "-Wall", "-Werror", "-fsyntax-only", "-I", inc] + extra + [str(src)], check=True)
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(library_path())
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", inc, str(src), "-L", libdir, "-lpfac",
+                    "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("PFAC_STATUS_INVALID_HANDLE")
