@@ -130,8 +130,8 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
  * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
 PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);
 
-/* ---- compiled-table files: parse, sort, number and lay out a large dictionary once (20,000
- * patterns: ~0.5 s), later processes read the result back.  Versioned and checksummed; a file that
+/* ---- compiled-table files: parse, sort, number and lay out a large dictionary once, later
+ * processes read the result back (20,000 patterns: 0.13 s to load, 0.15 s to compile).  Versioned and checksummed; a file that
  * is not recognised gives PFAC_STATUS_INVALID_PARAMETER (compile from the pattern file instead), a
  * missing one PFAC_STATUS_FILE_OPEN_ERROR.  PFAC_loadCompiledPatterns leaves the handle exactly as
  * PFAC_readPatternFromFile on the original pattern file would (same IDs, same dump, same results);

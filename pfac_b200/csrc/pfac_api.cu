@@ -405,8 +405,18 @@ PFAC_status_t uploadTables(PFAC_handle_t h) {
 }
 
 PFAC_status_t bindTable(PFAC_handle_t h) {
-    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, filterPolicy());
-    pfac::compileLayout(h->machine, hotBudget(h, true), h->layoutReduce, filterPolicy());
+    // the two layouts are independent functions of the (read-only) automaton: compile them side by side
+    const int policy = filterPolicy();
+    const size_t budgetReduce = hotBudget(h, true);
+    auto reduceSide = [&] { pfac::compileLayout(h->machine, budgetReduce, h->layoutReduce, policy); };
+    std::thread other;
+    try {
+        other = std::thread(reduceSide);
+    } catch (...) {  // no thread to be had: one after the other
+    }
+    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, policy);
+    if (other.joinable()) other.join();
+    else reduceSide();
     return uploadTables(h);
 }
 
