@@ -363,3 +363,46 @@ def test_saturated_hashed_filter_falls_back_to_exact_stage():
     want = brute_force_match(pats, text)
     got = np.array([emulate_layout_walk(L, len(pats), text, i) for i in range(text.size)], dtype=np.int32)
     assert np.array_equal(got, want) and (want > 0).mean() > 0.1
+
+
+def test_parser_fuzz_against_the_oracle(tmp_path):
+    """Random pattern-file images over {a, b, c, CR, NUL, 0xFF, LF}: blank lines, missing trailing
+    newline, duplicates, prefixes.  Whenever the image is valid for the reference (no pattern after
+    a blank line) the dump -- state numbering, edge order, pattern IDs and lengths -- and the
+    matches equal the oracle's (and the brute-force semantics when no pattern occurs twice);
+    otherwise INVALID_PARAMETER (the reference aborts on an assert)."""
+    rng = np.random.default_rng(2024)
+    sym = np.frombuffer(b"abc\r\x00\xff\n\n", dtype=np.uint8)        # LF twice: plenty of short lines
+    checked = rejected = 0
+    for trial in range(300):
+        image = sym[rng.integers(0, sym.size, size=int(rng.integers(0, 40)))].tobytes()
+        lines = image.split(b"\n")[:-1]                              # complete lines only
+        first_blank = next((i for i, l in enumerate(lines) if not l), None)
+        invalid = first_blank is not None and any(lines[first_blank:])
+        if invalid:
+            with pytest.raises(PFACError) as e:
+                TableCompiler(image=image)
+            assert e.value.status == Status.INVALID_PARAMETER, image
+            rejected += 1
+            continue
+        tc = TableCompiler(image=image)
+        pats = [l for l in lines if l]
+        assert tc.info()["num_patterns"] == len(pats), image
+        if not pats:
+            continue
+        o = Oracle(image=image)
+        a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+        o.dump(str(a))
+        tc.dump(str(b))
+        assert a.read_bytes() == b.read_bytes(), image
+        text = sym[rng.integers(0, sym.size - 2, size=200)].copy()
+        L = tc.layout()
+        got = np.array([emulate_layout_walk(L, len(pats), text, i) for i in range(text.size)], dtype=np.int32)
+        assert np.array_equal(got, o.match(text)), image
+        if len(set(pats)) == len(pats):
+            assert np.array_equal(got, brute_force_match(pats, text)), image
+        # (with duplicates the reference's construction -- first edge for building, last edge for
+        # matching -- makes the later copy win AND hides patterns that extend the duplicated one;
+        # the oracle and the layout reproduce that, the brute-force restatement does not)
+        checked += 1
+    assert checked > 100 and rejected > 30
