@@ -154,3 +154,33 @@ def test_against_reference_build_random(tmp_path, seed):
     o.dump(str(tmp_path / "o.txt"))
     r.dump(str(tmp_path / "r.txt"))
     assert (tmp_path / "o.txt").read_bytes() == (tmp_path / "r.txt").read_bytes()
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_parser_fuzz_against_reference_build(tmp_path):
+    """Random small pattern files over {a, b, c, CR, NUL, 0xFF, LF} (missing trailing newline, trailing
+    blank lines, prefixes; no pattern after a blank line -- the reference aborts there -- and no
+    duplicates -- its std::sort order is unspecified for them): table, dump and matches of the
+    restatement equal the reference build's."""
+    rng = np.random.default_rng(77)
+    sym = np.frombuffer(b"abc\r\x00\xff\n\n", dtype=np.uint8)
+    done = 0
+    for trial in range(400):
+        image = sym[rng.integers(0, sym.size, size=int(rng.integers(1, 40)))].tobytes()
+        lines = image.split(b"\n")[:-1]
+        first_blank = next((i for i, l in enumerate(lines) if not l), None)
+        pats = [l for l in lines if l]
+        if (first_blank is not None and any(lines[first_blank:])) or not pats or len(set(pats)) != len(pats):
+            continue
+        pfile = tmp_path / ("f%d.txt" % trial)
+        pfile.write_bytes(image)
+        o, r = Oracle(str(pfile)), RefOracle(str(pfile))
+        assert (o.num_patterns, o.num_states, o.max_pattern_len) == (r.num_patterns, r.num_states, r.max_pattern_len)
+        assert np.array_equal(o.dense_table(), r.dense_table()), image
+        text = sym[rng.integers(0, sym.size - 2, size=300)].copy()
+        assert np.array_equal(o.match(text), r.match(text, omp=False)), image
+        o.dump(str(tmp_path / "o.txt"))
+        r.dump(str(tmp_path / "r.txt"))
+        assert (tmp_path / "o.txt").read_bytes() == (tmp_path / "r.txt").read_bytes(), image
+        done += 1
+    assert done > 100
