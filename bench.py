@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-from pfac_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 
 GIB = 1 << 30
 METRIC = "input_GB_per_s_scanned"

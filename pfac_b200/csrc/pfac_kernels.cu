@@ -373,19 +373,20 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, uint32_t slow, int 
     return wtotal;
 }
 
-// Walk the queued survivors of one warp.  inb: staged text of the tile (stage_bytes bytes,
-// local position 0 = first byte), gin: the same bytes in global memory (for walks that run past
-// the staged halo), tile_rem: real input bytes from local position 0 to the end of the input.
-// DENSE: wres[local position] = id (non-zero only); else wres[queue slot] = id.
+// Walk one batch of queued survivors, one per lane, until the batch's longest walk ends (most
+// survivors die at their first step, so a batch is usually one trip through the loop).  inb: staged
+// text of the tile (stage_bytes bytes, local position 0 = first byte), gin: the same bytes in global
+// memory (for walks that run past the staged halo), tile_rem: real input bytes from local position 0
+// to the end of the input.  qe: this lane's queue entry (local position | kSlowFlag); returns the id
+// of the longest pattern starting there (0 = none, also for inactive lanes).
 //
 // Per survivor: root row (is c0 alone a match?) -> next2[rank of (c0,c1)] (the walk after two
 // bytes, no hashing) -> then per step either a chain (tail compared 4 bytes at a time) or a
 // hash probe (hot rows in shared memory below hot_depth, cold rows through L1/L2).
-template <bool DENSE, int CODE, bool HASHED>
-__device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char* inb, int stage_bytes,
-                                           const unsigned char* __restrict__ gin, int tile_rem,
-                                           const unsigned short* q16, int wtotal, int* wres, int lane) {
-    bool wrote = false;  // this lane produced a non-zero id
+template <int CODE, bool HASHED>
+__device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* inb, int stage_bytes,
+                                          const unsigned char* __restrict__ gin, int tile_rem, bool active,
+                                          unsigned qe, int& pl_out) {
     auto text_byte = [&](int at) -> uint32_t { return (at < stage_bytes) ? inb[at] : gin[at]; };
     // n (1..4) text bytes from `at`, little-endian, possibly with junk above byte n-1
     auto text_word = [&](int at, int n) -> uint32_t {
@@ -398,126 +399,130 @@ __device__ __forceinline__ bool walk_queue(const Tables& T, const unsigned char*
         for (int k = 0; k < nn; k++) x |= text_byte(at + k) << (8 * k);
         return x;
     };
-    // 32 survivors per batch, one per lane; the batch steps until its longest walk ends.  Most
-    // survivors die at their first step, so a batch is usually one trip through the loop.
     constexpr int K = 16 / CODE;
-    for (int base = 0; base < wtotal; base += 32) {
-        const int slot = base + lane;
-        bool active = slot < wtotal;
-        int pl = 0, d = 1, limit = 0, best = 0;
-        uint32_t v = kEmpty;
-        if (active) {
-            const unsigned qe = q16[slot];
-            pl = qe & (kSlowFlag - 1u);
-            limit = tile_rem - pl;                           // real input bytes from this position
-            if (!(qe & kSlowFlag)) {
-                // prefilter index again (survivors are few), its rank, and the direct tables
-                uint32_t idx;
-                if (CODE == 8) {
-                    idx = inb[pl] | (static_cast<uint32_t>(inb[pl + 1]) << 8);  // pl+1 is always staged
-                } else {
-                    idx = 0;
-#pragma unroll
-                    for (int i = 0; i < K; i++)
-                        idx |= (T.lut[inb[pl + i]] & ((1u << CODE) - 1u)) << (CODE * i);
-                }
-                const uint32_t word = T.pre2[idx >> 5];
-                const uint32_t rank = T.rank2[idx >> 5] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
-                // survivors of the hashed filter may hold any bytes: the exact 2-gram bit comes first
-                // (unset: c0 starts no pattern at all, or (c0,c1) leads nowhere and c0 alone is none)
-                bool viable = !HASHED || static_cast<int>(word << (idx & 31u)) < 0;
-                if (CODE == 8) {  // K-1 = 1 symbol: the root row tells whether c0 alone is a pattern
-                    const int r = viable ? T.root[idx & 0xFFu] : 0;
-                    best = (r <= T.num_final) ? r : 0;
-                } else {
-                    best = T.best2 ? static_cast<int>(T.best2[rank]) : 0;  // longest pattern inside K-1 symbols
-                }
-                // ... then the chk2 set of byte 2 (pl+2 is staged; a byte past the input can only fail
-                // a walk that needs it)
-                if (HASHED && viable && T.chk2) viable = (T.chk2[rank] >> (inb[pl + 2] & 15u)) & 1u;
-                v = (viable && limit >= K) ? T.next2[rank] : kEmpty;   // CODE 8: last byte of the input
-                d = K - 1;
+    int pl = 0, d = 1, limit = 0, best = 0;
+    uint32_t v = kEmpty;
+    if (active) {
+        pl = qe & (kSlowFlag - 1u);
+        limit = tile_rem - pl;                           // real input bytes from this position
+        if (!(qe & kSlowFlag)) {
+            // prefilter index again (survivors are few), its rank, and the direct tables
+            uint32_t idx;
+            if (CODE == 8) {
+                idx = inb[pl] | (static_cast<uint32_t>(inb[pl + 1]) << 8);  // pl+1 is always staged
             } else {
-                // generic path: from the root row, hash rows for every further step
-                const int r = T.root[inb[pl]];
-                v = (r < 0) ? kEmpty : static_cast<uint32_t>(r);
-                d = 0;
+                idx = 0;
+#pragma unroll
+                for (int i = 0; i < K; i++)
+                    idx |= (T.lut[inb[pl + i]] & ((1u << CODE) - 1u)) << (CODE * i);
             }
+            const uint32_t word = T.pre2[idx >> 5];
+            const uint32_t rank = T.rank2[idx >> 5] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
+            // survivors of the hashed filter may hold any bytes: the exact K-gram bit comes first
+            // (unset: c0 starts no pattern at all, or the K-gram leads nowhere and holds no pattern)
+            bool viable = !HASHED || static_cast<int>(word << (idx & 31u)) < 0;
+            if (CODE == 8) {  // K-1 = 1 symbol: the root row tells whether c0 alone is a pattern
+                const int r = viable ? T.root[idx & 0xFFu] : 0;
+                best = (r <= T.num_final) ? r : 0;
+            } else {
+                best = (viable && T.best2) ? static_cast<int>(T.best2[rank]) : 0;  // longest pattern inside K-1 symbols
+            }
+            // ... then the chk2 set of byte 2 (pl+2 is staged; a byte past the input can only fail
+            // a walk that needs it)
+            if (HASHED && CODE == 8 && viable && T.chk2) viable = (T.chk2[rank] >> (inb[pl + 2] & 15u)) & 1u;
+            v = (viable && limit >= K) ? T.next2[rank] : kEmpty;   // CODE 8: last byte of the input
+            d = K - 1;
+        } else {
+            // generic path: from the root row, hash rows for every further step
+            const int r = T.root[inb[pl]];
+            v = (r < 0) ? kEmpty : static_cast<uint32_t>(r);
+            d = 0;
         }
-        // v = the transition out of depth d (d bytes consumed): trap, chain or plain state
-        while (__any_sync(0xffffffffu, active)) {
-            if (active) {
-                bool done = false;
-                uint32_t s = 0;
-                if (v == kEmpty) {
-                    done = true;
-                } else if (v & kChainBit) {
-                    // the reference carries the chain's first tail byte: most false candidates end
-                    // here, before the record (usually an L2 access) is touched
-                    const bool first_ok =
-                        (d + 1 < limit) && text_byte(pl + d + 1) == ((v >> kChainByteShift) & 0xFFu);
-                    const uint4 rec = first_ok ? T.chains[v & kChainIndexMask]  // {tail offset, len, end|leaf, 4 bytes}
-                                               : make_uint4(0u, 0u, 0u, 0u);
-                    const int len = static_cast<int>(rec.y);
-                    if (!first_ok || d + 1 + len > limit) {
-                        done = true;  // no match, or cut off by the end of the input
-                    } else {
-                        const int at0 = pl + d + 1;
-                        {   // first 4 tail bytes travel inside the record: most candidates die here
-                            const uint32_t mask = (len >= 4) ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
-                            if ((text_word(at0, len) ^ rec.w) & mask) done = true;
-                        }
-                        // the rest 16 bytes per trip: four independent tail loads in flight at once
-                        const uint32_t* tw = reinterpret_cast<const uint32_t*>(T.tails + rec.x);
-                        for (int i = 4; i < len && !done; i += 16) {
-                            uint32_t t[4];
+    }
+    // v = the transition out of depth d (d bytes consumed): trap, chain or plain state
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) {
+            bool done = false;
+            uint32_t s = 0;
+            if (v == kEmpty) {
+                done = true;
+            } else if (v & kChainBit) {
+                // the reference carries the chain's first tail byte: most false candidates end
+                // here, before the record (usually an L2 access) is touched
+                const bool first_ok =
+                    (d + 1 < limit) && text_byte(pl + d + 1) == ((v >> kChainByteShift) & 0xFFu);
+                const uint4 rec = first_ok ? T.chains[v & kChainIndexMask]  // {tail offset, len, end|leaf, 4 bytes}
+                                           : make_uint4(0u, 0u, 0u, 0u);
+                const int len = static_cast<int>(rec.y);
+                if (!first_ok || d + 1 + len > limit) {
+                    done = true;  // no match, or cut off by the end of the input
+                } else {
+                    const int at0 = pl + d + 1;
+                    {   // first 4 tail bytes travel inside the record: most candidates die here
+                        const uint32_t mask = (len >= 4) ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
+                        if ((text_word(at0, len) ^ rec.w) & mask) done = true;
+                    }
+                    // the rest 16 bytes per trip: four independent tail loads in flight at once
+                    const uint32_t* tw = reinterpret_cast<const uint32_t*>(T.tails + rec.x);
+                    for (int i = 4; i < len && !done; i += 16) {
+                        uint32_t t[4];
 #pragma unroll
-                            for (int k = 0; k < 4; k++) t[k] = (i + 4 * k < len) ? tw[(i >> 2) + k] : 0u;
+                        for (int k = 0; k < 4; k++) t[k] = (i + 4 * k < len) ? tw[(i >> 2) + k] : 0u;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const int n = len - (i + 4 * k);
-                                if (n > 0 && !done) {
-                                    const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
-                                    if ((text_word(at0 + i + 4 * k, n) ^ t[k]) & mask) done = true;
-                                }
+                        for (int k = 0; k < 4; k++) {
+                            const int n = len - (i + 4 * k);
+                            if (n > 0 && !done) {
+                                const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
+                                if ((text_word(at0 + i + 4 * k, n) ^ t[k]) & mask) done = true;
                             }
                         }
-                        if (!done) {
-                            s = rec.z & ~kChainBit;
-                            d += 1 + len;
-                            if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
-                            if (rec.z & kChainBit) done = true;  // leaf: no out-edges
-                        }
                     }
+                    if (!done) {
+                        s = rec.z & ~kChainBit;
+                        d += 1 + len;
+                        if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                        if (rec.z & kChainBit) done = true;  // leaf: no out-edges
+                    }
+                }
+            } else {
+                s = v & ~kLeafPlainBit;
+                if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
+                d++;
+                if (v & kLeafPlainBit) done = true;  // no out-edges
+            }
+            if (!done) {
+                if (d >= limit) {
+                    done = true;
                 } else {
-                    s = v & ~kLeafPlainBit;
-                    if (static_cast<int>(s) <= T.num_final) best = static_cast<int>(s);
-                    d++;
-                    if (v & kLeafPlainBit) done = true;  // no out-edges
-                }
-                if (!done) {
-                    if (d >= limit) {
-                        done = true;
-                    } else {
-                        const uint32_t key = (s << 8) | text_byte(pl + d);
-                        // hot rows hold the edges of depth [K, hot_depth); the generic path's
-                        // shallow edges and everything deeper are cold
-                        v = (d >= K && d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
-                                                        : probe_cold(T.cold, T.cold_buckets, T.mul, key);
-                        if (v == kEmpty) done = true;
-                    }
-                }
-                if (done) {
-                    if (DENSE) {
-                        if (best) { wres[pl] = best; wrote = true; }
-                    } else {
-                        wres[slot] = best;
-                        wrote = wrote || (best != 0);
-                    }
-                    active = false;
+                    const uint32_t key = (s << 8) | text_byte(pl + d);
+                    // hot rows hold the edges of depth [K, hot_depth); the generic path's
+                    // shallow edges and everything deeper are cold
+                    v = (d >= K && d < T.hot_depth) ? probe_hot(T.hot, T.hot_buckets, T.mul, key)
+                                                    : probe_cold(T.cold, T.cold_buckets, T.mul, key);
+                    if (v == kEmpty) done = true;
                 }
             }
+            if (done) active = false;
         }
+    }
+    pl_out = pl;
+    return best;
+}
+
+// Dense kernel: walk the queued survivors of one warp 32 at a time; wres[local position] = id
+// (non-zero only).  Returns whether this lane produced a non-zero id.
+template <int CODE, bool HASHED>
+__device__ __forceinline__ bool walk_queue_dense(const Tables& T, const unsigned char* inb, int stage_bytes,
+                                                 const unsigned char* __restrict__ gin, int tile_rem,
+                                                 const unsigned short* q16, int wtotal, int* wres, int lane) {
+    bool wrote = false;
+    for (int base = 0; base < wtotal; base += 32) {
+        const int slot = base + lane;
+        const bool active = slot < wtotal;
+        const unsigned qe = active ? q16[slot] : 0u;
+        int pl;
+        const int best = walk_batch<CODE, HASHED>(T, inb, stage_bytes, gin, tile_rem, active, qe, pl);
+        if (best) { wres[pl] = best; wrote = true; }
     }
     return wrote;
 }
@@ -646,7 +651,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
             __syncwarp();
         }
         dirty = __any_sync(0xffffffffu,
-                           walk_queue<true, CODE, FILT >= 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
+                           walk_queue_dense<CODE, FILT >= 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
 
         int* gout = p.out + start;
         if (p.out_aligned && full) {
@@ -672,40 +677,54 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 // Reduce kernel: fused match + ordered stream compaction, one pass.
 //
 // Same warp-autonomous pipeline as the dense kernel (persistent CTA per SM, per-warp TMA input
-// stages, prefilter, queue, walk), with 31 matcher warps and one scanner warp per CTA.  Ordering:
+// stages, prefilter, queue, walk), with 31 matcher warps and one scanner warp per CTA, but a warp
+// tile is kRedSub = 3 consecutive 512-position blocks (1536 positions, one bulk copy): the walker
+// entry, the survivor scan, the tile bookkeeping and the ordering protocol below are paid once per
+// 1.5 KB of input instead of once per 512 B, and nothing here needs a per-position result slice.
+// Ordering:
 //   * "CTA tile" c = 31 consecutive warp tiles; CTA b handles c = r*G + b in round r (G = grid).
 //     The launch is cooperative, so all G CTAs are co-resident and may wait on each other.
-//   * a matcher deposits its tile's match count in a shared-memory ring slot, arrives, parks the
-//     compacted (id, position) pairs in a small FIFO and goes on matching; it writes a parked
-//     round's pairs at base + (counts of lower warps) once the scanner has posted the base, and
-//     never runs more than kLag rounds ahead of the scanner.
+//   * walker batches append their (id, position) pairs to the warp's parking ring as they finish;
+//     at the end of its tile the matcher deposits the tile's match count in a shared-memory ring
+//     slot, arrives, and goes on matching; it writes a parked round's pairs at
+//     base + (counts of lower warps) once the scanner has posted the base, and never runs more than
+//     kLag rounds ahead of the scanner.  A tile with more matches than the parking ring holds is
+//     walked again: once to count, and once more, after its base has arrived, writing directly.
 //   * the scanner publishes each round's CTA-tile aggregate as soon as all 31 counts are in
 //     (one store for the same round's later CTAs, one 64-bit atomic {1 CTA, matches} into the
 //     round word) and, independently, resolves bases in order: base(r, b) = matches of rounds < r
 //     (round words with every CTA accounted for) + aggregates of CTAs < b in round r, all read
 //     with the loads in flight at once.  No CTA publishes a prefix for the others, so rounds are
 //     not chained through a single writer.
-// shared memory: [mbarriers][root | pre2 | rank2][ring][per matcher: queue 1K | ids 2K |
-// pending 768 B | 2 input stages][next2][hot][chains][tails]
+//   * shared-memory flags (arrived / ready) are block-scope release/acquire operations; the words
+//     they guard (counts, base) are plain accesses ordered by them.
+// shared memory: [mbarriers][root | pre2 | rank2 | lut][ring][per matcher: queue 512 B | parking ids 1 KB |
+// parking positions 512 B | records 128 B | 2 input stages][hfilt][chk2][next2][hot][chains][tails]
 // =================================================================================================
 constexpr int kRedWarps = 32;                  // 31 matcher warps + 1 scanner warp
 constexpr int kRedMatchers = kRedWarps - 1;
 constexpr int kRedThreads = kRedWarps * 32;
 constexpr int kRedMaxHalo = kDenseMaxHalo;
 constexpr int kRedStages = 2;                  // input stages per matcher warp
+constexpr int kRedSub = 3;                     // 512-position blocks per warp tile
+constexpr int kRedTile = kRedSub * kWarpTile;  // 1536 start positions per warp per round
+constexpr int kQueueCap = 256;                 // survivors walked per pass; denser tiles go block by block
 constexpr int kLag = 6;                        // a matcher may run this many rounds ahead of the scanner
 // Ring slot reuse: a matcher that passed the lag wait of iteration j has written out every parked
 // record of rounds <= j-kLag, so after iteration j it holds records > j-kLag only.  Slot r is
 // rewritten by the first arrival at r+kRing, which needs ready(r+kRing-kLag), i.e. every matcher
 // finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
 constexpr int kRing = 16;                      // arrival ring slots
-constexpr int kPendCap = 128;                  // matches a warp can park while bases are computed
-constexpr int kPendRecs = 4;                   // ... spread over at most this many rounds (power of two)
+constexpr int kPendCap = 256;                  // matches a warp can park while bases are computed
+constexpr int kPendRecs = 8;                   // ... spread over at most this many rounds (power of two)
 constexpr int kPendRecBytes = kPendRecs * 16;  // {round, n, tile start (u64)} per record
 constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base | before
 constexpr int kRingBytes = kRing * kSlotBytes;
+constexpr int kRedWarpFixed = kQueueCap * 2 + kPendCap * 6 + kPendRecBytes;
 static_assert(kRing >= 2 * kLag + 1 && (kRing & (kRing - 1)) == 0, "ring size");
-static_assert((kPendCap & (kPendCap - 1)) == 0, "pending buffer is a power-of-two ring");
+static_assert((kPendCap & (kPendCap - 1)) == 0 && (kPendRecs & (kPendRecs - 1)) == 0, "parking rings are powers of two");
+static_assert(kRedSub <= 3 && kRedTile <= 2048, "survivor counts are scanned as 10-bit fields; queue entries hold 11-bit positions");
+static_assert(kQueueCap >= 8 * kPosPerThread, "a group of 8 lanes of one block must fit the queue");
 
 // per-round word: [63:40] CTAs that published, [39:0] matches of the round so far
 constexpr int kRoundShift = 40;
@@ -721,10 +740,18 @@ struct RingSlot {
 };
 static_assert(sizeof(RingSlot) == kSlotBytes, "ring slot layout");
 
-__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+// block-scope release/acquire on shared-memory flags (PTX memory model; the plain accesses to the
+// words a flag guards are ordered by it)
+__device__ __forceinline__ int ld_acquire_cta_s32(const int* p) {
     int v;
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_release_cta_s32(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_release_cta_s32(int* p, int v) {
+    asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 #ifdef PFAC_DEBUG_SPIN
 #define PFAC_SPIN_GUARD(n, what, a, b_, c)                                                          \
@@ -737,12 +764,42 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
 #define PFAC_SPIN_GUARD(n, what, a, b_, c)
 #endif
 
+// inclusive warp scan of a packed word (fields must not overflow into each other)
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// survivors of one 512-position block of a tile: prefilter + the clips for the end of the input
+// (windows reaching past it take the generic path) and for positions this shard does not own
+template <int CODE, int FILT>
+__device__ __forceinline__ uint32_t block_survivors(const Tables& T, const unsigned char* inb, int blk, int lane,
+                                                    int tile_rem, int tile_valid, uint32_t& slow) {
+    const int lb = lane * kPosPerThread;
+    uint32_t cand;
+    prefilter16<CODE, FILT>(inb + blk * kWarpTile, lb, T, cand, slow);
+    clip_windows<CODE>(tile_rem - blk * kWarpTile, lb, cand, slow);
+    const int valid = tile_valid - blk * kWarpTile;
+    if (valid < kWarpTile) {
+        int nv = valid - lb;
+        nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
+        cand &= (1u << nv) - 1u;
+        slow &= (1u << nv) - 1u;
+    }
+    return cand;
+}
+
 template <bool POS64, int CODE, int FILT>
 __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KParams p) {
     constexpr int NSTAGE = kRedStages;
+    constexpr bool HASHED = FILT >= 2;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int stage = kWarpTile + p.halo;
-    const int per_warp = kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + kPendRecBytes + NSTAGE * stage;
+    const int stage = kRedTile + p.halo;
+    const int per_warp = kRedWarpFixed + NSTAGE * stage;
     constexpr int kBarBytes = ((kRedWarps * NSTAGE * 8 + 127) / 128) * 128;
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
     unsigned char* s_fixed = smem + kBarBytes;
@@ -785,8 +842,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             bool progress = false;
             if (pub_r < my_rounds) {
                 RingSlot* slot = &ring[pub_r & (kRing - 1)];
-                if (ld_volatile_s32(&slot->arrived) == kRedMatchers) {
-                    __threadfence_block();
+                if (ld_acquire_cta_s32(&slot->arrived) == kRedMatchers) {
                     int c = (lane < kRedMatchers) ? slot->counts[lane] : 0;
 #pragma unroll
                     for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
@@ -794,7 +850,9 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                         const unsigned long long ttotal = static_cast<unsigned long long>(c);
                         st_relaxed_u64(g_desc + pub_r * G + b, kStatusAgg | ttotal);
                         atomicAdd(g_rs + pub_r, (1ull << kRoundShift) | ttotal);
-                        slot->arrived = 0;  // matchers are at most kLag rounds ahead
+                        // the next arrivals at this slot (round pub_r + kRing) follow a `ready`
+                        // released after this store (ring slot reuse, above)
+                        slot->arrived = 0;
                     }
                     __syncwarp();
                     pub_r++;
@@ -828,8 +886,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                     if (lane == 0) {
                         RingSlot* slot = &ring[r & (kRing - 1)];
                         slot->base = prev + part;
-                        __threadfence_block();
-                        slot->ready = static_cast<int>(r + 1);
+                        st_release_cta_s32(&slot->ready, static_cast<int>(r + 1));
                         run_total = prev;
                     }
                     __syncwarp();
@@ -853,18 +910,16 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     // ============================ matcher warps ==========================================================
     unsigned char* mine = s_warp + warp * per_warp;
     unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
-    int* wids = reinterpret_cast<int*>(mine + kWarpTile * 2);
-    int* pend_id = reinterpret_cast<int*>(mine + kWarpTile * 6);                                      // ring of kPendCap
-    unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kWarpTile * 6 + kPendCap * 4);  // ring of kPendCap
+    int* pend_id = reinterpret_cast<int*>(mine + kQueueCap * 2);                                   // ring of kPendCap
+    unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kQueueCap * 2 + kPendCap * 4);  // ring of kPendCap
     struct PendRec { uint32_t round; int n; unsigned long long start; };
-    PendRec* recs = reinterpret_cast<PendRec*>(mine + kWarpTile * 6 + kPendCap * 6);  // ring of kPendRecs
-    unsigned char* s_in = mine + kWarpTile * 6 + kPendCap * 6 + kPendRecBytes;
-    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kWarpTile);
+    PendRec* recs = reinterpret_cast<PendRec*>(mine + kQueueCap * 2 + kPendCap * 6);  // ring of kPendRecs
+    unsigned char* s_in = mine + kRedWarpFixed;
 
     auto issue_load = [&](uint32_t t, int st) {
         if (t < p.bulk_tiles) {
             mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
-            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kWarpTile, static_cast<uint32_t>(stage),
+            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kRedTile, static_cast<uint32_t>(stage),
                         &bar[st]);
         }
     };
@@ -875,44 +930,44 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     }
 
     auto round_ready = [&](uint32_t r) -> bool {
-        return ld_volatile_s32(&ring[r & (kRing - 1)].ready) >= static_cast<int>(r + 1);
+        return ld_acquire_cta_s32(&ring[r & (kRing - 1)].ready) >= static_cast<int>(r + 1);
     };
     auto wait_ready = [&](uint32_t r, const char* what) {
         unsigned long long spins = 0;
         (void)spins; (void)what;
         while (!round_ready(r)) {
             __nanosleep(100);
-            PFAC_SPIN_GUARD(spins, what, r, ld_volatile_s32(&ring[r & (kRing - 1)].ready), 0)
+            PFAC_SPIN_GUARD(spins, what, r, ld_acquire_cta_s32(&ring[r & (kRing - 1)].ready), 0)
         }
     };
-    // write n of one warp's matches of round r (entries [first, first+n) of a ring of `cap` slots)
-    auto write_out = [&](uint32_t r, const int* ids, const unsigned short* pos, int first, int n, int cap_mask,
-                         size_t tile_start) {
+    // where this warp's matches of round r (base posted) start in the output
+    auto out_offset = [&](uint32_t r) -> unsigned long long {
         RingSlot* slot = &ring[r & (kRing - 1)];
-        __threadfence_block();
         int lower = (static_cast<uint32_t>(lane) < warp) ? slot->counts[lane] : 0;
 #pragma unroll
         for (int dd = 16; dd > 0; dd >>= 1) lower += __shfl_xor_sync(0xffffffffu, lower, dd);
-        const unsigned long long off = slot->base + static_cast<unsigned long long>(lower);
-        const long long gbase = p.pos_base + static_cast<long long>(tile_start);
-        for (int i = lane; i < n; i += 32) {
-            const int e = (first + i) & cap_mask;
-            p.out_id[off + i] = ids[e];
-            const long long gpos = gbase + pos[e];
-            if (POS64) reinterpret_cast<long long*>(p.out_pos)[off + i] = gpos;
-            else reinterpret_cast<int*>(p.out_pos)[off + i] = static_cast<int>(gpos);
-        }
+        return slot->base + static_cast<unsigned long long>(lower);
+    };
+    auto store_pair = [&](unsigned long long at, int id, long long gpos) {
+        p.out_id[at] = id;
+        if (POS64) reinterpret_cast<long long*>(p.out_pos)[at] = gpos;
+        else reinterpret_cast<int*>(p.out_pos)[at] = static_cast<int>(gpos);
     };
 
-    // pending FIFO: matches of up to kPendRecs earlier rounds wait here for their CTA tile's base
-    int nrec = 0;         // records in use
+    // parking ring: matches of up to kPendRecs rounds wait here for their CTA tile's base
+    int nrec = 0;         // records in use (closed rounds)
     int rec_head = 0;     // ring index of the oldest record
     int pend_head = 0;    // ring index of the oldest parked entry
-    int pend_used = 0;
+    int pend_used = 0;    // entries in use, those of the round being matched included
     auto oldest_round = [&]() -> uint32_t { return recs[rec_head].round; };
     auto pop_oldest = [&]() {  // caller made sure its round is ready
         const PendRec rec = recs[rec_head];
-        write_out(rec.round, pend_id, pend_pos, pend_head, rec.n, kPendCap - 1, static_cast<size_t>(rec.start));
+        const unsigned long long off = out_offset(rec.round);
+        const long long gbase = p.pos_base + static_cast<long long>(rec.start);
+        for (int i = lane; i < rec.n; i += 32) {
+            const int e = (pend_head + i) & (kPendCap - 1);
+            store_pair(off + i, pend_id[e], gbase + pend_pos[e]);
+        }
         __syncwarp();
         pend_head = (pend_head + rec.n) & (kPendCap - 1);
         pend_used -= rec.n;
@@ -924,97 +979,181 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     int st = 0;
     for (uint32_t r = 0; r < my_rounds; ++r) {
         const uint32_t tile = tile_of(r);
-        const size_t start = static_cast<size_t>(tile) * kWarpTile;
+        const size_t start = static_cast<size_t>(tile) * kRedTile;
         int nmatch = 0;
+        const unsigned char* inb = s_in + st * stage;
+        int tile_rem = 0, tile_valid = 0;
+
+        // One walk over the tile's survivors.  MODE 0: park the pairs (returns -1 when the ring cannot
+        // hold the tile), 1: count only, 2: write at out[off...] directly.  Returns the match count.
+        auto tile_pass = [&](const int mode, const unsigned long long off) -> int {
+            int n = 0;
+            const long long gbase = p.pos_base + static_cast<long long>(start);
+            // walks q16[0, total) 32 at a time; false = parking overflow
+            auto walk_range = [&](int total) -> bool {
+                for (int base = 0; base < total; base += 32) {
+                    const int slot = base + lane;
+                    const bool active = slot < total;
+                    const unsigned qe = active ? q16[slot] : 0u;
+                    int pl;
+                    const int best = walk_batch<CODE, HASHED>(T, inb, stage, p.in + start, tile_rem, active, qe, pl);
+                    const unsigned m = __ballot_sync(0xffffffffu, best != 0);
+                    if (m == 0) continue;
+                    const int c = __popc(m);
+                    const int mine_at = __popc(m & lt_mask);
+                    if (mode == 0) {
+                        while (pend_used + c > kPendCap) {
+                            if (nrec == 0) return false;     // this tile alone fills the ring
+                            wait_ready(oldest_round(), "room");
+                            pop_oldest();
+                        }
+                        if (best) {
+                            const int e = (pend_head + pend_used + mine_at) & (kPendCap - 1);
+                            pend_id[e] = best;
+                            pend_pos[e] = static_cast<unsigned short>(pl);
+                        }
+                        pend_used += c;
+                    } else if (mode == 2) {
+                        if (best) store_pair(off + n + mine_at, best, gbase + pl);
+                    }
+                    n += c;
+                }
+                return true;
+            };
+            uint32_t cand[kRedSub], slow[kRedSub];
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < kRedSub; j++) {
+                cand[j] = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, slow[j]);
+                packed |= static_cast<uint32_t>(__popc(cand[j] | slow[j])) << (10 * j);
+            }
+            const uint32_t incl = warp_incl_scan(packed, lane);
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int wtotal = static_cast<int>((tot & 1023u) + ((tot >> 10) & 1023u) + (tot >> 20));
+            if (wtotal == 0) return 0;
+            bool ok = true;
+            if (wtotal <= kQueueCap) {
+                const uint32_t excl = incl - packed;
+                int qbase = 0;
+#pragma unroll
+                for (int j = 0; j < kRedSub; j++) {
+                    uint32_t all = cand[j] | slow[j];
+                    int o = qbase + static_cast<int>((excl >> (10 * j)) & 1023u);
+                    const int lb = j * kWarpTile + lane * kPosPerThread;
+                    while (all) {
+                        const int bit = __ffs(all) - 1;
+                        all &= all - 1;
+                        q16[o++] = static_cast<unsigned short>((lb + bit) | (((slow[j] >> bit) & 1u) ? kSlowFlag : 0u));
+                    }
+                    qbase += static_cast<int>((tot >> (10 * j)) & 1023u);
+                }
+                __syncwarp();
+                ok = walk_range(wtotal);
+                __syncwarp();
+            } else {
+                // dense survivors (adversarial text): 8 lanes of one block at a time (<= 128 survivors)
+                for (int j = 0; j < kRedSub && ok; j++) {
+                    uint32_t sl;
+                    const uint32_t cd = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, sl);
+                    const uint32_t cnt = static_cast<uint32_t>(__popc(cd | sl));
+                    const uint32_t inc = warp_incl_scan(cnt, lane);
+                    for (int g = 0; g < 4 && ok; g++) {
+                        const uint32_t lo = g ? __shfl_sync(0xffffffffu, inc, 8 * g - 1) : 0u;
+                        const uint32_t hi = __shfl_sync(0xffffffffu, inc, 8 * g + 7);
+                        if ((lane >> 3) == g) {
+                            uint32_t all = cd | sl;
+                            int o = static_cast<int>(inc - cnt - lo);
+                            const int lb = j * kWarpTile + lane * kPosPerThread;
+                            while (all) {
+                                const int bit = __ffs(all) - 1;
+                                all &= all - 1;
+                                q16[o++] = static_cast<unsigned short>((lb + bit) | (((sl >> bit) & 1u) ? kSlowFlag : 0u));
+                            }
+                        }
+                        __syncwarp();
+                        ok = walk_range(static_cast<int>(hi - lo));
+                        __syncwarp();
+                    }
+                }
+            }
+            if (!ok) {  // un-park what this pass parked
+                pend_used -= n;
+                return -1;
+            }
+            return n;
+        };
+
         if (tile < num_tiles) {
-            unsigned char* inb = s_in + st * stage;
             if (tile < p.bulk_tiles) {
                 mbar_wait(&bar[st], (parity >> st) & 1u);
                 parity ^= 1u << st;
             } else {
+                // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
+                unsigned char* w = s_in + st * stage;
                 for (int i = lane; i < stage; i += 32) {
                     const long long g = static_cast<long long>(start) + i;
-                    inb[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
+                    w[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
                 }
                 __syncwarp();
             }
             const long long total_left = p.n_total - static_cast<long long>(start);
-            const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
-            const int lb = lane * kPosPerThread;
-            uint32_t cand, slow;
-            prefilter16<CODE, FILT>(inb, lb, T, cand, slow);
-            clip_windows<CODE>(tile_rem, lb, cand, slow);
-            if (tile >= full_tiles) {
-                const int valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
-                int nv = valid - lb;
-                nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
-                cand &= (1u << nv) - 1u;
-                slow &= (1u << nv) - 1u;
+            tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
+            const long long owned_left = p.n_owned - static_cast<long long>(start);
+            tile_valid = owned_left > kRedTile ? kRedTile : static_cast<int>(owned_left);
+        }
+
+        // pass 0 parks; a tile the ring cannot hold is counted (pass 1) and, once its base is there,
+        // written directly (pass 2).  One call site: the walker is instantiated once.
+        int mode = 0;
+        unsigned long long off = 0;
+        for (;;) {
+            const int res = (tile < num_tiles) ? tile_pass(mode, off) : 0;
+            if (mode == 2) break;
+            if (res < 0) {
+                mode = 1;
+                continue;
             }
-            const int wtotal = push_survivors(cand, slow, lb, q16, lane);
-            __syncwarp();
-            const bool any_match = __any_sync(
-                0xffffffffu, walk_queue<false, CODE, FILT >= 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wids, lane));
-            __syncwarp();
-            // in-place ordered compaction of (position, id) to the front of q16 / wids
-            for (int base = 0; any_match && base < wtotal; base += 32) {
-                const int i = base + lane;
-                const int id = (i < wtotal) ? wids[i] : 0;
-                const unsigned short pos =
-                    (i < wtotal) ? static_cast<unsigned short>(q16[i] & (kSlowFlag - 1u)) : static_cast<unsigned short>(0);
-                const unsigned m = __ballot_sync(0xffffffffu, id != 0);
-                if (id != 0) {
-                    const int o = nmatch + __popc(m & lt_mask);
-                    wids[o] = id;
-                    q16[o] = pos;
+            nmatch = res;
+
+            // ---- flow control: nobody runs more than kLag rounds ahead of the scanner, so a ring slot
+            // (round r-kRing) is never rewritten while a warp may still read it
+            if (r >= kLag) wait_ready(r - kLag, "lag");
+
+            // ---- arrive: deposit the count; the scanner warp takes it from here ---------------------
+            RingSlot* slot = &ring[r & (kRing - 1)];
+            if (lane == 0) {
+                slot->counts[warp] = nmatch;
+                red_add_release_cta_s32(&slot->arrived, 1);
+            }
+
+            // ---- write parked matches whose base has arrived; close (or write) this round's ----------
+            while (nrec > 0 && round_ready(oldest_round())) pop_oldest();
+            if (mode == 0) {
+                if (nmatch > 0) {
+                    if (nrec == kPendRecs) {
+                        wait_ready(oldest_round(), "recs");
+                        pop_oldest();
+                    }
+                    if (lane == 0) {
+                        PendRec& rec = recs[(rec_head + nrec) & (kPendRecs - 1)];
+                        rec.round = r;
+                        rec.n = nmatch;
+                        rec.start = static_cast<unsigned long long>(start);
+                    }
+                    __syncwarp();
+                    nrec++;
                 }
-                nmatch += __popc(m);
+                break;
             }
-            __syncwarp();
-            if (elect_one()) issue_load(tile_of(r + NSTAGE), st);  // this stage is consumed
-            st = (st + 1 == NSTAGE) ? 0 : st + 1;
-        }
-
-        // ---- flow control: nobody runs more than kLag rounds ahead of the scanner, so a ring slot
-        // (round r-kRing) is never rewritten while a warp may still read it
-        if (r >= kLag) wait_ready(r - kLag, "lag");
-
-        // ---- arrive: deposit the count; the scanner warp takes it from here -------------------------
-        RingSlot* slot = &ring[r & (kRing - 1)];
-        if (lane == 0) {
-            slot->counts[warp] = nmatch;
-            __threadfence_block();
-            atomicAdd(&slot->arrived, 1);
-        }
-
-        // ---- write parked matches whose base has arrived; park (or write) this round's ----------------
-        while (nrec > 0 && round_ready(oldest_round())) pop_oldest();
-        if (nmatch > kPendCap) {
             while (nrec > 0) { wait_ready(oldest_round(), "drain"); pop_oldest(); }
             wait_ready(r, "direct");
-            write_out(r, wids, q16, 0, nmatch, 0x7fffffff, start);  // too many to park
+            off = out_offset(r);
+            mode = 2;
+        }
+        if (tile < num_tiles) {
             __syncwarp();
-        } else if (nmatch > 0) {
-            while (nrec == kPendRecs || pend_used + nmatch > kPendCap) {
-                wait_ready(oldest_round(), "room");
-                pop_oldest();
-            }
-            const int tail = (pend_head + pend_used) & (kPendCap - 1);
-            for (int i = lane; i < nmatch; i += 32) {
-                const int e = (tail + i) & (kPendCap - 1);
-                pend_id[e] = wids[i];
-                pend_pos[e] = q16[i];
-            }
-            __syncwarp();
-            if (lane == 0) {
-                PendRec& rec = recs[(rec_head + nrec) & (kPendRecs - 1)];
-                rec.round = r;
-                rec.n = nmatch;
-                rec.start = static_cast<unsigned long long>(start);
-            }
-            __syncwarp();
-            nrec++;
-            pend_used += nmatch;
+            if (elect_one()) issue_load(tile_of(r + NSTAGE), st);  // every pass over this stage is done
+            st = (st + 1 == NSTAGE) ? 0 : st + 1;
         }
     }
     while (nrec > 0) {
@@ -1045,7 +1184,7 @@ size_t denseFixedBytes(int halo) {
 size_t reduceFixedBytes(int halo) {
     const size_t bar = size_t((kRedWarps * kRedStages * 8 + 127) / 128) * 128;
     return bar + kFixedTableBytes + kRingBytes +
-           size_t(kRedMatchers) * (kWarpTile * 2 + kWarpTile * 4 + kPendCap * 6 + kPendRecBytes + kRedStages * (kWarpTile + halo));
+           size_t(kRedMatchers) * (kRedWarpFixed + kRedStages * (kRedTile + halo));
 }
 
 size_t tableSmemBytes(const DeviceTable& t) {
@@ -1099,9 +1238,9 @@ size_t tableSmemBudget(int maxPatternLen, bool reduceKernel) {
     return fixed < size_t(kMaxSmem) ? size_t(kMaxSmem) - fixed : 0;
 }
 
-// per CTA tile (16 KB of input): one aggregate word; per round: a running total and a counter
+// per CTA tile (46.5 KB of input): one aggregate word; per round: a running total and a counter
 size_t reduceWorkspaceWords(size_t n_owned) {
-    const size_t tiles = (n_owned + kWarpTile - 1) / kWarpTile;
+    const size_t tiles = (n_owned + kRedTile - 1) / kRedTile;
     const size_t ctiles = (tiles + kRedMatchers - 1) / kRedMatchers;
     return 3 * ctiles + 8;
 }
@@ -1141,7 +1280,7 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
         default: return cudaErrorInvalidValue;
     }
     if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
     long long grid = cfg.numSMs;
@@ -1157,7 +1296,7 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
                               unsigned long long* d_total, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
     const int halo = roundHalo(t.maxPatternLen, kRedMaxHalo);
-    KParams p = baseParams(t, in, n_owned, n_total, halo, kWarpTile);
+    KParams p = baseParams(t, in, n_owned, n_total, halo, kRedTile);
     if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.out_id = out_id;
     p.out_pos = out_pos;
@@ -1165,9 +1304,9 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     p.desc = desc;
     p.total = d_total;
     {
-        const long long stage = kWarpTile + halo;
+        const long long stage = kRedTile + halo;
         long long bulk = 0;
-        if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kWarpTile + 1;
+        if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kRedTile + 1;
         if (bulk > p.num_tiles) bulk = p.num_tiles;
         p.bulk_tiles = static_cast<uint32_t>(bulk);
     }
@@ -1187,7 +1326,7 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
         default: return cudaErrorInvalidValue;
     }
     if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kRedMatchers - 1) / kRedMatchers;
     long long grid = cfg.numSMs;

@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import RefOracle  # noqa: E402
-from pfac_b200 import synth   # noqa: E402
+from workloads import synth   # noqa: E402
 
 REF = "/root/reference/PFAC/test"
 

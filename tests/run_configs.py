@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-from pfac_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 from pfac_b200.sharding import shard_bounds  # noqa: E402
 
 GIB = 1 << 30

@@ -7,7 +7,7 @@ import sys
 
 import numpy as np
 
-from pfac_b200 import synth
+from workloads import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from pfac_b200 import synth
+from workloads import synth
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu

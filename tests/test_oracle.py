@@ -14,7 +14,7 @@ import pytest
 
 import oracle
 from oracle import Oracle, RefOracle, reduce_dense
-from pfac_b200 import synth
+from workloads import synth
 
 G1_DENSE = [1, 3, 4, 0, 4, 0, 2, 0, 0, 0]          # reference README.md:114-120 (+ trailing '\n')
 G2_POS, G2_IDS = [0, 1, 2, 4, 6], [1, 3, 4, 4, 2]  # user guide r1.2 p.29

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import Oracle
-from pfac_b200 import synth
+from workloads import synth
 from pfac_b200.sharding import exclusive_offsets, shard_bounds
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -91,7 +91,7 @@ import os, sys
 sys.path.insert(0, %(root)r)
 import numpy as np, torch, torch.distributed as dist
 from oracle import Oracle
-from pfac_b200 import synth
+from workloads import synth
 from pfac_b200.sharding import shard_bounds, allgather_count_offsets, place_runs
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)

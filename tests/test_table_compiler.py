@@ -13,7 +13,8 @@ import numpy as np
 import pytest
 
 from oracle import Oracle
-from pfac_b200 import PFACError, Status, TableCompiler, synth
+from pfac_b200 import PFACError, Status, TableCompiler
+from workloads import synth
 from tests.helpers import brute_force_match, emulate_layout_walk, read_patterns
 
 

@@ -25,7 +25,8 @@ def main():
     ap.add_argument("--skip-pinned", action="store_true")
     args = ap.parse_args()
     import torch
-    from pfac_b200 import PFAC, synth
+    from pfac_b200 import PFAC
+    from workloads import synth
 
     n = args.mib << 20
     pats = synth.patterns_c2(1000)

@@ -1,6 +1,7 @@
 import sys, time, numpy as np, torch
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
-from pfac_b200 import PFAC, synth
+from pfac_b200 import PFAC
+from workloads import synth
 import bench
 pats = synth.patterns_c2(1000)
 pfile = synth.write_pattern_file('/tmp/c2.pat', pats)
