@@ -62,6 +62,44 @@ PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char
                                                 long long *d_pos,
                                                 unsigned long long *h_num_matched);
 
+/* ---- cross-GPU count exchange, in the library and on the device.
+ * The only inter-GPU step of the path is an exclusive scan of the per-GPU match counts.  A PFAC_comm
+ * holds one small device block per rank (mailbox + this rank's region of a global list) that every
+ * rank maps: through CUDA IPC between processes (one process per GPU: PFAC_commCreate, exchange the
+ * 64-byte handles with whatever the host side has -- MPI, torch.distributed, a file --, then
+ * PFAC_commConnect), or through peer access inside one process (PFAC_commCreateLocal).  The reduce
+ * kernel then publishes its count into every rank's mailbox and scans the counts itself, over NVLink
+ * peer memory: no NCCL call and no host round trip sit between the match and the global offsets.
+ * (The reference has no counterpart: test/omp_PFAC.cpp:351-394 stitches on the host; its only
+ * inter-GPU mechanism is peer access to caller buffers, test/UVA.cpp:137, which this library also
+ * accepts for every d_* argument.)  At most 16 ranks (one NVLink domain). */
+typedef struct PFAC_comm *PFAC_comm_t;
+#define PFAC_COMM_HANDLE_BYTES 64
+PFAC_status_t PFAC_commCreate(PFAC_comm_t *comm, int rank, int world, size_t list_capacity,
+                              void *ipc_handle_out /* PFAC_COMM_HANDLE_BYTES, may be NULL when world == 1 */);
+PFAC_status_t PFAC_commConnect(PFAC_comm_t comm, const void *all_handles /* world x PFAC_COMM_HANDLE_BYTES, rank order */);
+PFAC_status_t PFAC_commCreateLocal(PFAC_comm_t *comms /* [num_devices] */, const int *devices, int num_devices,
+                                   size_t list_capacity);
+PFAC_status_t PFAC_commDestroy(PFAC_comm_t comm);
+/* this rank's region of the global list (device pointers) */
+PFAC_status_t PFAC_commGlobalList(PFAC_comm_t comm, int **d_ids, long long **d_pos, size_t *capacity);
+/* host copy of entries [first, first + n) of this rank's list region (synchronous cudaMemcpy) */
+PFAC_status_t PFAC_commReadGlobalList(PFAC_comm_t comm, size_t first, size_t n, int *h_ids, long long *h_pos);
+
+/* PFAC_matchShardFromDeviceReduce64 + the scan, one kernel; collective over the comm.  d_scan (device,
+ * 3 words; NULL = kept inside the comm) = {this rank's offset into the global list, total matches, this
+ * rank's count}.  h_scan == NULL: asynchronous on the handle's stream, nothing is read back; else the
+ * call synchronises once and returns the same three words. */
+PFAC_status_t PFAC_matchShardFromDeviceReduce64Global(PFAC_handle_t handle, PFAC_comm_t comm,
+                                                      const char *d_inputString, size_t n_owned, size_t n_total,
+                                                      long long pos_base, int *d_matched_result, long long *d_pos,
+                                                      unsigned long long *d_scan, unsigned long long *h_scan);
+/* optional second step, collective: every rank stores its run into rank dst_rank's list region at its
+ * scanned offset (P2P stores over NVLink; count and offset are read from d_scan on the device), dst_rank
+ * waits on the device until all runs have landed.  The list is then PFAC_commGlobalList(dst)[0, total). */
+PFAC_status_t PFAC_commGatherRuns(PFAC_handle_t handle, PFAC_comm_t comm, int dst_rank, const int *d_matched_result,
+                                  const long long *d_pos, const unsigned long long *d_scan, int synchronize);
+
 /* ---- table compiler, host only (no CUDA calls): pattern image -> reference-numbered trie
  * -> B200 device layout (dense root row, 2-byte prefilter bitmap, hot/cold bucketed hash
  * rows, path-compressed chains). */
@@ -186,6 +224,12 @@ PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char *h_inputString
  * PFAC_lastHostTransfer: bytes the handle's last PFAC_matchFromHost* call moved over PCIe.
  */
 PFAC_status_t PFAC_lastHostTransfer(PFAC_handle_t handle, size_t *h2d_bytes, size_t *d2h_bytes);
+/* The host pipelines keep their buffers in the handle between calls: per handle 2 x (chunk + halo) of
+ * input, 2 x 4 x chunk of ids / dense results, 2 x 4 x chunk of positions (8 x chunk once a 64-bit
+ * host call was made) on the device -- about 770 MiB at the default 32 MiB chunk
+ * (PFAC_B200_HOST_CHUNK_MB) -- plus 2 x chunk/2 of pinned (id, position) lists and, for pageable
+ * buffers, the pinned staging.  PFAC_destroy frees them; this call frees them earlier. */
+PFAC_status_t PFAC_releaseHostBuffers(PFAC_handle_t handle);
 
 PFAC_status_t PFAC_hostCopy(void *dst, const void *src, size_t bytes);
 /* the same pool's zero fill (streaming stores); PFAC_matchFromHost uses it for the sparse result path */

@@ -5,5 +5,5 @@ reference's public interface; include/PFAC_ext.h the additive 64-bit / shard / t
 entry points).  This Python package is a thin ctypes mirror of that ABI for tests, bench.py
 and tooling; it contains no matching logic and no CPU fallback.
 """
-from .api import (PFAC, PFACError, PFACMultiGPU, TableCompiler, Status, Platform, PerfMode, TextureMode,  # noqa: F401
+from .api import (PFAC, PFACComm, PFACError, PFACMultiGPU, TableCompiler, Status, Platform, PerfMode, TextureMode,  # noqa: F401
                   load_library, library_path)

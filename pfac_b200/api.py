@@ -136,6 +136,15 @@ def load_library():
         "PFAC_hostCopy": [vp, vp, sz],
         "PFAC_hostZero": [vp, sz],
         "PFAC_lastHostTransfer": [vp, ctypes.POINTER(sz), ctypes.POINTER(sz)],
+        "PFAC_releaseHostBuffers": [vp],
+        "PFAC_commCreate": [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, sz, vp],
+        "PFAC_commConnect": [vp, vp],
+        "PFAC_commCreateLocal": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int, sz],
+        "PFAC_commDestroy": [vp],
+        "PFAC_commGlobalList": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(sz)],
+        "PFAC_commReadGlobalList": [vp, sz, sz, vp, vp],
+        "PFAC_matchShardFromDeviceReduce64Global": [vp, vp, vp, sz, sz, ctypes.c_longlong, vp, vp, vp, vp],
+        "PFAC_commGatherRuns": [vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int],
         "PFAC_mgpuCreate": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int],
         "PFAC_mgpuDestroy": [vp],
         "PFAC_mgpuReadPatternFromFile": [vp, cp],
@@ -295,6 +304,22 @@ class PFAC:
                "PFAC_matchShardFromDeviceReduce64")
         return n.value
 
+    def matchShardFromDeviceReduce64Global(self, comm, d_input, n_owned, n_total, pos_base, d_result, d_pos64,
+                                           d_scan=None, sync=True):
+        """Shard reduce + the cross-GPU exclusive scan of the counts in one kernel (collective over
+        `comm`).  sync=True returns (offset, total, count); sync=False leaves them in d_scan (device)."""
+        h = (ctypes.c_ulonglong * 3)()
+        _check(self._L.PFAC_matchShardFromDeviceReduce64Global(
+            self._h, comm._c, _ptr(d_input), n_owned, n_total, pos_base, _ptr(d_result), _ptr(d_pos64),
+            _ptr(d_scan), ctypes.cast(h, ctypes.c_void_p) if sync else None),
+            "PFAC_matchShardFromDeviceReduce64Global")
+        return (int(h[0]), int(h[1]), int(h[2])) if sync else None
+
+    def gatherRuns(self, comm, dst_rank, d_result, d_pos64, d_scan=None, sync=True):
+        """Collective: every rank's run goes to rank dst_rank's global list at its scanned offset."""
+        _check(self._L.PFAC_commGatherRuns(self._h, comm._c, dst_rank, _ptr(d_result), _ptr(d_pos64), _ptr(d_scan),
+                                           1 if sync else 0), "PFAC_commGatherRuns")
+
     # -- matching: host buffers --------------------------------------------------------------------
     def matchFromHost(self, h_input, h_result=None, size=None):
         """h_input: bytes / uint8 ndarray / pinned CPU tensor.  Returns the int32 result array."""
@@ -304,6 +329,9 @@ class PFAC:
             h_result = np.zeros(n, dtype=np.int32)
         _check(self._L.PFAC_matchFromHost(self._h, _ptr(src), n, _ptr(h_result)), "PFAC_matchFromHost")
         return h_result
+
+    def releaseHostBuffers(self):
+        _check(self._L.PFAC_releaseHostBuffers(self._h), "PFAC_releaseHostBuffers")
 
     def lastHostTransfer(self):
         """(h2d_bytes, d2h_bytes) the last matchFromHost* call of this handle moved over PCIe."""
@@ -323,6 +351,85 @@ class PFAC:
         _check(self._L.PFAC_matchFromHostReduce(self._h, _ptr(src), n, _ptr(h_result), _ptr(h_pos),
                                                 ctypes.byref(m)), "PFAC_matchFromHostReduce")
         return h_result[:m.value], h_pos[:m.value]
+
+
+class PFACComm:
+    """PFAC_comm: the per-rank block (mailbox + global-list region) behind the in-kernel count scan.
+
+    One process per GPU:  c = PFACComm(rank, world, list_capacity); handles = all-gather of c.handle
+    (64 bytes per rank, any transport); c.connect(handles).  `from_torch` does the exchange with
+    torch.distributed.  One process, several GPUs: PFACComm.local(devices, list_capacity)."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, rank, world, list_capacity=0, _c=None):
+        self._L = load_library()
+        self.rank, self.world = rank, world
+        self.handle = (ctypes.c_ubyte * self.HANDLE_BYTES)()
+        if _c is not None:
+            self._c = _c
+            return
+        c = ctypes.c_void_p()
+        _check(self._L.PFAC_commCreate(ctypes.byref(c), rank, world, list_capacity,
+                                       ctypes.cast(self.handle, ctypes.c_void_p)), "PFAC_commCreate")
+        self._c = c
+        if world == 1:
+            self.connect(bytes(self.handle))
+
+    def connect(self, all_handles):
+        buf = bytes(all_handles)
+        if len(buf) != self.world * self.HANDLE_BYTES:
+            raise ValueError("expected %d handle bytes" % (self.world * self.HANDLE_BYTES))
+        _check(self._L.PFAC_commConnect(self._c, buf), "PFAC_commConnect")
+
+    @classmethod
+    def from_torch(cls, list_capacity=0, device=None, group=None):
+        """Create + exchange the IPC handles with torch.distributed (NCCL all-gather of 64 bytes per rank)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        c = cls(rank, world, list_capacity)
+        if world > 1:
+            mine = torch.frombuffer(bytearray(bytes(c.handle)), dtype=torch.uint8).to(device)
+            allh = torch.empty(world * cls.HANDLE_BYTES, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            c.connect(allh.cpu().numpy().tobytes())
+        return c
+
+    @classmethod
+    def local(cls, devices, list_capacity=0):
+        L = load_library()
+        n = len(devices)
+        arr = (ctypes.c_void_p * n)()
+        devs = (ctypes.c_int * n)(*devices)
+        _check(L.PFAC_commCreateLocal(arr, devs, n, list_capacity), "PFAC_commCreateLocal")
+        return [cls(i, n, list_capacity, _c=ctypes.c_void_p(arr[i])) for i in range(n)]
+
+    def global_list(self):
+        """(ids address, positions address, capacity) of this rank's list region (device memory)."""
+        a, b, cap = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self._L.PFAC_commGlobalList(self._c, ctypes.byref(a), ctypes.byref(b), ctypes.byref(cap)),
+               "PFAC_commGlobalList")
+        return a.value, b.value, cap.value
+
+    def read_global_list(self, n, first=0):
+        """Host copy of entries [first, first+n) of this rank's list region: (ids int32, positions int64)."""
+        ids = np.empty(n, dtype=np.int32)
+        pos = np.empty(n, dtype=np.int64)
+        _check(self._L.PFAC_commReadGlobalList(self._c, first, n, ids.ctypes.data, pos.ctypes.data),
+               "PFAC_commReadGlobalList")
+        return ids, pos
+
+    def destroy(self):
+        if getattr(self, "_c", None):
+            self._L.PFAC_commDestroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 class PFACMultiGPU:

@@ -244,7 +244,7 @@ struct HostPipe {  // cached buffers of the matchFromHost* pipelines
     int* d_pos[2] = {nullptr, nullptr};  // reduce positions
     size_t chunk = 0;                    // owned bytes per chunk
     size_t inCap = 0;
-    bool hasPos = false;
+    size_t posBytes = 0;                 // bytes per position in d_pos (0: none, 4: int, 8: long long)
     // pinned staging for pageable user buffers (allocated on first use)
     unsigned char* s_in[3] = {nullptr, nullptr, nullptr};
     int* s_out[2] = {nullptr, nullptr};
@@ -280,12 +280,40 @@ struct PFAC_context {
     std::mutex mu;      // guards the reduce workspace (several host threads may share a handle)
     unsigned long long* d_ws = nullptr;
     size_t wsWords = 0;
+    unsigned long long* d_park = nullptr;  // reduce kernel: per-warp spill rings
     unsigned long long* d_total = nullptr;
     unsigned long long* h_total = nullptr;  // pinned
     HostPipe pipe;
 };
 
+// Cross-GPU state of one rank (PFAC_ext.h "count exchange"): one device block = mailbox (4 KB: two
+// parities x 16 count words, two parities x 16 "placed" words, a ticket) followed by this rank's
+// region of the global (id, position) list; every rank maps every rank's block (CUDA IPC between
+// processes, peer access inside one process).
+struct PFAC_comm {
+    int rank = 0, world = 1, device = 0;
+    unsigned epoch = 0;        // count exchanges issued so far (all ranks call in the same order)
+    unsigned placeEpoch = 0;   // run placements issued so far
+    unsigned char* block = nullptr;
+    size_t blockBytes = 0;
+    size_t listCap = 0;        // entries of the list region
+    unsigned char* peer[pfac::kKernelCommMaxRanks] = {};
+    bool ipcOpened[pfac::kKernelCommMaxRanks] = {};
+    unsigned long long* d_scan = nullptr;   // 4 words, used when the caller passes no d_scan
+    unsigned long long* h_scan = nullptr;   // pinned, 4 words
+};
+
 namespace {
+
+constexpr size_t kCommMailboxBytes = 4096;
+constexpr int kCommPlacedWord = 2 * pfac::kKernelCommMaxRanks;   // u64 index of placed[0][0]
+constexpr int kCommTicketWord = 4 * pfac::kKernelCommMaxRanks;
+
+size_t commIdsBytes(size_t cap) { return ((cap * sizeof(int) + 255) / 256) * 256; }
+int* commListIds(unsigned char* block) { return reinterpret_cast<int*>(block + kCommMailboxBytes); }
+long long* commListPos(unsigned char* block, size_t cap) {
+    return reinterpret_cast<long long*>(block + kCommMailboxBytes + commIdsBytes(cap));
+}
 
 void freeDeviceTable(PFAC_handle_t h) {
     for (void* p : h->d_arrays) cudaFree(p);
@@ -405,23 +433,42 @@ PFAC_status_t uploadTables(PFAC_handle_t h) {
 }
 
 PFAC_status_t bindTable(PFAC_handle_t h) {
-    // the two layouts are independent functions of the (read-only) automaton: compile them side by side
+    // the two layouts are independent functions of the (read-only) automaton: compile them side by side.
+    // Large dictionaries allocate by the number of states: an allocation failure must come back as
+    // PFAC_STATUS_ALLOC_FAILED (as the reference does), not unwind through the C ABI or a std::thread.
     const int policy = filterPolicy();
     const size_t budgetReduce = hotBudget(h, true);
-    auto reduceSide = [&] { pfac::compileLayout(h->machine, budgetReduce, h->layoutReduce, policy); };
+    std::atomic<bool> failed{false};
+    auto reduceSide = [&] {
+        try {
+            pfac::compileLayout(h->machine, budgetReduce, h->layoutReduce, policy);
+        } catch (...) {
+            failed = true;
+        }
+    };
     std::thread other;
     try {
         other = std::thread(reduceSide);
     } catch (...) {  // no thread to be had: one after the other
     }
-    pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, policy);
+    try {
+        pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, policy);
+    } catch (...) {
+        failed = true;
+    }
     if (other.joinable()) other.join();
     else reduceSide();
+    if (failed) return PFAC_STATUS_ALLOC_FAILED;
     return uploadTables(h);
 }
 
 PFAC_status_t loadImage(PFAC_handle_t h, const char* image, size_t size) {
-    int st = pfac::buildMachine(image, size, h->machine);
+    int st;
+    try {
+        st = pfac::buildMachine(image, size, h->machine);
+    } catch (...) {
+        st = PFAC_STATUS_ALLOC_FAILED;
+    }
     if (st != PFAC_STATUS_SUCCESS) { freePatterns(h); return PFAC_status_t(st); }
     h->patternsReady = true;
     PFAC_status_t bs = bindTable(h);
@@ -453,8 +500,12 @@ PFAC_status_t cudaToStatus(cudaError_t e) {
 PFAC_status_t ensureReduceWorkspace(PFAC_handle_t h, size_t words) {
     if (!h->d_total) {
         if (cudaMalloc(reinterpret_cast<void**>(&h->d_total), 16) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
-        if (cudaMallocHost(reinterpret_cast<void**>(&h->h_total), 16) != cudaSuccess) return PFAC_STATUS_ALLOC_FAILED;
+        if (cudaMallocHost(reinterpret_cast<void**>(&h->h_total), 128) != cudaSuccess) return PFAC_STATUS_ALLOC_FAILED;
+        memset(h->h_total, 0, 128);   // [0]: count read-back, [8..15]: watchdog report of the reduce kernel
     }
+    if (!h->d_park &&
+        cudaMalloc(reinterpret_cast<void**>(&h->d_park), pfac::reduceParkWords(h->launch) * 8) != cudaSuccess)
+        return PFAC_STATUS_CUDA_ALLOC_FAILED;
     if (words > h->wsWords) {
         cudaFree(h->d_ws);
         h->d_ws = nullptr;
@@ -466,45 +517,62 @@ PFAC_status_t ensureReduceWorkspace(PFAC_handle_t h, size_t words) {
     return PFAC_STATUS_SUCCESS;
 }
 
-// one fused match+compaction over a device shard; synchronous (returns the count)
-PFAC_status_t reduceShard(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
-                          long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
-                          unsigned long long* count) {
-    std::lock_guard<std::mutex> lock(h->mu);
+// enqueue one fused match+compaction over a device shard on `stream` (workspace reset + kernel); the
+// count lands in h->d_total.  Caller holds h->mu.  comm != nullptr: the cross-GPU count exchange and
+// scan run inside the same kernel.
+PFAC_status_t reduceShardEnqueue(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
+                                 long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
+                                 const pfac::CommLaunch* comm) {
     const size_t words = pfac::reduceWorkspaceWords(n_owned);
     PFAC_status_t st = ensureReduceWorkspace(h, words);
     if (st != PFAC_STATUS_SUCCESS) return st;
     if (cudaMemsetAsync(h->d_ws, 0, words * 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     if (cudaMemsetAsync(h->d_total, 0, 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
-    cudaError_t e = pfac::launchMatchReduce(h->tableReduce, h->launch, d_in, n_owned, n_total, pos_base, d_id,
-                                            d_pos, pos64, h->d_ws, h->d_total, stream);
-    if (e != cudaSuccess) return cudaToStatus(e);
+    return cudaToStatus(pfac::launchMatchReduce(h->tableReduce, h->launch, d_in, n_owned, n_total, pos_base, d_id,
+                                                d_pos, pos64, h->d_ws, h->d_park, h->d_total, stream, comm, h->h_total + 8));
+}
+
+// one fused match+compaction over a device shard; synchronous (returns the count)
+PFAC_status_t reduceShard(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
+                          long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
+                          unsigned long long* count) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    PFAC_status_t st = reduceShardEnqueue(h, d_in, n_owned, n_total, pos_base, d_id, d_pos, pos64, stream, nullptr);
+    if (st != PFAC_STATUS_SUCCESS) return st;
     if (cudaMemcpyAsync(h->h_total, h->d_total, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) {
+        const unsigned long long* d = h->h_total + 8;
+        if (d[0])   // the kernel's watchdog fired: say where (pfac_kernels.cu, PFAC_SPIN_GUARD sites)
+            fprintf(stderr, "libpfac: reduce kernel wait watchdog: site %llu block %llu thread %llu values %lld %lld %lld\n",
+                    d[1], d[2] >> 32, d[2] & 0xFFFFFFFFull, (long long)d[3], (long long)d[4], (long long)d[5]);
+        return PFAC_STATUS_INTERNAL_ERROR;
+    }
     *count = *h->h_total;
     return PFAC_STATUS_SUCCESS;
 }
 
 // host pipeline buffers; caller holds h->pipeMu
-PFAC_status_t ensurePipe(PFAC_handle_t h, bool needPos) {
+PFAC_status_t ensurePipe(PFAC_handle_t h, size_t posBytes) {
     HostPipe& p = h->pipe;
     size_t chunk = envBytes("PFAC_B200_HOST_CHUNK_MB", 32, size_t(1) << 20);
     chunk = std::min(std::max(chunk, size_t(1) << 16), size_t(1) << 30);  // 64 KB .. 1 GiB (int positions per chunk)
     const size_t halo = size_t(h->machine.maxPatternLen > 1 ? h->machine.maxPatternLen - 1 : 0);
     const size_t inCap = ((chunk + halo + 255) / 256) * 256;
-    if (p.chunk == chunk && p.inCap >= inCap && (!needPos || p.hasPos)) return PFAC_STATUS_SUCCESS;
+    if (p.chunk == chunk && p.inCap >= inCap && p.posBytes >= posBytes) return PFAC_STATUS_SUCCESS;
+    posBytes = std::max(posBytes, p.posBytes);   // a handle that served a 64-bit call keeps the wider buffer
     freePipe(p);
     for (int i = 0; i < 2; i++) {
         if (cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_in[i]), inCap) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
-        // positions may be 64-bit (multi-GPU / shard forms)
-        if (needPos && cudaMalloc(reinterpret_cast<void**>(&p.d_pos[i]), chunk * 8) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
+        // sized by the position width the caller asked for (4 B for the legacy int calls, 8 B for the
+        // 64-bit shard forms); the dense fallback of the sparse path reuses it as int scratch
+        if (posBytes && cudaMalloc(reinterpret_cast<void**>(&p.d_pos[i]), chunk * posBytes) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
     }
     p.chunk = chunk;
     p.inCap = inCap;
-    p.hasPos = needPos;
+    p.posBytes = posBytes;
     return PFAC_STATUS_SUCCESS;
 }
 
@@ -568,6 +636,7 @@ PFAC_status_t PFAC_destroy(PFAC_handle_t handle) {
     freePatterns(handle);
     freePipe(handle->pipe);
     cudaFree(handle->d_ws);
+    cudaFree(handle->d_park);
     cudaFree(handle->d_total);
     if (handle->h_total) cudaFreeHost(handle->h_total);
     delete handle;
@@ -602,7 +671,7 @@ PFAC_status_t PFAC_setPerfMode(PFAC_handle_t handle, PFAC_perfMode_t mode) {
         std::lock_guard<std::mutex> lock(handle->mu);
         cudaDeviceSynchronize();  // no kernel may still be reading the old table
         PFAC_status_t st = bindTable(handle);
-        if (st != PFAC_STATUS_SUCCESS) { freeDeviceTable(handle); return st; }
+        if (st != PFAC_STATUS_SUCCESS) { freePatterns(handle); return st; }  // no tables: patterns are not ready
     }
     return PFAC_STATUS_SUCCESS;
 }
@@ -683,7 +752,12 @@ PFAC_status_t PFAC_readPatternFromArrays(PFAC_handle_t handle, const char* const
         freePatterns(handle);
     }
     handle->patternFile[0] = 0;
-    int st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, handle->machine);
+    int st;
+    try {
+        st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, handle->machine);
+    } catch (...) {
+        st = PFAC_STATUS_ALLOC_FAILED;
+    }
     if (st != PFAC_STATUS_SUCCESS) { freePatterns(handle); return PFAC_status_t(st); }
     handle->patternsReady = true;
     PFAC_status_t bs = bindTable(handle);
@@ -738,7 +812,7 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
                                      int* h_out) {
     std::lock_guard<std::mutex> lock(handle->pipeMu);
     {
-        PFAC_status_t st = ensurePipe(handle, true);
+        PFAC_status_t st = ensurePipe(handle, sizeof(int));
         if (st != PFAC_STATUS_SUCCESS) return st;
     }
     HostPipe& p = handle->pipe;
@@ -851,7 +925,7 @@ static PFAC_status_t hostDenseShard(PFAC_handle_t handle, const char* h_in, size
                                     int* h_out) {
     if (sparseHostResult()) return hostDenseSparse(handle, h_in, n_owned, n_total, h_out);
     std::lock_guard<std::mutex> lock(handle->pipeMu);
-    PFAC_status_t st = ensurePipe(handle, false);
+    PFAC_status_t st = ensurePipe(handle, 0);
     if (st != PFAC_STATUS_SUCCESS) return st;
     HostPipe& p = handle->pipe;
     const bool stIn = stagingEnabled() && isPageable(h_in);
@@ -977,7 +1051,7 @@ static PFAC_status_t hostReduceShard(PFAC_handle_t handle, const char* h_in, siz
                                      unsigned long long* h_num) {
     std::lock_guard<std::mutex> lock(handle->pipeMu);
     {
-        PFAC_status_t st = ensurePipe(handle, true);
+        PFAC_status_t st = ensurePipe(handle, pos64 ? sizeof(long long) : sizeof(int));
         if (st != PFAC_STATUS_SUCCESS) return st;
     }
     HostPipe& p = handle->pipe;
@@ -1084,6 +1158,199 @@ PFAC_status_t PFAC_memoryUsage(PFAC_handle_t handle) {
     return PFAC_STATUS_SUCCESS;
 }
 
+// ---- cross-GPU count exchange + global list (PFAC_ext.h) -------------------------------------------
+// The path's only inter-GPU step: an exclusive scan of the per-GPU match counts.
+// It runs on the device, inside the reduce kernel, over NVLink peer memory: no NCCL call, no host
+// round trip.  The reference's only inter-GPU mechanism is peer access to caller buffers
+// (reference test/UVA.cpp:137); its multi-GPU program stitches results on the host
+// (test/omp_PFAC.cpp:351-394).
+static PFAC_status_t commAlloc(PFAC_comm* c, size_t list_capacity) {
+    c->listCap = list_capacity;
+    c->blockBytes = kCommMailboxBytes + commIdsBytes(list_capacity) + list_capacity * sizeof(long long) + 256;
+    if (cudaMalloc(reinterpret_cast<void**>(&c->block), c->blockBytes) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
+    if (cudaMemset(c->block, 0, kCommMailboxBytes) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    if (cudaMalloc(reinterpret_cast<void**>(&c->d_scan), 32) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
+    if (cudaMallocHost(reinterpret_cast<void**>(&c->h_scan), 32) != cudaSuccess) return PFAC_STATUS_ALLOC_FAILED;
+    if (cudaDeviceSynchronize() != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    c->peer[c->rank] = c->block;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_commCreate(PFAC_comm_t* comm, int rank, int world, size_t list_capacity, void* ipc_handle_out) {
+    if (!comm) return PFAC_STATUS_INVALID_PARAMETER;
+    *comm = nullptr;
+    if (world < 1 || world > pfac::kKernelCommMaxRanks || rank < 0 || rank >= world) return PFAC_STATUS_INVALID_PARAMETER;
+    if (world > 1 && !ipc_handle_out) return PFAC_STATUS_INVALID_PARAMETER;
+    PFAC_comm* c = new (std::nothrow) PFAC_comm();
+    if (!c) return PFAC_STATUS_ALLOC_FAILED;
+    c->rank = rank;
+    c->world = world;
+    cudaError_t e = cudaGetDevice(&c->device);
+    if (e != cudaSuccess) { delete c; return PFAC_status_t(e); }
+    PFAC_status_t st = commAlloc(c, list_capacity);
+    if (st == PFAC_STATUS_SUCCESS && ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == PFAC_COMM_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t hd;
+        e = cudaIpcGetMemHandle(&hd, c->block);
+        if (e != cudaSuccess) st = PFAC_status_t(e);
+        else memcpy(ipc_handle_out, &hd, sizeof(hd));
+    }
+    if (st != PFAC_STATUS_SUCCESS) { PFAC_commDestroy(c); return st; }
+    *comm = c;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_commConnect(PFAC_comm_t comm, const void* all_handles) {
+    if (!comm) return PFAC_STATUS_INVALID_HANDLE;
+    if (comm->world > 1 && !all_handles) return PFAC_STATUS_INVALID_PARAMETER;
+    for (int r = 0; r < comm->world; r++) {
+        if (r == comm->rank || comm->peer[r]) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, static_cast<const char*>(all_handles) + size_t(r) * sizeof(hd), sizeof(hd));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return PFAC_status_t(e);
+        comm->peer[r] = static_cast<unsigned char*>(ptr);
+        comm->ipcOpened[r] = true;
+    }
+    return PFAC_STATUS_SUCCESS;
+}
+
+// one process driving several GPUs: blocks are mapped through peer access instead of IPC
+PFAC_status_t PFAC_commCreateLocal(PFAC_comm_t* comms, const int* devices, int num_devices, size_t list_capacity) {
+    if (!comms || !devices || num_devices < 1 || num_devices > pfac::kKernelCommMaxRanks) return PFAC_STATUS_INVALID_PARAMETER;
+    int saved = 0;
+    cudaGetDevice(&saved);
+    for (int i = 0; i < num_devices; i++) comms[i] = nullptr;
+    PFAC_status_t st = PFAC_STATUS_SUCCESS;
+    for (int i = 0; i < num_devices && st == PFAC_STATUS_SUCCESS; i++) {
+        cudaError_t e = cudaSetDevice(devices[i]);
+        if (e != cudaSuccess) { st = PFAC_status_t(e); break; }
+        PFAC_comm* c = new (std::nothrow) PFAC_comm();
+        if (!c) { st = PFAC_STATUS_ALLOC_FAILED; break; }
+        comms[i] = c;
+        c->rank = i;
+        c->world = num_devices;
+        c->device = devices[i];
+        st = commAlloc(c, list_capacity);
+        for (int j = 0; j < num_devices && st == PFAC_STATUS_SUCCESS; j++) {
+            if (devices[j] == devices[i]) continue;
+            e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) st = PFAC_status_t(e);
+        }
+    }
+    for (int i = 0; i < num_devices && st == PFAC_STATUS_SUCCESS; i++)
+        for (int j = 0; j < num_devices; j++) comms[i]->peer[j] = comms[j]->block;
+    cudaSetDevice(saved);
+    if (st != PFAC_STATUS_SUCCESS)
+        for (int i = 0; i < num_devices; i++) { if (comms[i]) PFAC_commDestroy(comms[i]); comms[i] = nullptr; }
+    return st;
+}
+
+PFAC_status_t PFAC_commDestroy(PFAC_comm_t comm) {
+    if (!comm) return PFAC_STATUS_INVALID_HANDLE;
+    int saved = 0;
+    cudaGetDevice(&saved);
+    cudaSetDevice(comm->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < comm->world; r++)
+        if (comm->ipcOpened[r]) cudaIpcCloseMemHandle(comm->peer[r]);
+    cudaFree(comm->block);
+    cudaFree(comm->d_scan);
+    if (comm->h_scan) cudaFreeHost(comm->h_scan);
+    cudaSetDevice(saved);
+    delete comm;
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_commGlobalList(PFAC_comm_t comm, int** d_ids, long long** d_pos, size_t* capacity) {
+    if (!comm) return PFAC_STATUS_INVALID_HANDLE;
+    if (d_ids) *d_ids = commListIds(comm->block);
+    if (d_pos) *d_pos = commListPos(comm->block, comm->listCap);
+    if (capacity) *capacity = comm->listCap;
+    return PFAC_STATUS_SUCCESS;
+}
+
+// host copy of entries [first, first + n) of this rank's list region (synchronous)
+PFAC_status_t PFAC_commReadGlobalList(PFAC_comm_t comm, size_t first, size_t n, int* h_ids, long long* h_pos) {
+    if (!comm) return PFAC_STATUS_INVALID_HANDLE;
+    if (first + n > comm->listCap || (n && (!h_ids || !h_pos))) return PFAC_STATUS_INVALID_PARAMETER;
+    if (n == 0) return PFAC_STATUS_SUCCESS;
+    int saved = 0;
+    cudaGetDevice(&saved);
+    cudaSetDevice(comm->device);
+    cudaError_t e = cudaMemcpy(h_ids, commListIds(comm->block) + first, n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h_pos, commListPos(comm->block, comm->listCap) + first, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaSetDevice(saved);
+    return cudaToStatus(e);
+}
+
+// PFAC_matchShardFromDeviceReduce64 + the exclusive scan of the ranks' counts, one kernel.  Collective:
+// every rank of the comm calls it, in the same order.  d_scan (device, 3 words, may be NULL) receives
+// {this rank's offset into the global list, total matches, this rank's count}.  h_scan == NULL: nothing
+// is read back and the call does not synchronise (the scan stays on the device for the kernels that
+// follow on the handle's stream); else one stream synchronisation and the same three words on the host.
+PFAC_status_t PFAC_matchShardFromDeviceReduce64Global(PFAC_handle_t handle, PFAC_comm_t comm, const char* d_in,
+                                                      size_t n_owned, size_t n_total, long long pos_base, int* d_id,
+                                                      long long* d_pos, unsigned long long* d_scan,
+                                                      unsigned long long* h_scan) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!comm) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (n_total < n_owned) return PFAC_STATUS_INVALID_PARAMETER;
+    if (n_owned && (!d_in || !d_pos || !d_id)) return PFAC_STATUS_INVALID_PARAMETER;
+    if (comm->device != handle->device) return PFAC_STATUS_INVALID_PARAMETER;
+    for (int r = 0; r < comm->world; r++) if (!comm->peer[r]) return PFAC_STATUS_INVALID_PARAMETER;  // not connected
+    std::lock_guard<std::mutex> lock(handle->mu);
+    pfac::CommLaunch cl;
+    for (int r = 0; r < comm->world; r++) cl.peer[r] = reinterpret_cast<unsigned long long*>(comm->peer[r]);
+    cl.scan = d_scan ? d_scan : comm->d_scan;
+    cl.world = comm->world;
+    cl.rank = comm->rank;
+    cl.epoch = ++comm->epoch;
+    PFAC_status_t st = reduceShardEnqueue(handle, reinterpret_cast<const unsigned char*>(d_in), n_owned, n_total, pos_base,
+                                          d_id, d_pos, true, handle->stream, &cl);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    if (h_scan) {
+        if (cudaMemcpyAsync(comm->h_scan, cl.scan, 24, cudaMemcpyDeviceToHost, handle->stream) != cudaSuccess)
+            return PFAC_STATUS_INTERNAL_ERROR;
+        if (cudaStreamSynchronize(handle->stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        h_scan[0] = comm->h_scan[0];
+        h_scan[1] = comm->h_scan[1];
+        h_scan[2] = comm->h_scan[2];
+    }
+    return PFAC_STATUS_SUCCESS;
+}
+
+// Optional second step: one global list on rank dst_rank.  Collective.  Every rank copies its run
+// d_id / d_pos [0, count) to the list region of dst_rank's comm block at its scanned offset (count and
+// offset are read from d_scan on the device) with stores to peer memory, then raises its "placed"
+// word there; dst_rank waits on the device until all ranks have.  Enqueued on the handle's stream;
+// synchronize != 0 waits for the stream.  The list is PFAC_commGlobalList of dst_rank, [0, total).
+PFAC_status_t PFAC_commGatherRuns(PFAC_handle_t handle, PFAC_comm_t comm, int dst_rank, const int* d_id,
+                                  const long long* d_pos, const unsigned long long* d_scan, int synchronize) {
+    if (!handle || !comm) return PFAC_STATUS_INVALID_HANDLE;
+    if (dst_rank < 0 || dst_rank >= comm->world || !d_id || !d_pos) return PFAC_STATUS_INVALID_PARAMETER;
+    if (comm->device != handle->device) return PFAC_STATUS_INVALID_PARAMETER;
+    for (int r = 0; r < comm->world; r++) if (!comm->peer[r]) return PFAC_STATUS_INVALID_PARAMETER;
+    const unsigned ep = ++comm->placeEpoch;
+    const int par = int(ep & 1u) * pfac::kKernelCommMaxRanks;
+    unsigned char* dst = comm->peer[dst_rank];
+    unsigned long long* dstWords = reinterpret_cast<unsigned long long*>(dst);
+    unsigned long long* ownWords = reinterpret_cast<unsigned long long*>(comm->block);
+    cudaError_t e = pfac::launchPlaceRun(d_id, d_pos, d_scan ? d_scan : comm->d_scan, commListIds(dst),
+                                         commListPos(dst, comm->listCap), comm->listCap,
+                                         dstWords + kCommPlacedWord + par + comm->rank, ownWords + kCommTicketWord, ep,
+                                         handle->launch.numSMs, handle->stream);
+    if (e == cudaSuccess && comm->rank == dst_rank)
+        e = pfac::launchWaitPlaced(ownWords + kCommPlacedWord + par, comm->world, ep, handle->stream);
+    if (e != cudaSuccess) return cudaToStatus(e);
+    if (synchronize && cudaStreamSynchronize(handle->stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    return PFAC_STATUS_SUCCESS;
+}
+
 // ---- multi-GPU driver (one process, one host thread per GPU) ---------------------------------------
 // What reference test/omp_PFAC.cpp:257-394 builds by hand: one handle per GPU, contiguous shards with
 // a tail halo of maxPatternLen-1 bytes, results stitched on the host.  For the reduced form the
@@ -1093,6 +1360,13 @@ struct PFAC_mgpu {
     std::vector<int> devices;
     std::vector<PFAC_handle_t> handles;
 };
+
+static bool mgpuReady(const PFAC_mgpu* mg) {  // a load that failed on one GPU leaves that handle without tables
+    if (mg->handles.empty()) return false;
+    for (PFAC_handle_t h : mg->handles)
+        if (!h->patternsReady) return false;
+    return true;
+}
 
 static void shardBounds(size_t size, int world, int rank, size_t halo, size_t* start, size_t* owned, size_t* total) {
     size_t per = (size + size_t(world) - 1) / size_t(world);
@@ -1147,6 +1421,13 @@ PFAC_status_t PFAC_mgpuReadPatternFromFile(PFAC_mgpu_t mg, char* filename) {
         cudaSetDevice(mg->devices[i]);
         st = PFAC_readPatternFromFile(mg->handles[i], filename);
     }
+    if (st != PFAC_STATUS_SUCCESS)   // all or nothing: no GPU keeps a dictionary the others lack
+        for (size_t i = 0; i < mg->handles.size(); i++) {
+            cudaSetDevice(mg->devices[i]);
+            std::lock_guard<std::mutex> lock(mg->handles[i]->mu);
+            if (mg->handles[i]->patternsReady) cudaDeviceSynchronize();
+            freePatterns(mg->handles[i]);
+        }
     cudaSetDevice(saved);
     return st;
 }
@@ -1154,7 +1435,7 @@ PFAC_status_t PFAC_mgpuReadPatternFromFile(PFAC_mgpu_t mg, char* filename) {
 PFAC_status_t PFAC_mgpuMatchFromHost(PFAC_mgpu_t mg, char* h_in, size_t size, int* h_out) {
     if (!mg) return PFAC_STATUS_INVALID_HANDLE;
     if (!h_in || !h_out) return PFAC_STATUS_INVALID_PARAMETER;
-    if (mg->handles.empty() || !mg->handles[0]->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!mgpuReady(mg)) return PFAC_STATUS_PATTERNS_NOT_READY;
     if (size == 0) return PFAC_STATUS_SUCCESS;
     const int G = int(mg->handles.size());
     const size_t halo = size_t(std::max(mg->handles[0]->machine.maxPatternLen - 1, 0));
@@ -1180,7 +1461,7 @@ PFAC_status_t PFAC_mgpuMatchFromHostReduce64(PFAC_mgpu_t mg, char* h_in, size_t 
                                              unsigned long long* h_num) {
     if (!mg) return PFAC_STATUS_INVALID_HANDLE;
     if (!h_in || !h_id || !h_pos || !h_num) return PFAC_STATUS_INVALID_PARAMETER;
-    if (mg->handles.empty() || !mg->handles[0]->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!mgpuReady(mg)) return PFAC_STATUS_PATTERNS_NOT_READY;
     *h_num = 0;
     if (size == 0) return PFAC_STATUS_SUCCESS;
     const int G = int(mg->handles.size());
@@ -1259,11 +1540,18 @@ PFAC_status_t PFAC_tableCompile(const char* image, size_t size, size_t hot_budge
     *table = nullptr;
     PFAC_table* t = new (std::nothrow) PFAC_table();
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
-    int st = pfac::buildMachine(image, size, t->machine);
+    int st;
+    try {
+        st = pfac::buildMachine(image, size, t->machine);
+        if (st == PFAC_STATUS_SUCCESS) {
+            t->budget = hot_budget_bytes;
+            t->policy = filterPolicy();
+            pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, t->policy);
+        }
+    } catch (...) {
+        st = PFAC_STATUS_ALLOC_FAILED;
+    }
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
-    t->budget = hot_budget_bytes;
-    t->policy = filterPolicy();
-    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, t->policy);
     *table = t;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1274,11 +1562,18 @@ PFAC_status_t PFAC_tableCompileArrays(const char* const* patterns, const size_t*
     *table = nullptr;
     PFAC_table* t = new (std::nothrow) PFAC_table();
     if (!t) return PFAC_STATUS_ALLOC_FAILED;
-    int st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, t->machine);
+    int st;
+    try {
+        st = pfac::buildMachineFromArrays(patterns, lengths, num_patterns, t->machine);
+        if (st == PFAC_STATUS_SUCCESS) {
+            t->budget = hot_budget_bytes;
+            t->policy = filterPolicy();
+            pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, t->policy);
+        }
+    } catch (...) {
+        st = PFAC_STATUS_ALLOC_FAILED;
+    }
     if (st != PFAC_STATUS_SUCCESS) { delete t; return PFAC_status_t(st); }
-    t->budget = hot_budget_bytes;
-    t->policy = filterPolicy();
-    pfac::compileLayout(t->machine, hot_budget_bytes, t->layout, t->policy);
     *table = t;
     return PFAC_STATUS_SUCCESS;
 }
@@ -1444,6 +1739,17 @@ PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
 PFAC_status_t PFAC_hostCopy(void* dst, const void* src, size_t bytes) {
     if (bytes && (!dst || !src)) return PFAC_STATUS_INVALID_PARAMETER;
     acquireCopyPool()->copy(dst, src, bytes, true);  // destination written with streaming stores
+    return PFAC_STATUS_SUCCESS;
+}
+
+// The matchFromHost* pipelines keep their device and pinned buffers between calls (the reference
+// allocates and frees per call, PFAC.cpp:915-961); a caller that is done with host calls can give
+// them back without destroying the handle.
+PFAC_status_t PFAC_releaseHostBuffers(PFAC_handle_t handle) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    std::lock_guard<std::mutex> lock(handle->pipeMu);
+    cudaDeviceSynchronize();
+    freePipe(handle->pipe);
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -49,6 +49,10 @@ constexpr int kDenseMaxHalo = 64;              // staged halo cap; walks that ru
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
+constexpr int kCommMaxRanks = kKernelCommMaxRanks;
+constexpr int kCommShift = 40;                    // mailbox word: [63:40] epoch, [39:0] count
+constexpr unsigned long long kCommMask = (1ull << kCommShift) - 1;
+
 struct KParams {
     const unsigned char* in;
     long long n_owned;
@@ -59,6 +63,8 @@ struct KParams {
     void* out_pos;              // reduce
     long long pos_base;
     unsigned long long* desc;
+    unsigned long long* park;   // reduce: per-warp spill rings
+    unsigned long long* dbg;    // reduce: 8 mapped host words for the wait watchdog (may be null)
     unsigned long long* total;
     const int32_t* root;
     const uint32_t* pre2;
@@ -89,6 +95,11 @@ struct KParams {
     int halo;                   // staged halo, multiple of 16, >= 16
     int in_aligned;             // in is 16-byte aligned
     int out_aligned;            // out is 16-byte aligned
+    // cross-GPU count exchange fused into the reduce kernel (comm_world == 0: off)
+    unsigned long long* comm_peer[kCommMaxRanks];  // every rank's mailbox (peer-mapped), [comm_rank] = own
+    unsigned long long* comm_scan;                 // out: {exclusive offset, total, own count}
+    int comm_world, comm_rank;
+    unsigned comm_epoch;
 };
 
 // tables as the walker sees them (shared-memory copies where available)
@@ -132,6 +143,19 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar) {
     asm volatile(
@@ -158,6 +182,58 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// The one cross-GPU step of the path, done by one warp over NVLink peer memory: every
+// rank stores {epoch, its match count} into slot [epoch & 1][rank] of every rank's mailbox, waits
+// until its own mailbox holds the current epoch from all ranks, and takes the exclusive prefix.
+// One 8-byte word carries flag and value, so relaxed system-scope accesses suffice.  Two parities:
+// a rank can be at most one call ahead of the slowest reader of its previous word (it cannot finish
+// call e+1 before every rank has published e+1, which each does after its own wait of call e).
+__device__ __forceinline__ void comm_exchange_scan(const KParams& p, unsigned long long total, int lane) {
+    const unsigned long long ep = static_cast<unsigned long long>(p.comm_epoch & 0xFFFFFFu);
+    const int par = static_cast<int>(p.comm_epoch & 1u) * kCommMaxRanks;
+    unsigned long long c = 0;
+    if (lane < p.comm_world) {
+        st_relaxed_sys_u64(p.comm_peer[lane] + par + p.comm_rank, (ep << kCommShift) | total);
+        const unsigned long long* mine = p.comm_peer[p.comm_rank] + par + lane;
+        unsigned long long v = ld_relaxed_sys_u64(mine);
+        while ((v >> kCommShift) != ep) {
+            __nanosleep(200);
+            v = ld_relaxed_sys_u64(mine);
+        }
+        c = v & kCommMask;
+    }
+    __syncwarp();
+    unsigned long long incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const unsigned long long all = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == p.comm_rank) {
+        p.comm_scan[0] = incl - c;
+        p.comm_scan[1] = all;
+        p.comm_scan[2] = c;
+    }
 }
 
 __device__ __forceinline__ uint32_t home_bucket(uint32_t key, uint32_t mul, uint32_t nb) {
@@ -196,10 +272,14 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     int* root = reinterpret_cast<int*>(s_fixed);
     uint4* pre2 = reinterpret_cast<uint4*>(s_fixed + 1024);
     uint4* rank2 = reinterpret_cast<uint4*>(s_fixed + 1024 + 8192);
+#pragma unroll 1
     for (int i = tid; i < 256; i += nthreads) root[i] = p.root[i];
+#pragma unroll 1
     for (int i = tid; i < 8192 / 16; i += nthreads) pre2[i] = reinterpret_cast<const uint4*>(p.pre2)[i];
+#pragma unroll 1
     for (int i = tid; i < 4096 / 16; i += nthreads) rank2[i] = reinterpret_cast<const uint4*>(p.rank2)[i];
     uint4* lut = reinterpret_cast<uint4*>(s_fixed + 1024 + 8192 + 4096);
+#pragma unroll 1
     for (int i = tid; i < 256 / 16; i += nthreads) lut[i] = reinterpret_cast<const uint4*>(p.lut)[i];
     Tables t;
     t.root = root;
@@ -211,30 +291,39 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     uint4* var = reinterpret_cast<uint4*>(s_var);
     t.hfilt = nullptr;
     if (p.hfilt_bytes) {
-        for (uint32_t i = tid; i < p.hfilt_bytes / 16; i += nthreads)
+#pragma unroll 1
+    #pragma unroll 1
+    for (uint32_t i = tid; i < p.hfilt_bytes / 16; i += nthreads)
             var[i] = reinterpret_cast<const uint4*>(p.hfilt)[i];
         t.hfilt = reinterpret_cast<const uint32_t*>(var);
         var += p.hfilt_bytes / 16;
     }
     t.chk2 = nullptr;
     if (p.chk2_bytes) {
-        for (uint32_t i = tid; i < p.chk2_bytes / 16; i += nthreads)
+#pragma unroll 1
+    #pragma unroll 1
+    for (uint32_t i = tid; i < p.chk2_bytes / 16; i += nthreads)
             var[i] = reinterpret_cast<const uint4*>(p.chk2)[i];
         t.chk2 = reinterpret_cast<const unsigned short*>(var);
         var += p.chk2_bytes / 16;
     }
     if (p.next2_hot) {
-        for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
+#pragma unroll 1
+    #pragma unroll 1
+    for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
             var[i] = reinterpret_cast<const uint4*>(p.next2)[i];
         t.next2 = reinterpret_cast<const uint32_t*>(var);
         var += p.next2_bytes / 16;
         if (p.has_best2) {
-            for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
+    #pragma unroll 1
+    #pragma unroll 1
+    for (uint32_t i = tid; i < p.next2_bytes / 16; i += nthreads)
                 var[i] = reinterpret_cast<const uint4*>(p.best2)[i];
             t.best2 = reinterpret_cast<const uint32_t*>(var);
             var += p.next2_bytes / 16;
         }
     }
+#pragma unroll 1
     for (uint32_t i = tid; i < p.hot_buckets; i += nthreads) var[i] = p.hot[i];
     t.hot = var;
     var += p.hot_buckets;
@@ -243,8 +332,12 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     t.tails = p.tails;
     if (p.chains_hot) {
         uint4* st = var + p.chain_bytes / 16;
-        for (uint32_t i = tid; i < p.chain_bytes / 16; i += nthreads) var[i] = p.chains[i];
-        for (uint32_t i = tid; i < p.tail_bytes / 16; i += nthreads)
+#pragma unroll 1
+    #pragma unroll 1
+    for (uint32_t i = tid; i < p.chain_bytes / 16; i += nthreads) var[i] = p.chains[i];
+#pragma unroll 1
+    #pragma unroll 1
+    for (uint32_t i = tid; i < p.tail_bytes / 16; i += nthreads)
             st[i] = reinterpret_cast<const uint4*>(p.tails)[i];
         t.chains = var;
         t.tails = reinterpret_cast<const unsigned char*>(st);
@@ -266,15 +359,24 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
 // Bit q of `cand` = position lb+q survives the prefilter; bit q of `slow` = it needs the generic path.
 // second prefilter stage for a position whose first-stage bit is set: the valid K-gram's rank
 // selects a 16-bit set of (next byte & 15) values that can still lead somewhere
-__device__ __forceinline__ bool second_stage(const Tables& T, uint32_t idx, uint32_t word, uint32_t next_byte) {
+// what the prefilter reads of the tables (all in shared memory); passed by value to out-of-line code
+struct FilterView {
+    const uint32_t* pre2;
+    const uint32_t* hfilt;
+    const unsigned short* rank2;
+    const unsigned short* chk2;
+    const unsigned char* lut;
+};
+template <typename TT>
+__device__ __forceinline__ bool second_stage(const TT& T, uint32_t idx, uint32_t word, uint32_t next_byte) {
     const uint32_t rank = T.rank2[(idx >> 5) & 0x7FFu] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
     return (T.chk2[rank] >> (next_byte & 15u)) & 1u;
 }
 
 // FILT: 0 = exact K-gram set only, 1 = + inline second stage (chk2), 2 / 3 = hashed 4-gram filter
 // testing one / two bits (byte alphabets; pfac_table.h) whose survivors the walker re-checks exactly
-template <int CODE, int FILT>
-__device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const Tables& T, uint32_t& cand,
+template <int CODE, int FILT, typename TT>
+__device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const TT& T, uint32_t& cand,
                                             uint32_t& slow) {
     constexpr int K = 16 / CODE;
     const uint32_t* s_pre2 = T.pre2;
@@ -682,14 +784,16 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 // entry, the survivor scan, the tile bookkeeping and the ordering protocol below are paid once per
 // 1.5 KB of input instead of once per 512 B, and nothing here needs a per-position result slice.
 // Ordering:
-//   * "CTA tile" c = 31 consecutive warp tiles; CTA b handles c = r*G + b in round r (G = grid).
-//     The launch is cooperative, so all G CTAs are co-resident and may wait on each other.
-//   * walker batches append their (id, position) pairs to the warp's parking ring as they finish;
-//     at the end of its tile the matcher deposits the tile's match count in a shared-memory ring
-//     slot, arrives, and goes on matching; it writes a parked round's pairs at
-//     base + (counts of lower warps) once the scanner has posted the base, and never runs more than
-//     kLag rounds ahead of the scanner.  A tile with more matches than the parking ring holds is
-//     walked again: once to count, and once more, after its base has arrived, writing directly.
+//   * "CTA tile" c = 31 consecutive warp tiles; CTA b handles c = r*G + b in round r (G = grid);
+//     matcher warp w takes warp tile w of it.  The launch is cooperative, so all G CTAs are
+//     co-resident and may wait on each other.
+//   * walker batches append their (id, position) pairs to the warp's parking as they finish: a small
+//     ring in shared memory, and, for what does not fit there (dense matches), the warp's spill ring
+//     in global memory (L2-resident; one whole tile always fits an empty one, so no tile is ever
+//     walked twice).  At the end of its tile the matcher deposits the tile's match count in a
+//     shared-memory ring slot, arrives, and goes on matching; it writes a parked tile's pairs at
+//     base + (counts of lower warps) once the scanner has posted the round's base, and never runs
+//     more than kLag rounds ahead of the scanner.
 //   * the scanner publishes each round's CTA-tile aggregate as soon as all 31 counts are in
 //     (one store for the same round's later CTAs, one 64-bit atomic {1 CTA, matches} into the
 //     round word) and, independently, resolves bases in order: base(r, b) = matches of rounds < r
@@ -698,11 +802,16 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
 //     not chained through a single writer.
 //   * shared-memory flags (arrived / ready) are block-scope release/acquire operations; the words
 //     they guard (counts, base) are plain accesses ordered by them.
-// shared memory: [mbarriers][root | pre2 | rank2 | lut][ring][per matcher: queue 512 B | parking ids 1 KB |
-// parking positions 512 B | records 128 B | 2 input stages][hfilt][chk2][next2][hot][chains][tails]
+//   * every wait loop carries a watchdog (PFAC_SPIN_GUARD): a wait that never ends reports where it
+//     stood and traps instead of hanging the GPU.
+// (A variant in which the warps of a CTA claim tiles from a shared counter instead of owning a slot
+// was measured 8 % slower on C2 and no faster on C4: profiles/r2_history.md.)
+// shared memory: [mbarriers][root | pre2 | rank2 | lut][ring][per matcher: queue 512 B | parking ids 512 B |
+// parking positions 256 B | records 192 B | 2 input stages][hfilt][chk2][next2][hot][chains][tails]
 // =================================================================================================
 constexpr int kRedWarps = 32;                  // 31 matcher warps + 1 scanner warp
 constexpr int kRedMatchers = kRedWarps - 1;
+constexpr int kRedSlots = kRedMatchers;        // warp tiles per CTA tile
 constexpr int kRedThreads = kRedWarps * 32;
 constexpr int kRedMaxHalo = kDenseMaxHalo;
 constexpr int kRedStages = 2;                  // input stages per matcher warp
@@ -711,20 +820,24 @@ constexpr int kRedTile = kRedSub * kWarpTile;  // 1536 start positions per warp 
 constexpr int kQueueCap = 256;                 // survivors walked per pass; denser tiles go block by block
 constexpr int kLag = 6;                        // a matcher may run this many rounds ahead of the scanner
 // Ring slot reuse: a matcher that passed the lag wait of iteration j has written out every parked
-// record of rounds <= j-kLag, so after iteration j it holds records > j-kLag only.  Slot r is
-// rewritten by the first arrival at r+kRing, which needs ready(r+kRing-kLag), i.e. every matcher
-// finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
+// record of rounds <= j-kLag (bases are posted in round order, and the flush that follows the wait
+// writes out everything whose base is there), so after iteration j it holds records > j-kLag only.
+// Slot r is rewritten by the first arrival at r+kRing, which needs ready(r+kRing-kLag), i.e. every
+// matcher finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
 constexpr int kRing = 16;                      // arrival ring slots
-constexpr int kPendCap = 256;                  // matches a warp can park while bases are computed
-constexpr int kPendRecs = 8;                   // ... spread over at most this many rounds (power of two)
-constexpr int kPendRecBytes = kPendRecs * 16;  // {round, n, tile start (u64)} per record
-constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base | before
+constexpr int kPendCap = 128;                  // matches a warp can park in shared memory while bases are computed
+constexpr int kPendRecs = 8;                   // ... spread over at most this many rounds (power of two, > kLag)
+constexpr int kPendRecBytes = kPendRecs * 24;  // {round, n_smem, n_spill, tile start (u64)} per record
+constexpr int kSpillCap = 2048;                // per-warp spill ring in global memory (entries of 8 bytes)
+constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base
 constexpr int kRingBytes = kRing * kSlotBytes;
 constexpr int kRedWarpFixed = kQueueCap * 2 + kPendCap * 6 + kPendRecBytes;
 static_assert(kRing >= 2 * kLag + 1 && (kRing & (kRing - 1)) == 0, "ring size");
-static_assert((kPendCap & (kPendCap - 1)) == 0 && (kPendRecs & (kPendRecs - 1)) == 0, "parking rings are powers of two");
+static_assert((kPendCap & (kPendCap - 1)) == 0 && (kPendRecs & (kPendRecs - 1)) == 0 && kPendRecs > kLag, "parking rings");
 static_assert(kRedSub <= 3 && kRedTile <= 2048, "survivor counts are scanned as 10-bit fields; queue entries hold 11-bit positions");
 static_assert(kQueueCap >= 8 * kPosPerThread, "a group of 8 lanes of one block must fit the queue");
+static_assert(kSpillCap >= kRedTile && (kSpillCap & (kSpillCap - 1)) == 0, "one tile always fits an empty spill ring");
+static_assert((kRedWarpFixed & 15) == 0, "input stages are 16-byte aligned (bulk copies)");
 
 // per-round word: [63:40] CTAs that published, [39:0] matches of the round so far
 constexpr int kRoundShift = 40;
@@ -735,8 +848,7 @@ struct RingSlot {
     int arrived;
     int ready;                 // round+1 once base is valid
     unsigned long long base;
-    unsigned long long before; // round word before this CTA's contribution (scanner only)
-    int pad[kSlotBytes / 4 - kRedWarps - 6];
+    int pad[kSlotBytes / 4 - kRedWarps - 4];
 };
 static_assert(sizeof(RingSlot) == kSlotBytes, "ring slot layout");
 
@@ -753,16 +865,24 @@ __device__ __forceinline__ void st_release_cta_s32(int* p, int v) {
 __device__ __forceinline__ void red_add_release_cta_s32(int* p, int v) {
     asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-#ifdef PFAC_DEBUG_SPIN
-#define PFAC_SPIN_GUARD(n, what, a, b_, c)                                                          \
-    if (++(n) > (1ull << 22)) {                                                                      \
-        printf("STUCK %s blk %d warp %d lane %d : %lld %lld %lld\n", what, int(blockIdx.x),         \
-               int(threadIdx.x >> 5), int(threadIdx.x & 31), (long long)(a), (long long)(b_), (long long)(c)); \
-        __trap();                                                                                    \
+// Watchdog of every wait loop of the reduce kernel: a wait that outlasts ~2^24 polls (seconds; a healthy
+// wait is microseconds) records where it stood in the handle's mapped host words and traps, so a
+// protocol fault surfaces as an error return instead of a GPU that never comes back.
+constexpr unsigned long long kSpinLimit = 1ull << 24;
+__device__ __noinline__ void pfac_stuck(unsigned long long* dbg, int site, long long a, long long b_, long long c) {
+    if (dbg && atomicCAS(dbg, 0ull, 1ull) == 0ull) {   // first reporter only
+        dbg[1] = static_cast<unsigned long long>(site);
+        dbg[2] = (static_cast<unsigned long long>(blockIdx.x) << 32) | threadIdx.x;
+        dbg[3] = static_cast<unsigned long long>(a);
+        dbg[4] = static_cast<unsigned long long>(b_);
+        dbg[5] = static_cast<unsigned long long>(c);
+        __threadfence_system();
     }
-#else
-#define PFAC_SPIN_GUARD(n, what, a, b_, c)
-#endif
+    __nanosleep(1000000);   // let the report land before the context dies
+    __trap();
+}
+#define PFAC_SPIN_GUARD(n, dbg, site, a, b_, c) \
+    if (++(n) > kSpinLimit) pfac_stuck(dbg, site, (long long)(a), (long long)(b_), (long long)(c));
 
 // inclusive warp scan of a packed word (fields must not overflow into each other)
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -776,8 +896,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 // survivors of one 512-position block of a tile: prefilter + the clips for the end of the input
 // (windows reaching past it take the generic path) and for positions this shard does not own
-template <int CODE, int FILT>
-__device__ __forceinline__ uint32_t block_survivors(const Tables& T, const unsigned char* inb, int blk, int lane,
+template <int CODE, int FILT, typename TT>
+__device__ __forceinline__ uint32_t block_survivors(const TT& T, const unsigned char* inb, int blk, int lane,
                                                     int tile_rem, int tile_valid, uint32_t& slow) {
     const int lb = lane * kPosPerThread;
     uint32_t cand;
@@ -791,6 +911,15 @@ __device__ __forceinline__ uint32_t block_survivors(const Tables& T, const unsig
         slow &= (1u << nv) - 1u;
     }
     return cand;
+}
+// the same, out of line, for the rare tiles whose survivors are walked block by block: keeps a second
+// copy of the prefilter out of the instruction stream of the common path.  Returns cand | slow << 16.
+template <int CODE, int FILT>
+__device__ __noinline__ uint32_t block_survivors_cold(FilterView fv, const unsigned char* inb, int blk, int lane,
+                                                      int tile_rem, int tile_valid) {
+    uint32_t slow;
+    const uint32_t cand = block_survivors<CODE, FILT>(fv, inb, blk, lane, tile_rem, tile_valid, slow);
+    return cand | (slow << 16);
 }
 
 template <bool POS64, int CODE, int FILT>
@@ -818,13 +947,14 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
         for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#pragma unroll 1
     for (int i = tid; i < kRingBytes / 4; i += kRedThreads) reinterpret_cast<int*>(ring)[i] = 0;
     __syncthreads();  // the only CTA-wide barrier
 
     const uint32_t G = gridDim.x;
     const uint32_t b = blockIdx.x;
     const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
-    const uint32_t num_ctiles = (num_tiles + kRedMatchers - 1) / kRedMatchers;
+    const uint32_t num_ctiles = (num_tiles + kRedSlots - 1) / kRedSlots;
     const uint32_t num_rounds = (num_ctiles + G - 1) / G;
     // rounds this CTA takes part in: r with r*G + b < num_ctiles
     const uint32_t my_rounds = (num_ctiles > b) ? (num_ctiles - b + G - 1) / G : 0;
@@ -836,6 +966,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
         // Never blocks on one round: publishing round r (needs only this CTA's counts) is not held up
         // by resolving an earlier round (needs other CTAs' aggregates and the previous round total).
         uint32_t pub_r = 0, res_r = 0;
+        unsigned long long idle = 0;       // consecutive polls without progress (watchdog)
         unsigned long long run_total = 0;  // matches of all rounds < res_r - 1 (lane 0)
         auto round_size = [&](uint32_t r) -> uint32_t { return (r + 1 < num_rounds) ? G : (num_ctiles - r * G); };
         while (res_r < my_rounds) {
@@ -894,15 +1025,28 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                     progress = true;
                 }
             }
-            if (!progress) __nanosleep(40);
-        }
-        if (b == 0 && lane == 0) {  // CTA 0 takes part in every round: it owns the grand total
-            unsigned long long v = ld_relaxed_u64(g_rs + (num_rounds - 1));
-            while ((v >> kRoundShift) != round_size(num_rounds - 1)) {
+            if (!progress) {
                 __nanosleep(40);
-                v = ld_relaxed_u64(g_rs + (num_rounds - 1));
+                if (lane == 0) { PFAC_SPIN_GUARD(idle, p.dbg, 4, (static_cast<long long>(pub_r) << 32) | res_r, my_rounds, ring[pub_r & (kRing - 1)].arrived) }
+            } else {
+                idle = 0;
             }
-            *p.total = run_total + (v & kRoundMask);
+        }
+        if (b == 0) {  // CTA 0 takes part in every round: it owns the grand total
+            unsigned long long total = 0;
+            if (lane == 0) {
+                unsigned long long v = ld_relaxed_u64(g_rs + (num_rounds - 1));
+                unsigned long long spins = 0;
+                while ((v >> kRoundShift) != round_size(num_rounds - 1)) {
+                    __nanosleep(40);
+                    v = ld_relaxed_u64(g_rs + (num_rounds - 1));
+                    PFAC_SPIN_GUARD(spins, p.dbg, 5, num_rounds, v >> kRoundShift, v & kRoundMask)
+                }
+                total = run_total + (v & kRoundMask);
+                *p.total = total;
+            }
+            // multi-GPU: publish the count to every rank over peer memory and scan, in this kernel
+            if (p.comm_world > 0) comm_exchange_scan(p, __shfl_sync(0xffffffffu, total, 0), lane);
         }
         return;
     }
@@ -912,9 +1056,13 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
     int* pend_id = reinterpret_cast<int*>(mine + kQueueCap * 2);                                   // ring of kPendCap
     unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kQueueCap * 2 + kPendCap * 4);  // ring of kPendCap
-    struct PendRec { uint32_t round; int n; unsigned long long start; };
+    struct PendRec { uint32_t round; uint32_t n_smem, n_spill, pad; unsigned long long start; };
+    static_assert(sizeof(PendRec) == kPendRecBytes / kPendRecs, "record layout");
     PendRec* recs = reinterpret_cast<PendRec*>(mine + kQueueCap * 2 + kPendCap * 6);  // ring of kPendRecs
     unsigned char* s_in = mine + kRedWarpFixed;
+    // this warp's spill ring in global memory (L2-resident): entry = id | position in tile << 32
+    unsigned long long* spill = p.park + (static_cast<size_t>(b) * kRedMatchers + warp) * kSpillCap;
+    const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut};
 
     auto issue_load = [&](uint32_t t, int st) {
         if (t < p.bulk_tiles) {
@@ -932,21 +1080,12 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     auto round_ready = [&](uint32_t r) -> bool {
         return ld_acquire_cta_s32(&ring[r & (kRing - 1)].ready) >= static_cast<int>(r + 1);
     };
-    auto wait_ready = [&](uint32_t r, const char* what) {
+    auto wait_ready = [&](uint32_t r, int site) {
         unsigned long long spins = 0;
-        (void)spins; (void)what;
         while (!round_ready(r)) {
             __nanosleep(100);
-            PFAC_SPIN_GUARD(spins, what, r, ld_acquire_cta_s32(&ring[r & (kRing - 1)].ready), 0)
+            PFAC_SPIN_GUARD(spins, p.dbg, site, r, ring[r & (kRing - 1)].ready, warp)
         }
-    };
-    // where this warp's matches of round r (base posted) start in the output
-    auto out_offset = [&](uint32_t r) -> unsigned long long {
-        RingSlot* slot = &ring[r & (kRing - 1)];
-        int lower = (static_cast<uint32_t>(lane) < warp) ? slot->counts[lane] : 0;
-#pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) lower += __shfl_xor_sync(0xffffffffu, lower, dd);
-        return slot->base + static_cast<unsigned long long>(lower);
     };
     auto store_pair = [&](unsigned long long at, int id, long long gpos) {
         p.out_id[at] = id;
@@ -954,25 +1093,50 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
         else reinterpret_cast<int*>(p.out_pos)[at] = static_cast<int>(gpos);
     };
 
-    // parking ring: matches of up to kPendRecs rounds wait here for their CTA tile's base
-    int nrec = 0;         // records in use (closed rounds)
+    // parking: a tile's matches wait for their round's base in the shared-memory ring; what does not
+    // fit there goes on to the warp's spill ring in global memory
+    int nrec = 0;         // records in use (closed tiles)
     int rec_head = 0;     // ring index of the oldest record
-    int pend_head = 0;    // ring index of the oldest parked entry
-    int pend_used = 0;    // entries in use, those of the round being matched included
+    int pend_head = 0;    // shared-memory ring: index of the oldest entry, entries in use
+    int pend_used = 0;    // (those of the tile being matched included)
+    uint32_t spill_head = 0, spill_used = 0;
     auto oldest_round = [&]() -> uint32_t { return recs[rec_head].round; };
     auto pop_oldest = [&]() {  // caller made sure its round is ready
         const PendRec rec = recs[rec_head];
-        const unsigned long long off = out_offset(rec.round);
+        RingSlot* slot = &ring[rec.round & (kRing - 1)];
+        int lower = (static_cast<uint32_t>(lane) < warp) ? slot->counts[lane] : 0;
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) lower += __shfl_xor_sync(0xffffffffu, lower, dd);
+        const unsigned long long off = slot->base + static_cast<unsigned long long>(lower);
         const long long gbase = p.pos_base + static_cast<long long>(rec.start);
-        for (int i = lane; i < rec.n; i += 32) {
-            const int e = (pend_head + i) & (kPendCap - 1);
+#pragma unroll 1
+        for (uint32_t i = lane; i < rec.n_smem; i += 32) {
+            const int e = (pend_head + static_cast<int>(i)) & (kPendCap - 1);
             store_pair(off + i, pend_id[e], gbase + pend_pos[e]);
         }
+#pragma unroll 1
+        for (uint32_t i = lane; i < rec.n_spill; i += 32) {
+            const unsigned long long e = spill[(spill_head + i) & (kSpillCap - 1)];
+            store_pair(off + rec.n_smem + i, static_cast<int>(e & 0xFFFFFFFFu), gbase + static_cast<long long>(e >> 32));
+        }
         __syncwarp();
-        pend_head = (pend_head + rec.n) & (kPendCap - 1);
-        pend_used -= rec.n;
+        pend_head = (pend_head + static_cast<int>(rec.n_smem)) & (kPendCap - 1);
+        pend_used -= static_cast<int>(rec.n_smem);
+        spill_head = (spill_head + rec.n_spill) & (kSpillCap - 1);
+        spill_used -= rec.n_spill;
         rec_head = (rec_head + 1) & (kPendRecs - 1);
         nrec--;
+    };
+    // writes out parked tiles whose base has arrived, and keeps going (waiting for bases) while more
+    // than keep_recs records stay parked (0: everything out)
+    auto flush = [&](int keep_recs) {
+        while (nrec > 0) {
+            if (!round_ready(oldest_round())) {
+                if (nrec <= keep_recs) break;
+                wait_ready(oldest_round(), 1);
+            }
+            pop_oldest();
+        }
     };
 
     uint32_t parity = 0u;
@@ -980,46 +1144,31 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     for (uint32_t r = 0; r < my_rounds; ++r) {
         const uint32_t tile = tile_of(r);
         const size_t start = static_cast<size_t>(tile) * kRedTile;
-        int nmatch = 0;
         const unsigned char* inb = s_in + st * stage;
-        int tile_rem = 0, tile_valid = 0;
+        uint32_t n_smem = 0;     // this tile's matches parked in shared memory ...
+        uint32_t n_spill = 0;    // ... and, after those, in the spill ring
 
-        // One walk over the tile's survivors.  MODE 0: park the pairs (returns -1 when the ring cannot
-        // hold the tile), 1: count only, 2: write at out[off...] directly.  Returns the match count.
-        auto tile_pass = [&](const int mode, const unsigned long long off) -> int {
-            int n = 0;
-            const long long gbase = p.pos_base + static_cast<long long>(start);
-            // walks q16[0, total) 32 at a time; false = parking overflow
-            auto walk_range = [&](int total) -> bool {
-                for (int base = 0; base < total; base += 32) {
-                    const int slot = base + lane;
-                    const bool active = slot < total;
-                    const unsigned qe = active ? q16[slot] : 0u;
-                    int pl;
-                    const int best = walk_batch<CODE, HASHED>(T, inb, stage, p.in + start, tile_rem, active, qe, pl);
-                    const unsigned m = __ballot_sync(0xffffffffu, best != 0);
-                    if (m == 0) continue;
-                    const int c = __popc(m);
-                    const int mine_at = __popc(m & lt_mask);
-                    if (mode == 0) {
-                        while (pend_used + c > kPendCap) {
-                            if (nrec == 0) return false;     // this tile alone fills the ring
-                            wait_ready(oldest_round(), "room");
-                            pop_oldest();
-                        }
-                        if (best) {
-                            const int e = (pend_head + pend_used + mine_at) & (kPendCap - 1);
-                            pend_id[e] = best;
-                            pend_pos[e] = static_cast<unsigned short>(pl);
-                        }
-                        pend_used += c;
-                    } else if (mode == 2) {
-                        if (best) store_pair(off + n + mine_at, best, gbase + pl);
-                    }
-                    n += c;
+        if (tile < num_tiles) {
+            if (tile < p.bulk_tiles) {
+                unsigned long long spins = 0;
+                while (!mbar_try_wait(&bar[st], (parity >> st) & 1u)) { PFAC_SPIN_GUARD(spins, p.dbg, 6, tile, st, r) }
+                parity ^= 1u << st;
+            } else {
+                // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
+                unsigned char* w = s_in + st * stage;
+#pragma unroll 1
+                for (int i = lane; i < stage; i += 32) {
+                    const long long g = static_cast<long long>(start) + i;
+                    w[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
                 }
-                return true;
-            };
+                __syncwarp();
+            }
+            const long long total_left = p.n_total - static_cast<long long>(start);
+            const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
+            const long long owned_left = p.n_owned - static_cast<long long>(start);
+            const int tile_valid = owned_left > kRedTile ? kRedTile : static_cast<int>(owned_left);
+
+            // ---- survivors of the three blocks, one scan for all three counts (10-bit fields)
             uint32_t cand[kRedSub], slow[kRedSub];
             uint32_t packed = 0;
 #pragma unroll
@@ -1030,9 +1179,12 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             const uint32_t incl = warp_incl_scan(packed, lane);
             const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
             const int wtotal = static_cast<int>((tot & 1023u) + ((tot >> 10) & 1023u) + (tot >> 20));
-            if (wtotal == 0) return 0;
-            bool ok = true;
-            if (wtotal <= kQueueCap) {
+            // normally one segment: the whole tile's survivors.  Dense survivors are walked one block at a
+            // time, or 8 lanes of a block at a time (<= 128 survivors) when a block alone overflows the
+            // queue, the block's prefilter recomputed out of line; one walker call site either way.
+            int nseg = 0, seg_total = wtotal;
+            if (wtotal > 0 && wtotal <= kQueueCap) {
+                nseg = 1;
                 const uint32_t excl = incl - packed;
                 int qbase = 0;
 #pragma unroll
@@ -1047,118 +1199,145 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                     }
                     qbase += static_cast<int>((tot >> (10 * j)) & 1023u);
                 }
-                __syncwarp();
-                ok = walk_range(wtotal);
-                __syncwarp();
-            } else {
-                // dense survivors (adversarial text): 8 lanes of one block at a time (<= 128 survivors)
-                for (int j = 0; j < kRedSub && ok; j++) {
-                    uint32_t sl;
-                    const uint32_t cd = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, sl);
-                    const uint32_t cnt = static_cast<uint32_t>(__popc(cd | sl));
+            } else if (wtotal > 0) {
+                const bool by_block = (tot & 1023u) <= kQueueCap && ((tot >> 10) & 1023u) <= kQueueCap && (tot >> 20) <= kQueueCap;
+                nseg = by_block ? kRedSub : kRedSub * 4;
+            }
+            for (int seg = 0; seg < nseg; seg++) {
+                if (nseg > 1) {
+                    const int j = (nseg == kRedSub) ? seg : (seg >> 2);
+                    const uint32_t both = block_survivors_cold<CODE, FILT>(fv, inb, j, lane, tile_rem, tile_valid);
+                    const uint32_t sl = both >> 16;
+                    uint32_t all = (both & 0xFFFFu) | sl;
+                    const uint32_t cnt = static_cast<uint32_t>(__popc(all));
                     const uint32_t inc = warp_incl_scan(cnt, lane);
-                    for (int g = 0; g < 4 && ok; g++) {
-                        const uint32_t lo = g ? __shfl_sync(0xffffffffu, inc, 8 * g - 1) : 0u;
-                        const uint32_t hi = __shfl_sync(0xffffffffu, inc, 8 * g + 7);
-                        if ((lane >> 3) == g) {
-                            uint32_t all = cd | sl;
-                            int o = static_cast<int>(inc - cnt - lo);
-                            const int lb = j * kWarpTile + lane * kPosPerThread;
-                            while (all) {
-                                const int bit = __ffs(all) - 1;
-                                all &= all - 1;
-                                q16[o++] = static_cast<unsigned short>((lb + bit) | (((sl >> bit) & 1u) ? kSlowFlag : 0u));
-                            }
-                        }
-                        __syncwarp();
-                        ok = walk_range(static_cast<int>(hi - lo));
-                        __syncwarp();
+                    uint32_t lo = 0, hi = __shfl_sync(0xffffffffu, inc, 31);
+                    if (nseg != kRedSub) {
+                        const int g = seg & 3;
+                        lo = g ? __shfl_sync(0xffffffffu, inc, 8 * g - 1) : 0u;
+                        hi = __shfl_sync(0xffffffffu, inc, 8 * g + 7);
+                        if ((lane >> 3) != g) all = 0;
                     }
+                    int o = static_cast<int>(inc - cnt - lo);
+                    const int lb = j * kWarpTile + lane * kPosPerThread;
+                    while (all) {
+                        const int bit = __ffs(all) - 1;
+                        all &= all - 1;
+                        q16[o++] = static_cast<unsigned short>((lb + bit) | (((sl >> bit) & 1u) ? kSlowFlag : 0u));
+                    }
+                    seg_total = static_cast<int>(hi - lo);
                 }
-            }
-            if (!ok) {  // un-park what this pass parked
-                pend_used -= n;
-                return -1;
-            }
-            return n;
-        };
-
-        if (tile < num_tiles) {
-            if (tile < p.bulk_tiles) {
-                mbar_wait(&bar[st], (parity >> st) & 1u);
-                parity ^= 1u << st;
-            } else {
-                // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
-                unsigned char* w = s_in + st * stage;
-                for (int i = lane; i < stage; i += 32) {
-                    const long long g = static_cast<long long>(start) + i;
-                    w[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
+                __syncwarp();
+                // ---- walk the queue 32 survivors at a time; park the matches of every batch
+                for (int base = 0; base < seg_total; base += 32) {
+                    const int qslot = base + lane;
+                    const bool active = qslot < seg_total;
+                    const unsigned qe = active ? q16[qslot] : 0u;
+                    int pl;
+                    const int best = walk_batch<CODE, HASHED>(T, inb, stage, p.in + start, tile_rem, active, qe, pl);
+                    const unsigned m = __ballot_sync(0xffffffffu, best != 0);
+                    if (m == 0) continue;
+                    const uint32_t c = static_cast<uint32_t>(__popc(m));
+                    const uint32_t mine_at = static_cast<uint32_t>(__popc(m & lt_mask));
+                    if (n_spill == 0 && pend_used + static_cast<int>(c) <= kPendCap) {
+                        if (best) {
+                            const int e = (pend_head + pend_used + static_cast<int>(mine_at)) & (kPendCap - 1);
+                            pend_id[e] = best;
+                            pend_pos[e] = static_cast<unsigned short>(pl);
+                        }
+                        pend_used += static_cast<int>(c);
+                        n_smem += c;
+                    } else {
+                        // the rest of this tile goes to the spill ring (order: shared-memory part first)
+                        if (spill_used + c > kSpillCap) flush(0);   // older tiles out: this one then fits
+                        if (best)
+                            spill[(spill_head + spill_used + mine_at) & (kSpillCap - 1)] =
+                                static_cast<unsigned long long>(static_cast<uint32_t>(best)) |
+                                (static_cast<unsigned long long>(pl) << 32);
+                        spill_used += c;
+                        n_spill += c;
+                    }
                 }
                 __syncwarp();
             }
-            const long long total_left = p.n_total - static_cast<long long>(start);
-            tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
-            const long long owned_left = p.n_owned - static_cast<long long>(start);
-            tile_valid = owned_left > kRedTile ? kRedTile : static_cast<int>(owned_left);
+            if (elect_one()) issue_load(tile_of(r + NSTAGE), st);  // every lane is done with this stage
+            st ^= 1;
         }
 
-        // pass 0 parks; a tile the ring cannot hold is counted (pass 1) and, once its base is there,
-        // written directly (pass 2).  One call site: the walker is instantiated once.
-        int mode = 0;
-        unsigned long long off = 0;
-        for (;;) {
-            const int res = (tile < num_tiles) ? tile_pass(mode, off) : 0;
-            if (mode == 2) break;
-            if (res < 0) {
-                mode = 1;
-                continue;
-            }
-            nmatch = res;
+        // ---- flow control: nobody runs more than kLag rounds ahead of the scanner, so a ring slot
+        // (round r-kRing) is never rewritten while a warp may still read it
+        if (r >= kLag) wait_ready(r - kLag, 3);
 
-            // ---- flow control: nobody runs more than kLag rounds ahead of the scanner, so a ring slot
-            // (round r-kRing) is never rewritten while a warp may still read it
-            if (r >= kLag) wait_ready(r - kLag, "lag");
+        // ---- arrive: deposit the count; the scanner warp takes it from here -------------------------
+        RingSlot* slot = &ring[r & (kRing - 1)];
+        const uint32_t nmatch = n_smem + n_spill;
+        if (lane == 0) {
+            slot->counts[warp] = static_cast<int>(nmatch);
+            red_add_release_cta_s32(&slot->arrived, 1);
+        }
 
-            // ---- arrive: deposit the count; the scanner warp takes it from here ---------------------
-            RingSlot* slot = &ring[r & (kRing - 1)];
+        // ---- close this tile's record; write parked tiles whose base has arrived (after the lag wait
+        // that is everything of rounds <= r - kLag); the last round waits for everything
+        if (nmatch > 0) {
             if (lane == 0) {
-                slot->counts[warp] = nmatch;
-                red_add_release_cta_s32(&slot->arrived, 1);
+                PendRec& rec = recs[(rec_head + nrec) & (kPendRecs - 1)];
+                rec.round = r;
+                rec.n_smem = n_smem;
+                rec.n_spill = n_spill;
+                rec.start = static_cast<unsigned long long>(start);
             }
-
-            // ---- write parked matches whose base has arrived; close (or write) this round's ----------
-            while (nrec > 0 && round_ready(oldest_round())) pop_oldest();
-            if (mode == 0) {
-                if (nmatch > 0) {
-                    if (nrec == kPendRecs) {
-                        wait_ready(oldest_round(), "recs");
-                        pop_oldest();
-                    }
-                    if (lane == 0) {
-                        PendRec& rec = recs[(rec_head + nrec) & (kPendRecs - 1)];
-                        rec.round = r;
-                        rec.n = nmatch;
-                        rec.start = static_cast<unsigned long long>(start);
-                    }
-                    __syncwarp();
-                    nrec++;
-                }
-                break;
-            }
-            while (nrec > 0) { wait_ready(oldest_round(), "drain"); pop_oldest(); }
-            wait_ready(r, "direct");
-            off = out_offset(r);
-            mode = 2;
-        }
-        if (tile < num_tiles) {
             __syncwarp();
-            if (elect_one()) issue_load(tile_of(r + NSTAGE), st);  // every pass over this stage is done
-            st = (st + 1 == NSTAGE) ? 0 : st + 1;
+            nrec++;
+        }
+        flush((r + 1 == my_rounds) ? 0 : kPendRecs - 1);
+    }
+}
+
+// a rank whose shard is empty still takes part in the exchange
+__global__ void pfac_comm_scan_kernel(const KParams p) { comm_exchange_scan(p, 0ull, threadIdx.x & 31); }
+
+// Optional second step: every rank copies its run of (id, position) pairs into ONE
+// list that lives on rank dst, at its scanned offset, with plain stores to peer memory (NVLink);
+// the last CTA to finish raises this rank's "placed" word in dst's mailbox.
+struct PlaceParams {
+    const int* ids;
+    const long long* pos;
+    const unsigned long long* scan;      // {offset, total, count} of this rank (device)
+    int* g_ids;                          // list on dst (peer-mapped)
+    long long* g_pos;
+    unsigned long long capacity;
+    unsigned long long* placed;          // dst mailbox word of this rank for this epoch's parity
+    unsigned long long* ticket;          // own mailbox scratch word (zero between calls)
+    unsigned long long epoch_tag;        // epoch << kCommShift
+};
+__global__ void __launch_bounds__(256) pfac_place_kernel(const PlaceParams q) {
+    const unsigned long long off = q.scan[0], n = q.scan[2];
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+        if (off + i < q.capacity) {
+            q.g_ids[off + i] = q.ids[i];
+            q.g_pos[off + i] = q.pos[i];
         }
     }
-    while (nrec > 0) {
-        wait_ready(oldest_round(), "final");
-        pop_oldest();
+    __threadfence_system();   // this thread's peer stores before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(q.ticket, 1ull);
+        if (t + 1 == gridDim.x) {
+            *q.ticket = 0;
+            __threadfence_system();
+            st_release_sys_u64(q.placed, q.epoch_tag | (n & kCommMask));
+        }
+    }
+}
+// dst: the list is complete when every rank's "placed" word carries this epoch
+__global__ void pfac_wait_placed_kernel(const unsigned long long* placed, int world, unsigned long long epoch) {
+    const int lane = threadIdx.x;
+    if (lane < world) {
+        unsigned long long v = ld_acquire_sys_u64(placed + lane);
+        while ((v >> kCommShift) != epoch) {
+            __nanosleep(200);
+            v = ld_acquire_sys_u64(placed + lane);
+        }
     }
 }
 
@@ -1241,9 +1420,12 @@ size_t tableSmemBudget(int maxPatternLen, bool reduceKernel) {
 // per CTA tile (46.5 KB of input): one aggregate word; per round: a running total and a counter
 size_t reduceWorkspaceWords(size_t n_owned) {
     const size_t tiles = (n_owned + kRedTile - 1) / kRedTile;
-    const size_t ctiles = (tiles + kRedMatchers - 1) / kRedMatchers;
+    const size_t ctiles = (tiles + kRedSlots - 1) / kRedSlots;
     return 3 * ctiles + 8;
 }
+
+// one spill ring per matcher warp of the grid (never initialised: written before it is read)
+size_t reduceParkWords(const LaunchConfig& cfg) { return size_t(cfg.numSMs) * kRedMatchers * kSpillCap; }
 
 unsigned long long kernelLaunchCount() { return g_launches.load(); }
 
@@ -1292,9 +1474,21 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
 
 cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                               size_t n_owned, size_t n_total, long long pos_base, int* out_id,
-                              void* out_pos, bool pos64, unsigned long long* desc,
-                              unsigned long long* d_total, cudaStream_t stream) {
-    if (n_owned == 0) return cudaSuccess;
+                              void* out_pos, bool pos64, unsigned long long* desc, unsigned long long* park,
+                              unsigned long long* d_total, cudaStream_t stream, const CommLaunch* comm,
+                              unsigned long long* dbg) {
+    if (n_owned == 0) {
+        if (!comm) return cudaSuccess;
+        KParams p{};   // nothing to match: the count exchange alone
+        for (int i = 0; i < comm->world; i++) p.comm_peer[i] = comm->peer[i];
+        p.comm_scan = comm->scan;
+        p.comm_world = comm->world;
+        p.comm_rank = comm->rank;
+        p.comm_epoch = comm->epoch;
+        pfac_comm_scan_kernel<<<1, 32, 0, stream>>>(p);
+        g_launches++;
+        return cudaGetLastError();
+    }
     const int halo = roundHalo(t.maxPatternLen, kRedMaxHalo);
     KParams p = baseParams(t, in, n_owned, n_total, halo, kRedTile);
     if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -1302,7 +1496,16 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     p.out_pos = out_pos;
     p.pos_base = pos_base;
     p.desc = desc;
+    p.park = park;
+    p.dbg = dbg;
     p.total = d_total;
+    if (comm) {
+        for (int i = 0; i < comm->world; i++) p.comm_peer[i] = comm->peer[i];
+        p.comm_scan = comm->scan;
+        p.comm_world = comm->world;
+        p.comm_rank = comm->rank;
+        p.comm_epoch = comm->epoch;
+    }
     {
         const long long stage = kRedTile + halo;
         long long bulk = 0;
@@ -1328,13 +1531,29 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
-    const long long ctaTiles = (p.num_tiles + kRedMatchers - 1) / kRedMatchers;
+    const long long ctaTiles = (p.num_tiles + kRedSlots - 1) / kRedSlots;
     long long grid = cfg.numSMs;
     if (grid > ctaTiles) grid = ctaTiles;
     // cooperative launch: every CTA is resident, so waiting on another CTA's aggregate is safe
     void* args[] = {&p};
     e = cudaLaunchCooperativeKernel(kernel, dim3(unsigned(grid)), dim3(kRedThreads), args, smem, stream);
     if (e != cudaSuccess) return e;
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launchPlaceRun(const int* ids, const long long* pos, const unsigned long long* scan, int* g_ids,
+                           long long* g_pos, unsigned long long capacity, unsigned long long* placed,
+                           unsigned long long* ticket, unsigned epoch, int numSMs, cudaStream_t stream) {
+    PlaceParams q{ids, pos, scan, g_ids, g_pos, capacity, placed, ticket,
+                  static_cast<unsigned long long>(epoch & 0xFFFFFFu) << kCommShift};
+    pfac_place_kernel<<<numSMs * 4, 256, 0, stream>>>(q);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launchWaitPlaced(const unsigned long long* placed, int world, unsigned epoch, cudaStream_t stream) {
+    pfac_wait_placed_kernel<<<1, 32, 0, stream>>>(placed, world, static_cast<unsigned long long>(epoch & 0xFFFFFFu));
     g_launches++;
     return cudaGetLastError();
 }

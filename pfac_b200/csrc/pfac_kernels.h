@@ -13,6 +13,7 @@ constexpr uint32_t kKernelHashFilterMul = 0x9E3779B1u;
 constexpr uint32_t kKernelHashFilterMul2 = 0x85EBCA6Bu;
 constexpr uint32_t kKernelHashFilterMul3 = 0xC2B2AE35u;
 constexpr int kKernelHashFilterWords = 8192;
+constexpr int kKernelCommMaxRanks = 16;   // GPUs of one NVLink domain taking part in a count exchange
 
 // Device-resident compiled table (uploaded by the handle).
 struct DeviceTable {
@@ -58,17 +59,39 @@ size_t tableSmemBudget(int maxPatternLen, bool reduceKernel);
 
 // Look-back descriptor words needed by the reduce kernel for an n_owned-byte shard.
 size_t reduceWorkspaceWords(size_t n_owned);
+// Words of the per-warp spill rings (matches that do not fit the shared-memory parking; about 75 MB,
+// L2-resident in use); needs no initialisation.
+size_t reduceParkWords(const LaunchConfig& cfg);
 
 // Dense result: out[i] for i in [0,n_owned); walks may read in[0,n_total).
 cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                              size_t n_owned, size_t n_total, int* out, cudaStream_t stream);
 
-// Fused match + ordered compaction.  desc: reduceWorkspaceWords(n_owned) zeroed uint64 words.
+// Cross-GPU count exchange fused into the reduce kernel: every rank's mailbox (2 x kKernelCommMaxRanks
+// words, peer-mapped), the call's epoch, and where {exclusive offset, total, own count} go.
+struct CommLaunch {
+    unsigned long long* peer[kKernelCommMaxRanks];
+    unsigned long long* scan;
+    int world = 0, rank = 0;
+    unsigned epoch = 0;
+};
+
+// Fused match + ordered compaction.  desc: reduceWorkspaceWords(n_owned) zeroed uint64 words; park:
+// reduceParkWords(cfg) uint64 words; dbg: 8 zeroed host-mapped words where a wait that never ends
+// reports before the kernel traps (nullptr: trap without a report).
 // d_total: one uint64 receiving the match count.  pos64 selects long long vs int positions.
 cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                               size_t n_owned, size_t n_total, long long pos_base, int* out_id,
-                              void* out_pos, bool pos64, unsigned long long* desc,
-                              unsigned long long* d_total, cudaStream_t stream);
+                              void* out_pos, bool pos64, unsigned long long* desc, unsigned long long* park,
+                              unsigned long long* d_total, cudaStream_t stream, const CommLaunch* comm = nullptr,
+                              unsigned long long* dbg = nullptr);
+
+// Copy this rank's run (count and offset read from `scan` on the device) into the list on the
+// destination rank and raise `placed`; the destination waits for all ranks with launchWaitPlaced.
+cudaError_t launchPlaceRun(const int* ids, const long long* pos, const unsigned long long* scan, int* g_ids,
+                           long long* g_pos, unsigned long long capacity, unsigned long long* placed,
+                           unsigned long long* ticket, unsigned epoch, int numSMs, cudaStream_t stream);
+cudaError_t launchWaitPlaced(const unsigned long long* placed, int world, unsigned epoch, cudaStream_t stream);
 
 // Number of kernels launched by this library since load (bench.py reports it).
 unsigned long long kernelLaunchCount();

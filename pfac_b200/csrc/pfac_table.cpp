@@ -719,6 +719,84 @@ void getLayout(Reader& r, DeviceLayout& L) {
         r.ok = false;
 }
 
+// A compiled-table file is input like any other: a truncated, mismatched or hostile image must be
+// rejected here (the caller then compiles from the pattern file) instead of indexing out of bounds
+// in the dump, in a recompile for another budget, or on the device.
+#ifdef PFAC_VALID_DEBUG
+#define PFAC_INVALID do { fprintf(stderr, "compiled table rejected at %s:%d\n", __FILE__, __LINE__); return false; } while (0)
+#else
+#define PFAC_INVALID return false
+#endif
+bool validMachine(const Machine& m) {
+    if (m.numPatterns < 0 || m.numFinal != m.numPatterns || m.initialState != m.numFinal + 1) PFAC_INVALID;
+    if (m.numStates <= m.initialState || m.numStates > kMaxStates || m.maxPatternLen < 0 || m.numLeaves < 0) PFAC_INVALID;
+    if (m.lenById.size() != size_t(m.numFinal) + 1 || m.offById.size() != size_t(m.numFinal) + 1) PFAC_INVALID;
+    if (m.sortedId.size() != size_t(m.numPatterns) || m.sortedOff.size() != size_t(m.numPatterns)) PFAC_INVALID;
+    if (m.rows.size() < size_t(m.numStates)) PFAC_INVALID;
+    for (int id = 1; id <= m.numFinal; id++) {
+        const int len = m.lenById[size_t(id)];
+        if (len <= 0 || len > m.maxPatternLen) PFAC_INVALID;
+        if (m.offById[size_t(id)] > m.image.size() || size_t(len) > m.image.size() - m.offById[size_t(id)]) PFAC_INVALID;
+    }
+    for (int i = 0; i < m.numPatterns; i++) {
+        if (m.sortedId[size_t(i)] < 1 || m.sortedId[size_t(i)] > m.numFinal) PFAC_INVALID;
+        if (m.sortedOff[size_t(i)] >= m.image.size()) PFAC_INVALID;
+    }
+    for (size_t st = 0; st < m.rows.size(); st++)
+        for (const Edge& e : m.rows[st])
+            if (e.ch < 0 || e.ch >= kCharSet || e.next <= 0 || e.next >= m.numStates) PFAC_INVALID;
+    return true;
+}
+
+bool validLayout(const DeviceLayout& L, const Machine& m) {
+    if (!((L.codeBits == 8 || L.codeBits == 4 || L.codeBits == 2) && L.gramLen == 16 / L.codeBits)) PFAC_INVALID;
+    if (L.pre2.size() != 2048 || L.rank2.size() != 2048) PFAC_INVALID;
+    size_t bits = 0;
+    for (size_t w = 0; w < 2048; w++) {
+        if (L.rank2[w] != bits) PFAC_INVALID;
+        bits += size_t(__builtin_popcount(L.pre2[w]));
+    }
+    if (L.next2.size() != std::max<size_t>(bits, 1)) PFAC_INVALID;
+    if (!L.best2.empty() && L.best2.size() != L.next2.size()) PFAC_INVALID;
+    if (!L.chk2.empty() && L.chk2.size() != L.next2.size()) PFAC_INVALID;
+    if (!L.hfilt.empty() && (L.hfilt.size() != size_t(kHashFilterWords) || L.hfiltK < 1 || L.hfiltK > 2 || L.codeBits != 8)) PFAC_INVALID;
+    if (L.hot.size() != size_t(L.hotBuckets) * 4 || L.cold.size() != size_t(L.coldBuckets) * 4 || L.coldBuckets == 0) PFAC_INVALID;
+    if ((L.chains.size() & 3) || (L.tails.size() & 15) || L.hotDepth < 1) PFAC_INVALID;
+    if (L.numChains < 0 || size_t(L.numChains) > L.chains.size() / 4) PFAC_INVALID;
+    const size_t nchains = size_t(L.numChains);   // an empty table still holds one all-zero record
+    const uint32_t states = uint32_t(m.numStates);
+    auto okValue = [&](uint32_t v) {   // what next2 / a hash slot may hold
+        if (v == kTrap) return true;
+        if (v & kChainFlag) return size_t(v & kChainIndexMask) < nchains;
+        return (v & ~kLeafPlain) < states && (v & ~kLeafPlain) != 0;
+    };
+    for (uint32_t v : L.next2) if (!okValue(v)) PFAC_INVALID;
+    for (uint32_t v : L.best2) if (v > uint32_t(m.numFinal)) PFAC_INVALID;
+    for (int c = 0; c < kCharSet; c++) if (L.root[c] < -1 || L.root[c] >= m.numStates || L.root[c] == 0) PFAC_INVALID;
+    for (const std::vector<uint32_t>* tab : {&L.hot, &L.cold}) {
+        bool terminator = tab->empty();   // probing ends at a bucket whose second slot is empty
+        for (size_t b = 0; b + 3 < tab->size(); b += 4) {
+            const uint32_t* e = tab->data() + b;
+            for (int sl = 0; sl < 2; sl++) {
+                if (e[2 * sl] == kEmptyKey) continue;
+                if ((e[2 * sl] >> 8) >= states || !okValue(e[2 * sl + 1]) || e[2 * sl + 1] == kTrap) PFAC_INVALID;
+            }
+            if (e[0] == kEmptyKey && e[2] != kEmptyKey) PFAC_INVALID;   // slot 0 fills first
+            terminator = terminator || e[2] == kEmptyKey;
+        }
+        if (!terminator) PFAC_INVALID;
+    }
+    for (size_t i = 0; i < nchains; i++) {
+        const uint32_t off = L.chains[4 * i], len = L.chains[4 * i + 1], end = L.chains[4 * i + 2];
+        if ((off & 3) || len == 0 || len > uint32_t(m.maxPatternLen)) PFAC_INVALID;
+        if (size_t(off) + ((size_t(len) + 3) & ~size_t(3)) > L.tails.size()) PFAC_INVALID;
+        if ((end & ~kLeafFlag) >= states || (end & ~kLeafFlag) == 0) PFAC_INVALID;
+    }
+    return true;
+}
+
+#undef PFAC_INVALID
+
 }  // namespace
 
 bool saveCompiled(const char* filename, const Machine& m, const std::vector<const CompiledLayout*>& layouts) {
@@ -771,6 +849,9 @@ bool loadCompiled(const char* filename, Machine& m, std::vector<CompiledLayout>&
         getLayout(r, ls[i].layout);
     }
     if (!r.ok || r.p != r.end) return false;
+    if (!validMachine(mm)) return false;
+    for (const CompiledLayout& c : ls)
+        if (!validLayout(c.layout, mm)) return false;
     m = std::move(mm);
     layouts = std::move(ls);
     return true;

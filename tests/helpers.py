@@ -131,3 +131,39 @@ def brute_force_match(patterns, text):
                     out[i] = pid
                     break
     return out
+
+
+class CheckerOracle:
+    """The checker the GPU tests compare with: the reference's own CPU matcher (oracle/_ref, compiled
+    from /root/reference by oracle/Makefile; it travels to the GPU box as a built .so) when it is
+    there, else the plain-C restatement (oracle/pfac_oracle.c) -- the two are pinned against each
+    other in tests/test_oracle.py.  Same surface as oracle.Oracle."""
+
+    def __init__(self, pattern_file):
+        import oracle
+        self.kind = "reference" if oracle.ref_available() else "port"
+        port = oracle.Oracle(pattern_file)   # raises on files the reference would assert-abort on
+        self._o = oracle.RefOracle(pattern_file) if oracle.ref_available() else port
+        for k in ("num_patterns", "num_states", "initial_state", "max_pattern_len"):
+            setattr(self, k, getattr(self._o, k))
+
+    @staticmethod
+    def set_threads(n):
+        import oracle
+        (oracle.RefOracle if oracle.ref_available() else oracle.Oracle).set_threads(n)
+
+    def match(self, text, omp=True):
+        return self._o.match(text, omp=omp)
+
+    def match_shard(self, text, n_owned):
+        """Results for positions [0, n_owned); walks may read all of `text` (owned + tail halo)."""
+        if self.kind == "port":
+            return self._o.match_shard(text, n_owned)
+        return self._o.match(text, omp=True)[:n_owned]
+
+    def reduce(self, dense):
+        import oracle
+        return oracle.reduce_dense(dense)
+
+    def dump(self, path):
+        return self._o.dump(path)

@@ -31,36 +31,7 @@ import numpy as np  # noqa: E402
 from workloads import synth  # noqa: E402
 from pfac_b200.sharding import shard_bounds  # noqa: E402
 
-GIB = 1 << 30
-
-CONFIGS = {
-    "c2": dict(patterns=lambda: synth.patterns_c2(1000), kind="random", seed=synth.SEED_BASE + 2,
-               bytes=GIB, every=4096, api="dense"),
-    "c3": dict(patterns=lambda: synth.patterns_snort_like(20000), kind="ascii", seed=synth.SEED_BASE + 3,
-               bytes=4 * GIB, every=2048, api="dense"),
-    "c4": dict(patterns=lambda: synth.patterns_dna(5000), kind="dna", seed=synth.SEED_BASE + 4,
-               bytes=2_000_000_000, every=0, api="reduce"),
-    "c4dense": dict(patterns=lambda: synth.patterns_dna(5000, short=64), kind="dna", seed=synth.SEED_BASE + 4,
-                    bytes=2_000_000_000, every=0, api="reduce"),
-    "c5": dict(patterns=lambda: synth.patterns_snort_like(10000, seed=synth.SEED_BASE + 5), kind="ascii",
-               seed=synth.SEED_BASE + 5, bytes=32 * GIB, every=2048, api="reduce64"),
-}
-
-
-def gen_text(kind, seed, start, n, total_len, pats, every):
-    out = np.empty(n, dtype=np.uint8)
-    piece = 64 << 20
-    for off in range(0, n, piece):
-        m = min(piece, n - off)
-        if kind == "random":
-            out[off:off + m] = synth.random_bytes(seed, start + off, m)
-        elif kind == "ascii":
-            out[off:off + m] = synth.ascii_weighted_bytes(seed, start + off, m)
-        else:
-            out[off:off + m] = synth.dna_bytes(seed, start + off, m)
-    if every:
-        synth.plant(out, start, total_len, pats, seed, every=every)
-    return out
+from tests.configs import CONFIGS, GIB, ChunkedCheck, device_text, nonzero_pairs  # noqa: E402
 
 
 def main():
@@ -71,6 +42,7 @@ def main():
                     help="bytes per rank to verify against the oracle (-1 = all, 0 = none)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--perf-mode", type=int, default=0)
+    ap.add_argument("--out", default="", help="also append the JSON line to this file")
     ap.add_argument("--gather", action="store_true",
                     help="multi-GPU reduce: also deliver every rank's run to rank 0 (sharding.place_runs) and time it")
     args = ap.parse_args()
@@ -78,7 +50,7 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
-    from oracle import Oracle
+    from tests.helpers import CheckerOracle
     from pfac_b200 import PFAC
     from pfac_b200.sharding import allgather_count_offsets, place_runs
 
@@ -106,16 +78,16 @@ def main():
 
     start, owned, total = shard_bounds(total_len, world, rank, maxlen)
     t0 = time.time()
-    text = gen_text(cfg["kind"], cfg["seed"], start, total, total_len, pats, cfg["every"])
+    d_in = device_text(cfg, start, total, total_len, pats, dev)   # regenerated on the GPU from the counter hash
+    torch.cuda.synchronize()
     gen_s = time.time() - t0
-    d_in = torch.from_numpy(text).to(dev)
     api = cfg["api"]
     res = {"config": args.config, "api": api, "rank": rank, "world": world, "total_bytes": total_len,
            "owned_bytes": owned, "patterns": len(pats), "states": info["num_states"],
            "max_pattern_len": maxlen, "table": {k: info[k] for k in (
                "hash_edges", "num_chains", "tail_bytes", "hot_depth", "hot_buckets", "cold_buckets",
                "next2_hot", "chains_hot", "pre2_bits_set", "device_bytes")},
-           "compile_s": round(compile_s, 3), "gen_s": round(gen_s, 1), "perf_mode": args.perf_mode}
+           "compile_s": round(compile_s, 3), "gen_s": round(gen_s, 3), "perf_mode": args.perf_mode}
 
     def sync():
         torch.cuda.synchronize()
@@ -183,39 +155,72 @@ def main():
         res["algorithmic_bytes"] = owned + (12 if pos64 else 8) * count
     else:
         res["algorithmic_bytes"] = 5 * owned
+    # ---- the same step inside the library: count exchange + scan fused into the reduce kernel over
+    # peer memory (PFAC_comm, CUDA IPC mailboxes), then the runs placed into rank 0's list by P2P stores
+    if api == "reduce64":
+        from pfac_b200 import PFACComm
+        comm = PFACComm.from_torch(list_capacity=int(total_m) + 16 if rank == 0 else 0, device=dev) if world > 1 \
+            else PFACComm(0, 1, int(total_m) + 16)
+        d_scan = torch.zeros(3, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            g_off, g_total, g_count = pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, start, d_id, d_pos)
+        assert (g_off, g_total, g_count) == (off, total_m, count), ((g_off, g_total, g_count), (off, total_m, count))
+        sync()
+        ev0.record()
+        for _ in range(args.steps):
+            pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, start, d_id, d_pos, d_scan=d_scan, sync=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        gms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        res["global_scan_ms_per_step"] = float(gms.item())          # kernel + in-kernel exchange, device-timed
+        res["global_scan_input_GBps_all_ranks"] = total_len / (float(gms.item()) * 1e-3) / 1e9
+        if args.gather:
+            sync()
+            ev0.record()
+            pf.gatherRuns(comm, 0, d_id, d_pos, d_scan=d_scan, sync=False)
+            ev1.record()
+            torch.cuda.synchronize()
+            res["p2p_gather_ms"] = ev0.elapsed_time(ev1)
+            sync()
+            if rank == 0:   # the list on rank 0: ascending, this rank's run first
+                k = min(int(total_m), 1 << 24)
+                ids0, pos0 = comm.read_global_list(k)
+                okp = bool(np.all(pos0[1:] > pos0[:-1])) if k > 1 else True
+                kk = min(k, count)
+                okp = okp and np.array_equal(ids0[:kk], d_id[:kk].cpu().numpy()) and \
+                    np.array_equal(pos0[:kk], d_pos[:kk].cpu().numpy())
+                tail_ids, tail_pos = comm.read_global_list(min(int(total_m), 4096), first=max(int(total_m) - 4096, 0))
+                res["p2p_gather_ok"] = bool(okp) and bool(np.all(tail_pos[1:] > tail_pos[:-1]))
+                res["p2p_gather_last_pos"] = int(tail_pos[-1]) if tail_pos.size else -1
+        sync()
+        comm.destroy()
     res["roofline_frac_of_6548.5"] = res["algorithmic_bytes"] / (ms_max * 1e-3) / 1e9 / 6548.5
 
     # ---- parity vs the oracle, chunked ---------------------------------------------------------------
     check = owned if args.check_bytes < 0 else min(args.check_bytes, owned)
     if check:
-        Oracle.set_threads(max(1, (os.cpu_count() or 1) // world))  # torchrun exports OMP_NUM_THREADS=1
-        orc = Oracle(pfile)
-        chunk = 256 << 20
-        halo = maxlen - 1
+        CheckerOracle.set_threads(max(1, (os.cpu_count() or 1) // world))  # torchrun exports OMP_NUM_THREADS=1
+        orc = CheckerOracle(pfile)
         nmis = 0
         t0 = time.time()
-        g_ids, g_pos = [], []
-        for c0 in range(0, check, chunk):
-            c1 = min(c0 + chunk, check)
-            seg = text[c0:min(c1 + halo, total)]
-            want = orc.match_shard(seg, c1 - c0)
+        k = 0
+        for c0, c1, want in ChunkedCheck(orc, d_in, owned, maxlen - 1, limit=check):
             if api == "dense":
-                got = d_out[c0:c1].cpu().numpy()
-                nmis += int((got != want).sum())
+                nmis += int((d_out[c0:c1] != torch.from_numpy(want).to(dev)).sum().item())
             else:
-                ids, pos = orc.reduce(want)
-                g_ids.append(ids)
-                g_pos.append(pos + c0 + (start if pos64 else 0))
+                ids, pos = nonzero_pairs(want, c0 + (start if pos64 else 0))
+                g_ids = d_id[k:k + ids.size].cpu().numpy()
+                g_pos = d_pos[k:k + ids.size].cpu().numpy().astype(np.int64)
+                nmis += int(g_ids.size != ids.size) + int((g_ids != ids[:g_ids.size]).sum()) + \
+                    int((g_pos != pos[:g_pos.size]).sum())
+                k += ids.size
         if api != "dense":
-            w_ids = np.concatenate(g_ids)
-            w_pos = np.concatenate(g_pos)
-            k = w_ids.size
-            got_ids = d_id[:k].cpu().numpy()
-            got_pos = d_pos[:k].cpu().numpy().astype(np.int64)
             if check == owned and k != count:
                 nmis += abs(k - count) + 1
-            nmis += int((got_ids != w_ids).sum()) + int((got_pos != w_pos).sum())
             res["oracle_matches_checked"] = int(k)
+        res["oracle"] = orc.kind
         res["checked_bytes"] = check
         res["mismatches"] = nmis
         res["oracle_s"] = round(time.time() - t0, 1)
@@ -224,6 +229,9 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "a") as f:
         f.write(json.dumps(res) + "\n")
+    if args.out:
+        with open(args.out, "a") as f:
+            f.write(json.dumps(res) + "\n")
     pf.destroy()
     if world > 1:
         dist.destroy_process_group()

@@ -1,7 +1,9 @@
 """GPU parity tests: the CUDA path, called through the C ABI (libpfac.so), against the oracle.
 
-Bit-exact (integer results).  The oracle is oracle/libpfac_oracle.so (plain-C restatement of the
-reference CPU matcher); /root/reference is never read here.
+Bit-exact (integer results).  The checker is the reference's own CPU matcher compiled from the
+reference sources (oracle/_ref/libpfac_ref.so, built where /root/reference exists and shipped as a
+binary) when present, else oracle/libpfac_oracle.so (the plain-C restatement); /root/reference is
+never read here.
 """
 import os
 
@@ -24,8 +26,8 @@ def cuda():
 
 
 def _oracle(path):
-    from oracle import Oracle
-    return Oracle(path)
+    from tests.helpers import CheckerOracle
+    return CheckerOracle(path)
 
 
 def _dev_match(pf, text, cuda, owned=None):

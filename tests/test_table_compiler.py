@@ -351,6 +351,52 @@ def test_compiled_table_file_round_trip(tmp_path, golden_dir):
     assert e.value.status == Status.FILE_OPEN_ERROR
 
 
+def _fnv1a64(b):
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & ((1 << 64) - 1)
+    return h
+
+
+def test_compiled_table_file_content_is_validated(tmp_path, golden_dir):
+    """A file whose checksum is right but whose content is not (a hostile or mismatched image) must be
+    rejected at load, not crash the dump / a recompile / the kernels: patch fields and recompute the FNV."""
+    import struct
+    src = os.path.join(golden_dir, "example_pattern")
+    a = TableCompiler(src, hot_budget_bytes=0)
+    f = str(tmp_path / "ok.pfacb")
+    a.save(f)
+    blob = bytearray(open(f, "rb").read())
+    head, payload = blob[:40], blob[40:]
+    (image_len,) = struct.unpack_from("<Q", payload, 0)
+    ints = 8 + image_len          # numPatterns, numFinal, initialState, numStates, maxPatternLen, numLeaves
+    assert struct.unpack_from("<i", payload, ints)[0] == a.info()["num_patterns"]
+
+    def reject(mut):
+        pl = bytearray(payload)
+        mut(pl)
+        out = bytes(head[:32]) + struct.pack("<Q", _fnv1a64(pl)) + bytes(pl)
+        bad = str(tmp_path / "bad.pfacb")
+        open(bad, "wb").write(out)
+        with pytest.raises(PFACError) as e:
+            TableCompiler(compiled_file=bad)
+        assert e.value.status == Status.INVALID_PARAMETER
+
+    # the unmodified payload with a recomputed checksum still loads
+    out = bytes(head[:32]) + struct.pack("<Q", _fnv1a64(payload)) + bytes(payload)
+    good = str(tmp_path / "good.pfacb")
+    open(good, "wb").write(out)
+    assert TableCompiler(compiled_file=good).info() == a.info()
+    reject(lambda pl: struct.pack_into("<i", pl, ints + 4, 50_000_000))     # numFinal
+    reject(lambda pl: struct.pack_into("<i", pl, ints + 8, 3))              # initialState != numFinal + 1
+    reject(lambda pl: struct.pack_into("<i", pl, ints + 12, 1 << 30))       # numStates
+    # an edge target beyond the automaton: the flattened edge list is the last vector of the machine
+    # (per-state counts, then {ch, next} pairs); find the pair (ord('A'), next) of the first edge
+    edge = bytes(payload).find(struct.pack("<i", ord("A")), ints + 24)
+    assert edge > 0
+    reject(lambda pl: struct.pack_into("<i", pl, edge + 4, 1 << 28))
+
+
 def test_saturated_hashed_filter_falls_back_to_exact_stage():
     """Dozens of 1-byte patterns fill the hashed filter (256 words each): the compiler then keeps the
     exact 2-gram stage; results are the brute-force ones either way."""
