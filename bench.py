@@ -11,9 +11,13 @@ is weak scaling: rank r owns bytes [r GiB, (r+1) GiB) of an N GiB stream, no dat
 collective.  value = total input GB (1e9 B) scanned by all ranks per second of the slowest rank.
 
 Extra objects on the JSON line: roofline (dominant kernel vs the measured HBM peak),
-cpu_baseline (reference CPU_OMP matcher on this box's host cores, rank 0, N=1), e2e (same
-metric through PFAC_matchFromHost with pinned host buffers, copies inside the timed region),
-reduce (the fused compaction path on the same shard, with the cross-GPU count scan at N>1).
+cpu_baseline (reference CPU_OMP matcher on this box's host cores, rank 0, N=1; plus the reference's
+single-thread PFAC_CPU on a smaller sample), e2e (same metric through PFAC_matchFromHost with pinned
+host buffers, copies inside the timed region), reduce (the fused compaction path on the same shard with
+the cross-GPU count scan done inside the kernel over peer memory), c5 (BASELINE configs[4]: 32 GiB of
+text regenerated on the GPUs, 10,000 patterns, sharded reduce + in-kernel global offset scan + the runs
+placed into one list by P2P stores, 512 MiB per rank checked against the oracle outside the timed region),
+table (what the table compiler built).  `config` is identical for both arms.
 """
 import argparse
 import json
@@ -129,12 +133,14 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
+    (profiles/traffic.json: per-launch dram__bytes_read.sum + dram__bytes_write.sum, the kernel it was
+    taken on and the commit).  Returns (bytes, provenance)."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return d.get("dense_dram_bytes_per_launch")
+        return d.get("dense_dram_bytes_per_launch"), {k: d.get(k) for k in ("kernel", "commit", "round", "source")}
     except Exception:
-        return None
+        return None, None
 
 
 def cpu_reference(pfile, text, threads, reps, budget_s=None):
@@ -150,7 +156,7 @@ def cpu_reference(pfile, text, threads, reps, budget_s=None):
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        m.match(text, omp=True)
+        m.match(text, omp=threads > 1)
         dt = time.perf_counter() - t0
         times.append(dt)
         best = dt if best is None else min(best, dt)
@@ -202,6 +208,141 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+C5_PATTERNS = 10000
+C5_TOTAL = 32 * GIB
+
+
+def run_c5(pf_factory, rank, local_rank, world, dev, dist, torch, barrier, max_over_ranks, steps, total_len, peak):
+    """BASELINE configs[4]: `total_len` bytes of ASCII-weighted text regenerated on the GPUs from the
+    counter hash (no host buffer, no H2D), 10,000 Snort-like patterns, contiguous shards with a
+    (maxPatternLen-1)-byte tail halo; per step every rank runs the fused reduce kernel, which publishes
+    its match count into every rank's mailbox over NVLink peer memory and takes the exclusive prefix
+    itself (PFAC_comm), then the runs are placed into one global list on rank 0 by P2P stores.  Device
+    timed, max over ranks.  Parity (outside the timed region): the first 512 MiB of every shard against
+    the oracle, global 64-bit positions, offsets = exclusive scan of the counts."""
+    from pfac_b200 import PFACComm
+    from pfac_b200.sharding import shard_bounds
+    from tests import configs
+    cfg = dict(configs.CONFIGS["c5"])
+    pats = cfg["patterns"]()
+    tmp = tempfile.mkdtemp(prefix="pfac_c5_")
+    pfile = synth.write_pattern_file(os.path.join(tmp, "c5_rank%d.pat" % rank), pats)
+    pf = pf_factory()
+    pf.readPatternFromFile(pfile)
+    info = pf.tableInfo()
+    maxlen = info["max_pattern_len"]
+    start, owned, total = shard_bounds(total_len, world, rank, maxlen)
+    t0 = time.perf_counter()
+    d_in = configs.device_text(cfg, start, total, total_len, pats, dev)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    cap = max(owned // 32, 1 << 20)           # ~0.9 % of the positions match; 3 % holds them
+    d_id = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_pos = torch.empty(cap, dtype=torch.int64, device=dev)
+    d_scan = torch.zeros(3, dtype=torch.int64, device=dev)
+    # the global list lives on rank 0 (every rank maps it); sized after a first pass tells the total
+    comm0 = PFACComm.from_torch(0, device=dev) if world > 1 else PFACComm(0, 1, 0)
+    off, total_m, count = pf.matchShardFromDeviceReduce64Global(comm0, d_in, owned, total, start, d_id, d_pos)
+    barrier()
+    comm0.destroy()
+    comm = (PFACComm.from_torch(total_m + 64 if rank == 0 else 0, device=dev) if world > 1
+            else PFACComm(0, 1, total_m + 64))
+
+    def step():
+        pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, start, d_id, d_pos, d_scan=d_scan, sync=False)
+        pf.gatherRuns(comm, 0, d_id, d_pos, d_scan=d_scan, sync=False)
+
+    for _ in range(3):
+        step()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(steps):
+        step()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / steps)
+    # the same kernel with nobody to wait for (a one-rank comm) and no placement: what the cross-GPU
+    # part of the step costs is the difference
+    solo = PFACComm(0, 1, 0)
+    d_scan1 = torch.zeros(3, dtype=torch.int64, device=dev)
+    for _ in range(2):
+        pf.matchShardFromDeviceReduce64Global(solo, d_in, owned, total, start, d_id, d_pos, d_scan=d_scan1, sync=False)
+    barrier()
+    ev[0].record()
+    for _ in range(steps):
+        pf.matchShardFromDeviceReduce64Global(solo, d_in, owned, total, start, d_id, d_pos, d_scan=d_scan1, sync=False)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms_plain = max_over_ranks(ev[0].elapsed_time(ev[1]) / steps)
+    solo.destroy()
+    barrier()
+    scan = [int(x) for x in d_scan.cpu().tolist()]
+    assert scan == [off, total_m, count], (scan, off, total_m, count)
+    # ---- parity, outside the timed region
+    from tests.helpers import CheckerOracle
+    check = min(owned, 512 << 20)
+    CheckerOracle.set_threads(max(1, (os.cpu_count() or 1) // world))
+    orc = CheckerOracle(pfile)
+    mism, k = 0, 0
+    t0 = time.perf_counter()
+    for c0, c1, want in configs.ChunkedCheck(orc, d_in, owned, maxlen - 1, limit=check):
+        ids, pos = configs.nonzero_pairs(want, c0 + start)
+        g_ids = d_id[k:k + ids.size].cpu().numpy()
+        g_pos = d_pos[k:k + ids.size].cpu().numpy()
+        mism += int(g_ids.size != ids.size) + int((g_ids != ids[:g_ids.size]).sum()) + int((g_pos != pos[:g_pos.size]).sum())
+        k += ids.size
+    oracle_s = time.perf_counter() - t0
+    # offsets: exclusive scan of the counts, checked against an NCCL all-gather of the same counts
+    counts = torch.tensor([count], dtype=torch.int64, device=dev)
+    if world > 1:
+        allc = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, counts)
+    else:
+        allc = counts
+    allc = [int(x) for x in allc.cpu().tolist()]
+    ok_scan = off == sum(allc[:rank]) and total_m == sum(allc)
+    # the global list on rank 0: this rank's run sits at its offset; ascending over rank boundaries
+    ok_list = True
+    if rank == 0:
+        kk = min(count, 1 << 22)
+        ids0, pos0 = comm.read_global_list(kk)
+        ok_list = bool(np.array_equal(ids0, d_id[:kk].cpu().numpy()) and np.array_equal(pos0, d_pos[:kk].cpu().numpy()))
+        lo = max(count - 2048, 0)
+        seam_ids, seam_pos = comm.read_global_list(min(total_m - lo, 4096), first=lo)
+        ok_list = ok_list and bool(np.all(seam_pos[1:] > seam_pos[:-1]))
+        tail_ids, tail_pos = comm.read_global_list(min(total_m, 4096), first=max(total_m - 4096, 0))
+        ok_list = ok_list and bool(np.all(tail_pos[1:] > tail_pos[:-1])) and int(tail_pos[-1]) < total_len
+    flags = torch.tensor([mism, 0 if (ok_scan and ok_list) else 1], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flags)
+    bit_exact = int(flags[0].item()) == 0 and int(flags[1].item()) == 0
+    barrier()
+    comm.destroy()
+    pf.destroy()
+    algo = owned + 12 * count
+    return {
+        "workload": "C5: %d Snort-like patterns over %.0f GiB ASCII-weighted planted text regenerated on the GPUs, "
+                    "%d contiguous shards + %d-byte tail halo, PFAC_matchShardFromDeviceReduce64Global (fused match + "
+                    "compaction + in-kernel cross-GPU count scan) + PFAC_commGatherRuns (one global list on rank 0)"
+                    % (len(pats), total_len / GIB, world, maxlen - 1),
+        "value": total_len / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "per_gpu_GBps": owned / (ms * 1e-3) / 1e9, "bytes_per_gpu": owned, "total_bytes": total_len,
+        "kernel_only_ms_per_call": ms_plain,
+        "cross_gpu_ms_per_step": max(ms - ms_plain, 0.0),
+        "cross_gpu": "count exchange + exclusive scan inside the reduce kernel over NVLink peer memory, then %d B "
+                     "per match stored into rank 0's list by P2P stores; no NCCL call, no host round trip in the step"
+                     % 12,
+        "matches_total": total_m, "matches_rank0": count if rank == 0 else None, "states": info["num_states"],
+        "roofline": {"bound": "hbm", "kernel": "pfac_reduce_kernel<1, 8, %d>" % (info["hashed_filter"] + 1 if info["hashed_filter"] else 0),
+                     "algorithmic_bytes_per_launch": int(algo), "achieved": algo / (ms_plain * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": algo / (ms_plain * 1e-3) / 1e9 / peak,
+                     "note": "rank 0, N + 12 M bytes per launch; issue-bound, not HBM-bound"},
+        "gen_s": gen_s, "oracle": orc.kind, "oracle_checked_bytes_per_rank": check, "oracle_s": oracle_s,
+        "bit_exact": bit_exact,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,9 +352,12 @@ def main():
     ap.add_argument("--bytes", type=int, default=GIB, help="input bytes per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--reduce-steps", type=int, default=10)
+    ap.add_argument("--c5-steps", type=int, default=5)
+    ap.add_argument("--c5-bytes", type=int, default=C5_TOTAL, help="total bytes of the C5 leg (all ranks)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-reduce", action="store_true")
+    ap.add_argument("--skip-c5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -228,12 +372,14 @@ def main():
     # NCCL prints its version banner / debug lines to stdout: keep stdout for the one JSON line by
     # pointing fd 1 at stderr while the ranks run and printing the line to the saved stdout
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # the host copy pool is per process: share the box's cores among the ranks of this job
+    os.environ.setdefault("PFAC_B200_COPY_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // max(world, 1)))))
     sys.stdout.flush()
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     import torch
     import torch.distributed as dist
-    from pfac_b200 import PFAC
+    from pfac_b200 import PFAC, PFACComm
     from pfac_b200.api import kernel_launch_count
 
     if not torch.cuda.is_available():
@@ -253,6 +399,12 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
     patterns = synth.patterns_c2(N_PATTERNS)
@@ -302,8 +454,11 @@ def main():
     avg_launch_ms = float(np.mean(per_launch_ms))
     algo_bytes = 5 * owned  # 1 B read + 4 B written per position
     achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
+    kernel_name = "pfac_dense_kernel<3, %d, %d>" % (
+        info["code_bits"], (3 if info["hashed_filter"] == 2 else 2) if info["hashed_filter"] else (1 if info["has_chk2"] else 0))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pfac_match_kernel<dense>",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_ms,
                 "median_launch_ms": float(np.median(per_launch_ms)), "best_launch_ms": float(np.min(per_launch_ms)),
                 "frac_of_8TBps_spec": achieved / 8000.0}
@@ -314,6 +469,7 @@ def main():
         h_in = torch.empty(owned, dtype=torch.uint8, pin_memory=True)
         h_in.numpy()[:] = shard[:owned]
         h_out = torch.empty(owned, dtype=torch.int32, pin_memory=True)
+
         def time_host_calls():
             pf.matchFromHost(h_in, h_out, size=owned)  # warm-up: allocates the pipeline buffers
             h_out.fill_(-1)                            # every timed call must rewrite the whole array
@@ -321,13 +477,16 @@ def main():
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 pf.matchFromHost(h_in, h_out, size=owned)
-            return max_over_ranks(time.perf_counter() - t0)
+            mine = time.perf_counter() - t0
+            return max_over_ranks(mine), mine
 
-        dt = time_host_calls()
+        dt, mine = time_host_calls()
         h2d_b, d2h_b = pf.lastHostTransfer()           # counted by the library around its cudaMemcpyAsync calls
         e2e = {"value": owned * world * args.e2e_steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
-               "steps": args.e2e_steps,
+               "steps": args.e2e_steps, "per_rank_value": owned * args.e2e_steps / mine / 1e9,
+               "sum_of_rank_rates": sum_over_ranks(owned * args.e2e_steps / mine / 1e9),
+               "host_threads_per_rank": int(os.environ["PFAC_B200_COPY_THREADS"]),
                "api": "PFAC_matchFromHost (pinned host buffers; chunked H2D / fused match+compaction / D2H of the "
                       "(id, position) pairs; the host zero-fills and scatters the dense int32 array it returns)"}
         if world == 1:
@@ -335,7 +494,7 @@ def main():
             assert bool((torch.from_numpy(h_out.numpy()).to(dev) == d_out).all().item()), "e2e result differs"
         # the same call with the dense array itself crossing PCIe (the reference's data movement)
         os.environ["PFAC_B200_HOST_RESULT"] = "dense"
-        dt = time_host_calls()
+        dt, _ = time_host_calls()
         del os.environ["PFAC_B200_HOST_RESULT"]
         h2d_b, d2h_b = pf.lastHostTransfer()
         e2e["dense_d2h"] = {"value": owned * world * args.e2e_steps / dt / 1e9, "unit": UNIT,
@@ -360,55 +519,60 @@ def main():
                                  "api": "PFAC_matchFromHostReduce", "matches": int(ids.size)}
             del r_id, r_pos
         del h_in
+        pf.releaseHostBuffers()
 
-    # ---- fused reduce path on the same shard, with the cross-GPU count scan --------------------------
+    # ---- fused reduce path on the same shard, the cross-GPU count scan inside the kernel -----------------
     reduce_info = None
     if not args.skip_reduce:
         cap = max(owned // 16, 1 << 20)
         d_id = torch.empty(cap, dtype=torch.int32, device=dev)
         d_pos = torch.empty(cap, dtype=torch.int64, device=dev)
+        d_scan = torch.zeros(3, dtype=torch.int64, device=dev)
         base = rank * args.bytes
-
-        def count_scan(m):
-            """The only cross-GPU step: all-gather of one int64 per rank (NCCL) + exclusive scan."""
-            counts = torch.tensor([m], dtype=torch.int64, device=dev)
-            if world > 1:
-                allc = torch.empty(world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(allc, counts)
-            else:
-                allc = counts
-            offs = torch.cumsum(allc, 0) - allc
-            return int(offs[rank].item()), int(allc.sum().item())
-
-        for _ in range(3):  # warm-up: workspace allocation, NCCL channel, torch kernels
-            m = pf.matchShardFromDeviceReduce64(d_in, owned, total, base, d_id, d_pos)
-            my_off, total_m = count_scan(m)
+        comm = PFACComm.from_torch(0, device=dev) if world > 1 else PFACComm(0, 1, 0)
+        for _ in range(3):  # warm-up: workspace allocation
+            my_off, total_m, m = pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, base, d_id, d_pos)
         barrier()
-        t_call = 0.0
-        t_scan = 0.0
+        # (a) synchronous call, the exclusive offsets returned to the host: one stream sync per step
         t0 = time.perf_counter()
         for _ in range(args.reduce_steps):
-            ta = time.perf_counter()
-            m = pf.matchShardFromDeviceReduce64(d_in, owned, total, base, d_id, d_pos)  # synchronous
-            tb = time.perf_counter()
-            my_off, total_m = count_scan(m)
-            t_call += tb - ta
-            t_scan += time.perf_counter() - tb
+            my_off, total_m, m = pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, base, d_id, d_pos)
         dt = max_over_ranks(time.perf_counter() - t0)
-        t_call = max_over_ranks(t_call)
-        assert m == n_matches, "reduce count %d != dense non-zeros %d" % (m, n_matches)
+        # (b) the same enqueued without a host sync (scan kept on the device), device-timed
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reduce_steps):
+            pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, base, d_id, d_pos, d_scan=d_scan, sync=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_global = max_over_ranks(e0.elapsed_time(e1) / args.reduce_steps)
+        # (c) the kernel without the exchange (plain shard call, synchronous), for the cost of the scan
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.reduce_steps):
+            m2 = pf.matchShardFromDeviceReduce64Cap(d_in, owned, total, base, d_id, d_pos)
+        t_call = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        comm.destroy()
+        assert m == n_matches and m2 == m, "reduce count %d != dense non-zeros %d" % (m, n_matches)
+        assert [int(x) for x in d_scan.cpu().tolist()] == [my_off, total_m, m]
         # spot-check order and content against the dense result of the timed kernel
         pos_local = d_pos[:m] - base
         assert bool((pos_local[1:] > pos_local[:-1]).all().item()), "positions not ascending"
         assert bool((d_out[pos_local] == d_id[:m]).all().item()), "reduce ids differ from dense result"
         reduce_info = {"value": owned * world * args.reduce_steps / dt / 1e9, "unit": UNIT,
-                       "api": "PFAC_matchShardFromDeviceReduce64 (synchronous: includes the count read-back) + "
-                              "count all-gather/exclusive scan",
+                       "api": "PFAC_matchShardFromDeviceReduce64Global (fused match + compaction + in-kernel count "
+                              "exchange and exclusive scan over peer memory; synchronous form: offsets returned to the host)",
+                       "device_timed_value": owned * world / (ms_global * 1e-3) / 1e9,
+                       "device_timed_ms_per_step": ms_global,
                        "call_only_value": owned * world * args.reduce_steps / t_call / 1e9,
                        "ms_per_call": t_call / args.reduce_steps * 1e3,
                        "matches_total": total_m, "rank0_offset": my_off if rank == 0 else None,
-                       "count_scan_ms_per_step": t_scan / args.reduce_steps * 1e3,
-                       "algorithmic_bytes_per_step": int(owned + 12 * m), "steps": args.reduce_steps}
+                       "count_scan_ms_per_step": max(dt / args.reduce_steps * 1e3 - t_call / args.reduce_steps * 1e3, 0.0),
+                       "algorithmic_bytes_per_step": int(owned + 12 * m), "steps": args.reduce_steps,
+                       "roofline_frac": (owned + 12 * m) / (ms_global * 1e-3) / 1e9 / peak}
+        del d_id, d_pos
 
     # ---- reference CPU path beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None
@@ -419,25 +583,38 @@ def main():
         cpu = {"value": sample_n / best / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": "first %.0f MiB of the shard, best of %d passes of PFAC_CPU_OMP_timeDriven, %d threads"
                          % (sample_n / (1 << 20), len(times), threads)}
+        one_n = min(owned, 64 << 20)   # the reference's single-thread PFAC_CPU
+        _, _, best1, _ = cpu_reference(pfile, shard[:one_n], 1, 1)
+        cpu["single_thread"] = {"value": one_n / best1 / 1e9, "unit": UNIT, "cores": 1,
+                                "sample": "first %.0f MiB of the shard, one pass of PFAC_CPU_timeDriven" % (one_n / (1 << 20))}
+
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    pf.destroy()
+
+    # ---- BASELINE configs[4]: the sharded 32 GiB run with the global offset scan ------------------------
+    c5 = None
+    if not args.skip_c5:
+        c5 = run_c5(PFAC, rank, local_rank, world, dev, dist, torch, barrier, max_over_ranks, args.c5_steps,
+                    args.c5_bytes, peak)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": dict(workload_config(args.bytes, world), states=info["num_states"],
-                           hot_depth=info["hot_depth"], hot_buckets=info["hot_buckets"],
-                           first_stage=("hashed 4-gram filter, %d bit(s) per lookup, %d of 262144 bits set" % (info["hashed_filter"], info["hfilt_bits_set"])
-                                        if info["hashed_filter"] else
-                                        "exact 2-gram set, %d of 65536 bits set" % info["pre2_bits_set"]),
-                           matches_per_gpu=n_matches),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reduce": reduce_info,
+            "config": workload_config(args.bytes, world),
+            "table": {"states": info["num_states"], "hot_depth": info["hot_depth"], "hot_buckets": info["hot_buckets"],
+                      "first_stage": ("hashed 4-gram filter, %d bit(s) per lookup, %d of 262144 bits set"
+                                      % (info["hashed_filter"], info["hfilt_bits_set"]) if info["hashed_filter"] else
+                                      "exact 2-gram set, %d of 65536 bits set" % info["pre2_bits_set"]),
+                      "device_bytes": info["device_bytes"], "matches_per_gpu": n_matches},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reduce": reduce_info, "c5": c5,
             "gpu_launches": int(launches), "clocks": clocks,
             "gbps_reference_unit": value * 8.0,
         }
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
-    pf.destroy()
     if world > 1:
         dist.destroy_process_group()
 

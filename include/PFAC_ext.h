@@ -62,6 +62,14 @@ PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char
                                                 long long *d_pos,
                                                 unsigned long long *h_num_matched);
 
+/* the same with the capacity (entries) of d_matched_result / d_pos stated: nothing is stored past it;
+ * *h_num_matched is always the full count, and PFAC_STATUS_INVALID_PARAMETER says it exceeded the
+ * capacity.  (The calls without a capacity follow the reference: buffers of n_owned entries.) */
+PFAC_status_t PFAC_matchShardFromDeviceReduce64Cap(PFAC_handle_t handle, const char *d_inputString,
+                                                   size_t n_owned, size_t n_total, long long pos_base,
+                                                   int *d_matched_result, long long *d_pos, size_t capacity,
+                                                   unsigned long long *h_num_matched);
+
 /* ---- cross-GPU count exchange, in the library and on the device.
  * The only inter-GPU step of the path is an exclusive scan of the per-GPU match counts.  A PFAC_comm
  * holds one small device block per rank (mailbox + this rank's region of a global list) that every
@@ -86,14 +94,16 @@ PFAC_status_t PFAC_commGlobalList(PFAC_comm_t comm, int **d_ids, long long **d_p
 /* host copy of entries [first, first + n) of this rank's list region (synchronous cudaMemcpy) */
 PFAC_status_t PFAC_commReadGlobalList(PFAC_comm_t comm, size_t first, size_t n, int *h_ids, long long *h_pos);
 
-/* PFAC_matchShardFromDeviceReduce64 + the scan, one kernel; collective over the comm.  d_scan (device,
+/* PFAC_matchShardFromDeviceReduce64Cap + the scan, one kernel; collective over the comm.  d_scan (device,
  * 3 words; NULL = kept inside the comm) = {this rank's offset into the global list, total matches, this
  * rank's count}.  h_scan == NULL: asynchronous on the handle's stream, nothing is read back; else the
- * call synchronises once and returns the same three words. */
+ * call synchronises once and returns the same three words (PFAC_STATUS_INVALID_PARAMETER when this
+ * rank's count exceeded `capacity`, the entries d_matched_result / d_pos hold). */
 PFAC_status_t PFAC_matchShardFromDeviceReduce64Global(PFAC_handle_t handle, PFAC_comm_t comm,
                                                       const char *d_inputString, size_t n_owned, size_t n_total,
                                                       long long pos_base, int *d_matched_result, long long *d_pos,
-                                                      unsigned long long *d_scan, unsigned long long *h_scan);
+                                                      size_t capacity, unsigned long long *d_scan,
+                                                      unsigned long long *h_scan);
 /* optional second step, collective: every rank stores its run into rank dst_rank's list region at its
  * scanned offset (P2P stores over NVLink; count and offset are read from d_scan on the device), dst_rank
  * waits on the device until all runs have landed.  The list is then PFAC_commGlobalList(dst)[0, total). */
@@ -131,6 +141,10 @@ typedef struct {
     int root_fanout;       /* valid first bytes */
     int hashed_filter;     /* 1 / 2: the per-position test is the hashed 4-gram filter (8192 words), 1 or 2 bits per lookup */
     int hfilt_bits_set;    /* of 262144 */
+    int code_shift;        /* b = 2 with an arithmetic symbol code: code = (byte >> code_shift) & 3; else -1.  With
+                              hashed_filter == 2 and code_bits == 2 the first stage hashes ten symbols (20 bits):
+                              word ((x * 0x9E3779B1) >> 19) & 8191, bits 31 - ((x * 0x85EBCA6B) >> 27) and
+                              31 - ((x * 0xC2B2AE35) >> 27), products mod 2^32 */
     size_t device_bytes;   /* total bytes uploaded */
 } PFAC_tableInfo_t;
 

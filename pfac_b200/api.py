@@ -63,7 +63,8 @@ class TableInfo(ctypes.Structure):
                 ("hash_mul", ctypes.c_uint), ("hot_max_probe", ctypes.c_int),
                 ("cold_max_probe", ctypes.c_int), ("pre2_bits_set", ctypes.c_int),
                 ("root_fanout", ctypes.c_int), ("hashed_filter", ctypes.c_int),
-                ("hfilt_bits_set", ctypes.c_int), ("device_bytes", ctypes.c_size_t)]
+                ("hfilt_bits_set", ctypes.c_int), ("code_shift", ctypes.c_int),
+                ("device_bytes", ctypes.c_size_t)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -143,7 +144,8 @@ def load_library():
         "PFAC_commDestroy": [vp],
         "PFAC_commGlobalList": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(sz)],
         "PFAC_commReadGlobalList": [vp, sz, sz, vp, vp],
-        "PFAC_matchShardFromDeviceReduce64Global": [vp, vp, vp, sz, sz, ctypes.c_longlong, vp, vp, vp, vp],
+        "PFAC_matchShardFromDeviceReduce64Global": [vp, vp, vp, sz, sz, ctypes.c_longlong, vp, vp, sz, vp, vp],
+        "PFAC_matchShardFromDeviceReduce64Cap": [vp, vp, sz, sz, ctypes.c_longlong, vp, vp, sz, ctypes.POINTER(ull)],
         "PFAC_commGatherRuns": [vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int],
         "PFAC_mgpuCreate": [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int],
         "PFAC_mgpuDestroy": [vp],
@@ -304,13 +306,24 @@ class PFAC:
                "PFAC_matchShardFromDeviceReduce64")
         return n.value
 
+    def matchShardFromDeviceReduce64Cap(self, d_input, n_owned, n_total, pos_base, d_result, d_pos64):
+        """Shard reduce with the buffers' capacity stated (entries of d_result): nothing is stored past it."""
+        n = ctypes.c_ulonglong(0)
+        cap = min(int(d_result.numel()), int(d_pos64.numel()))
+        _check(self._L.PFAC_matchShardFromDeviceReduce64Cap(self._h, _ptr(d_input), n_owned, n_total, pos_base,
+                                                            _ptr(d_result), _ptr(d_pos64), cap, ctypes.byref(n)),
+               "PFAC_matchShardFromDeviceReduce64Cap")
+        return n.value
+
     def matchShardFromDeviceReduce64Global(self, comm, d_input, n_owned, n_total, pos_base, d_result, d_pos64,
                                            d_scan=None, sync=True):
         """Shard reduce + the cross-GPU exclusive scan of the counts in one kernel (collective over
-        `comm`).  sync=True returns (offset, total, count); sync=False leaves them in d_scan (device)."""
+        `comm`).  sync=True returns (offset, total, count); sync=False leaves them in d_scan (device).
+        The capacity passed to the library is the size of d_result / d_pos64."""
         h = (ctypes.c_ulonglong * 3)()
+        cap = min(int(d_result.numel()), int(d_pos64.numel())) if hasattr(d_result, "numel") else (1 << 62)
         _check(self._L.PFAC_matchShardFromDeviceReduce64Global(
-            self._h, comm._c, _ptr(d_input), n_owned, n_total, pos_base, _ptr(d_result), _ptr(d_pos64),
+            self._h, comm._c, _ptr(d_input), n_owned, n_total, pos_base, _ptr(d_result), _ptr(d_pos64), cap,
             _ptr(d_scan), ctypes.cast(h, ctypes.c_void_p) if sync else None),
             "PFAC_matchShardFromDeviceReduce64Global")
         return (int(h[0]), int(h[1]), int(h[2])) if sync else None
@@ -571,7 +584,7 @@ class TableCompiler:
             "best2": arr(p2[1], max(info["pre2_bits_set"], 1) * 4 if info["has_best2"] else 0, np.uint32),
             "chk2": arr(p2[2], max(info["pre2_bits_set"], 1) * 2 if info["has_chk2"] else 0, np.uint16),
             "hfilt": arr(pf, 32768 if info["hashed_filter"] else 0, np.uint32),
-            "hfilt_k": info["hashed_filter"],
+            "hfilt_k": info["hashed_filter"], "code_shift": info["code_shift"],
             "code_bits": info["code_bits"], "gram_len": info["gram_len"],
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],
         }

@@ -396,6 +396,7 @@ PFAC_status_t uploadLayout(PFAC_handle_t h, const pfac::DeviceLayout& L, pfac::D
     t.hasBest2 = !L.best2.empty();
     t.codeBits = L.codeBits;
     t.gramLen = L.gramLen;
+    t.codeShift = L.codeShift;
     PFAC_UP(hot, const uint4*, L.hot.data(), L.hot.size() * 4)
     PFAC_UP(cold, const uint4*, L.cold.data(), L.cold.size() * 4)
     PFAC_UP(chains, const uint4*, L.chains.data(), L.chains.size() * 4)
@@ -522,22 +523,23 @@ PFAC_status_t ensureReduceWorkspace(PFAC_handle_t h, size_t words) {
 // scan run inside the same kernel.
 PFAC_status_t reduceShardEnqueue(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
                                  long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
-                                 const pfac::CommLaunch* comm) {
+                                 const pfac::CommLaunch* comm, unsigned long long capacity = ~0ull) {
     const size_t words = pfac::reduceWorkspaceWords(n_owned);
     PFAC_status_t st = ensureReduceWorkspace(h, words);
     if (st != PFAC_STATUS_SUCCESS) return st;
     if (cudaMemsetAsync(h->d_ws, 0, words * 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     if (cudaMemsetAsync(h->d_total, 0, 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     return cudaToStatus(pfac::launchMatchReduce(h->tableReduce, h->launch, d_in, n_owned, n_total, pos_base, d_id,
-                                                d_pos, pos64, h->d_ws, h->d_park, h->d_total, stream, comm, h->h_total + 8));
+                                                d_pos, pos64, h->d_ws, h->d_park, h->d_total, stream, comm, h->h_total + 8,
+                                                capacity));
 }
 
 // one fused match+compaction over a device shard; synchronous (returns the count)
 PFAC_status_t reduceShard(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
                           long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
-                          unsigned long long* count) {
+                          unsigned long long* count, unsigned long long capacity = ~0ull) {
     std::lock_guard<std::mutex> lock(h->mu);
-    PFAC_status_t st = reduceShardEnqueue(h, d_in, n_owned, n_total, pos_base, d_id, d_pos, pos64, stream, nullptr);
+    PFAC_status_t st = reduceShardEnqueue(h, d_in, n_owned, n_total, pos_base, d_id, d_pos, pos64, stream, nullptr, capacity);
     if (st != PFAC_STATUS_SUCCESS) return st;
     if (cudaMemcpyAsync(h->h_total, h->d_total, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
@@ -1003,6 +1005,23 @@ PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char
                        d_id, d_pos, true, handle->stream, h_num);
 }
 
+// the same with the capacity of d_id / d_pos stated: nothing is stored past it, *h_num is the full count
+// (larger than `capacity` = the caller's buffers were too small: PFAC_STATUS_INVALID_PARAMETER)
+PFAC_status_t PFAC_matchShardFromDeviceReduce64Cap(PFAC_handle_t handle, const char* d_in, size_t n_owned,
+                                                   size_t n_total, long long pos_base, int* d_id, long long* d_pos,
+                                                   size_t capacity, unsigned long long* h_num) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    if (!d_in || !h_num || !d_pos || !d_id) return PFAC_STATUS_INVALID_PARAMETER;
+    if (n_total < n_owned) return PFAC_STATUS_INVALID_PARAMETER;
+    *h_num = 0;
+    if (n_owned == 0) return PFAC_STATUS_SUCCESS;
+    PFAC_status_t st = reduceShard(handle, reinterpret_cast<const unsigned char*>(d_in), n_owned, n_total, pos_base,
+                                   d_id, d_pos, true, handle->stream, h_num, capacity);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    return *h_num > capacity ? PFAC_STATUS_INVALID_PARAMETER : PFAC_STATUS_SUCCESS;
+}
+
 PFAC_status_t PFAC_matchFromDeviceReduce64(PFAC_handle_t handle, const char* d_in, size_t size, int* d_id,
                                            long long* d_pos, unsigned long long* h_num) {
     return PFAC_matchShardFromDeviceReduce64(handle, d_in, size, size, 0, d_id, d_pos, h_num);
@@ -1294,7 +1313,7 @@ PFAC_status_t PFAC_commReadGlobalList(PFAC_comm_t comm, size_t first, size_t n, 
 // follow on the handle's stream); else one stream synchronisation and the same three words on the host.
 PFAC_status_t PFAC_matchShardFromDeviceReduce64Global(PFAC_handle_t handle, PFAC_comm_t comm, const char* d_in,
                                                       size_t n_owned, size_t n_total, long long pos_base, int* d_id,
-                                                      long long* d_pos, unsigned long long* d_scan,
+                                                      long long* d_pos, size_t capacity, unsigned long long* d_scan,
                                                       unsigned long long* h_scan) {
     if (!handle) return PFAC_STATUS_INVALID_HANDLE;
     if (!comm) return PFAC_STATUS_INVALID_HANDLE;
@@ -1311,7 +1330,7 @@ PFAC_status_t PFAC_matchShardFromDeviceReduce64Global(PFAC_handle_t handle, PFAC
     cl.rank = comm->rank;
     cl.epoch = ++comm->epoch;
     PFAC_status_t st = reduceShardEnqueue(handle, reinterpret_cast<const unsigned char*>(d_in), n_owned, n_total, pos_base,
-                                          d_id, d_pos, true, handle->stream, &cl);
+                                          d_id, d_pos, true, handle->stream, &cl, capacity);
     if (st != PFAC_STATUS_SUCCESS) return st;
     if (h_scan) {
         if (cudaMemcpyAsync(comm->h_scan, cl.scan, 24, cudaMemcpyDeviceToHost, handle->stream) != cudaSuccess)
@@ -1320,6 +1339,7 @@ PFAC_status_t PFAC_matchShardFromDeviceReduce64Global(PFAC_handle_t handle, PFAC
         h_scan[0] = comm->h_scan[0];
         h_scan[1] = comm->h_scan[1];
         h_scan[2] = comm->h_scan[2];
+        if (h_scan[2] > capacity) return PFAC_STATUS_INVALID_PARAMETER;   // the run did not fit d_id / d_pos
     }
     return PFAC_STATUS_SUCCESS;
 }
@@ -1532,6 +1552,7 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->root_fanout = L.rootFanout;
     info->hashed_filter = L.hfilt.empty() ? 0 : L.hfiltK;
     info->hfilt_bits_set = L.hfiltBitsSet;
+    info->code_shift = L.codeShift;
     info->device_bytes = L.deviceBytes();
 }
 

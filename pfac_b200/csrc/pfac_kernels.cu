@@ -61,6 +61,7 @@ struct KParams {
     int* out;                   // dense
     int* out_id;                // reduce
     void* out_pos;              // reduce
+    unsigned long long out_cap; // reduce: entries out_id / out_pos hold (matches beyond it are counted, not stored)
     long long pos_base;
     unsigned long long* desc;
     unsigned long long* park;   // reduce: per-warp spill rings
@@ -92,6 +93,7 @@ struct KParams {
     int next2_hot;
     int chains_hot;
     int num_final;
+    int code_shift;
     int halo;                   // staged halo, multiple of 16, >= 16
     int in_aligned;             // in is 16-byte aligned
     int out_aligned;            // out is 16-byte aligned
@@ -118,6 +120,7 @@ struct Tables {
     const unsigned char* tails; // smem or global
     uint32_t hot_buckets, cold_buckets, mul;
     int hot_depth, num_final;
+    int code_shift;             // 2-bit alphabets: code = (byte >> code_shift) & 3 (hashed 10-mer first stage)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -347,6 +350,7 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
     t.mul = p.mul;
     t.hot_depth = p.hot_depth;
     t.num_final = p.num_final;
+    t.code_shift = p.code_shift;
     return t;
 }
 
@@ -366,6 +370,7 @@ struct FilterView {
     const unsigned short* rank2;
     const unsigned short* chk2;
     const unsigned char* lut;
+    int code_shift;
 };
 template <typename TT>
 __device__ __forceinline__ bool second_stage(const TT& T, uint32_t idx, uint32_t word, uint32_t next_byte) {
@@ -383,6 +388,30 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
     constexpr bool two_stage = FILT == 1;  // second stage compiled in only for the tables that use it
     cand = 0;
     slow = 0;
+    if (CODE == 2 && FILT == 4) {
+        // hashed 10-mer first stage (pfac_table.h): 25 text bytes -> 25 two-bit codes, four bytes at a time
+        // (shift, mask, one multiply gathers the four 2-bit fields into a byte), then per position a
+        // 20-bit window of the code stream, one filter word, two bits of it.  Bytes outside the
+        // alphabet alias to some code and bytes past the input are zeros: the filter stays free of false
+        // negatives either way (short patterns set all their continuations) and the walker re-checks.
+        const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
+        const uint2 u = *reinterpret_cast<const uint2*>(inb + lb + 16);
+        const uint32_t w6 = *reinterpret_cast<const uint32_t*>(inb + lb + 24);
+        const int sh = T.code_shift;
+        auto code4 = [&](uint32_t w) -> uint32_t { return (((w >> sh) & 0x03030303u) * 0x01041040u) >> 24; };
+        const uint32_t lo = code4(v.x) | (code4(v.y) << 8) | (code4(v.z) << 16) | (code4(v.w) << 24);  // symbols 0..15
+        const uint32_t hi = code4(u.x) | (code4(u.y) << 8) | (code4(w6) << 16);                       // symbols 16..27
+#pragma unroll
+        for (int q = 15; q >= 0; q--) {
+            const uint32_t x = ((q == 0) ? lo : __funnelshift_r(lo, hi, 2 * q)) & 0xFFFFFu;
+            const uint32_t hw = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const unsigned char*>(T.hfilt) + (((x * kHashFilterMul) >> 17) & static_cast<uint32_t>(kHashFilterWords * 4 - 4)));
+            const uint32_t rot = __funnelshift_l(hw, hw, (x * kHashFilterMul2) >> 27) &
+                                 __funnelshift_l(hw, hw, (x * kHashFilterMul3) >> 27);
+            cand = __funnelshift_l(rot, cand, 1);
+        }
+        return;
+    }
     if (CODE == 8) {
         uint32_t w[5];
         const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
@@ -507,17 +536,25 @@ __device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* 
     if (active) {
         pl = qe & (kSlowFlag - 1u);
         limit = tile_rem - pl;                           // real input bytes from this position
-        if (!(qe & kSlowFlag)) {
-            // prefilter index again (survivors are few), its rank, and the direct tables
-            uint32_t idx;
-            if (CODE == 8) {
-                idx = inb[pl] | (static_cast<uint32_t>(inb[pl + 1]) << 8);  // pl+1 is always staged
-            } else {
-                idx = 0;
+        // prefilter index again (survivors are few), its rank, and the direct tables
+        uint32_t idx;
+        bool generic = (qe & kSlowFlag) != 0;
+        if (CODE == 8) {
+            idx = inb[pl] | (static_cast<uint32_t>(inb[pl + 1]) << 8);  // pl+1 is always staged
+        } else {
+            idx = 0;
+            uint32_t bad = 0;
 #pragma unroll
-                for (int i = 0; i < K; i++)
-                    idx |= (T.lut[inb[pl + i]] & ((1u << CODE) - 1u)) << (CODE * i);
+            for (int i = 0; i < K; i++) {
+                const uint32_t e = T.lut[inb[pl + i]];
+                idx |= (e & ((1u << CODE) - 1u)) << (CODE * i);
+                bad |= e;
             }
+            // survivors of the hashed first stage were not screened for bytes outside the alphabet or
+            // windows cut off by the end of the input: those walk from the root row
+            if (HASHED && ((bad & 0x80u) || limit < K)) generic = true;
+        }
+        if (!generic) {
             const uint32_t word = T.pre2[idx >> 5];
             const uint32_t rank = T.rank2[idx >> 5] + __popc(word & ~(0xFFFFFFFFu >> (idx & 31u)));
             // survivors of the hashed filter may hold any bytes: the exact K-gram bit comes first
@@ -732,7 +769,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
         const int lb = lane * kPosPerThread;
         uint32_t cand, slow;
         prefilter16<CODE, FILT>(inb, lb, T, cand, slow);
-        clip_windows<CODE>(tile_rem, lb, cand, slow);
+        if (FILT != 4) clip_windows<CODE>(tile_rem, lb, cand, slow);
         int valid = kWarpTile;
         if (!full) {  // tail tile: drop positions we do not own
             valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
@@ -902,7 +939,7 @@ __device__ __forceinline__ uint32_t block_survivors(const TT& T, const unsigned 
     const int lb = lane * kPosPerThread;
     uint32_t cand;
     prefilter16<CODE, FILT>(inb + blk * kWarpTile, lb, T, cand, slow);
-    clip_windows<CODE>(tile_rem - blk * kWarpTile, lb, cand, slow);
+    if (FILT != 4) clip_windows<CODE>(tile_rem - blk * kWarpTile, lb, cand, slow);  // FILT 4: the walker sorts those out
     const int valid = tile_valid - blk * kWarpTile;
     if (valid < kWarpTile) {
         int nv = valid - lb;
@@ -1062,7 +1099,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     unsigned char* s_in = mine + kRedWarpFixed;
     // this warp's spill ring in global memory (L2-resident): entry = id | position in tile << 32
     unsigned long long* spill = p.park + (static_cast<size_t>(b) * kRedMatchers + warp) * kSpillCap;
-    const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut};
+    const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut, T.code_shift};
 
     auto issue_load = [&](uint32_t t, int st) {
         if (t < p.bulk_tiles) {
@@ -1088,6 +1125,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
         }
     };
     auto store_pair = [&](unsigned long long at, int id, long long gpos) {
+        if (at >= p.out_cap) return;   // caller-stated capacity: counted, not stored
         p.out_id[at] = id;
         if (POS64) reinterpret_cast<long long*>(p.out_pos)[at] = gpos;
         else reinterpret_cast<int*>(p.out_pos)[at] = static_cast<int>(gpos);
@@ -1404,6 +1442,7 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
     p.hot_depth = t.hotDepth;
     p.chains_hot = t.chainsHot ? 1 : 0;
     p.num_final = t.numFinal;
+    p.code_shift = t.codeShift;
     p.halo = halo;
     p.in_aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     return p;
@@ -1458,10 +1497,14 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
             else kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 0> : pfac_dense_kernel<2, 8, 0>;
             break;
         case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4, 0> : pfac_dense_kernel<2, 4, 0>; break;
-        case 2: kernel = (nst == 3) ? pfac_dense_kernel<3, 2, 0> : pfac_dense_kernel<2, 2, 0>; break;
+        case 2:  // hashed 10-mer first stage when the table compiler built one (arithmetic symbol code)
+            if (t.hfiltBytes) kernel = (nst == 3) ? pfac_dense_kernel<3, 2, 4> : pfac_dense_kernel<2, 2, 4>;
+            else kernel = (nst == 3) ? pfac_dense_kernel<3, 2, 0> : pfac_dense_kernel<2, 2, 0>;
+            break;
         default: return cudaErrorInvalidValue;
     }
-    if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
+    if (t.codeBits == 4 && filt) return cudaErrorInvalidValue;
+    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
@@ -1476,7 +1519,7 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
                               size_t n_owned, size_t n_total, long long pos_base, int* out_id,
                               void* out_pos, bool pos64, unsigned long long* desc, unsigned long long* park,
                               unsigned long long* d_total, cudaStream_t stream, const CommLaunch* comm,
-                              unsigned long long* dbg) {
+                              unsigned long long* dbg, unsigned long long out_cap) {
     if (n_owned == 0) {
         if (!comm) return cudaSuccess;
         KParams p{};   // nothing to match: the count exchange alone
@@ -1494,6 +1537,7 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.out_id = out_id;
     p.out_pos = out_pos;
+    p.out_cap = out_cap;
     p.pos_base = pos_base;
     p.desc = desc;
     p.park = park;
@@ -1525,10 +1569,14 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
             else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 0> : (const void*)pfac_reduce_kernel<false, 8, 0>;
             break;
         case 4: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 4, 0> : (const void*)pfac_reduce_kernel<false, 4, 0>; break;
-        case 2: kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, 0> : (const void*)pfac_reduce_kernel<false, 2, 0>; break;
+        case 2:
+            if (t.hfiltBytes) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, 4> : (const void*)pfac_reduce_kernel<false, 2, 4>;
+            else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, 0> : (const void*)pfac_reduce_kernel<false, 2, 0>;
+            break;
         default: return cudaErrorInvalidValue;
     }
-    if (filt && t.codeBits != 8) return cudaErrorInvalidValue;
+    if (t.codeBits == 4 && filt) return cudaErrorInvalidValue;
+    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kRedSlots - 1) / kRedSlots;

@@ -33,6 +33,7 @@ struct DeviceTable {
     bool hasBest2 = false;
     int codeBits = 8;                 // bits per symbol of the prefilter index
     int gramLen = 2;                  // symbols covered by the prefilter
+    int codeShift = -1;               // 2-bit alphabets with a hashed first stage: code = (byte >> codeShift) & 3
     const uint4* hot = nullptr;       // hotBuckets (copied into shared memory by each CTA)
     const uint4* cold = nullptr;      // coldBuckets (read through L1/L2)
     const uint4* chains = nullptr;    // chain records (16 B each)
@@ -78,13 +79,14 @@ struct CommLaunch {
 
 // Fused match + ordered compaction.  desc: reduceWorkspaceWords(n_owned) zeroed uint64 words; park:
 // reduceParkWords(cfg) uint64 words; dbg: 8 zeroed host-mapped words where a wait that never ends
-// reports before the kernel traps (nullptr: trap without a report).
+// reports before the kernel traps (nullptr: trap without a report).  out_cap: entries the output
+// arrays hold; matches beyond it are counted but not stored.
 // d_total: one uint64 receiving the match count.  pos64 selects long long vs int positions.
 cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                               size_t n_owned, size_t n_total, long long pos_base, int* out_id,
                               void* out_pos, bool pos64, unsigned long long* desc, unsigned long long* park,
                               unsigned long long* d_total, cudaStream_t stream, const CommLaunch* comm = nullptr,
-                              unsigned long long* dbg = nullptr);
+                              unsigned long long* dbg = nullptr, unsigned long long out_cap = ~0ull);
 
 // Copy this rank's run (count and offset read from `scan` on the device) into the list on the
 // destination rank and raise `placed`; the destination waits for all ranks with launchWaitPlaced.

@@ -285,13 +285,33 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
     L.codeBits = (alphabet <= 4) ? 2 : (alphabet <= 16) ? 4 : 8;
     L.gramLen = 16 / L.codeBits;
     const int K = L.gramLen, B = L.codeBits;
-    uint8_t byteOfCode[kCharSet];
+    int byteOfCode[kCharSet];   // -1: code not in use
+    std::fill(byteOfCode, byteOfCode + kCharSet, -1);
     int ncodes = 0;
-    for (int c = 0; c < kCharSet; c++) {
-        if (B == 8) { L.lut[c] = uint8_t(c); byteOfCode[c] = uint8_t(c); continue; }  // identity
-        if (used[c]) { byteOfCode[ncodes] = uint8_t(c); L.lut[c] = uint8_t(ncodes++); }
-        else L.lut[c] = 0x80;
+    // 2-bit alphabets: when two bits of the byte itself tell the symbols apart (ACGT and acgt: bits 1-2),
+    // those bits ARE the code, and the kernels code four text bytes at a time with a shift, a mask and a
+    // multiply instead of one table lookup per byte (the hashed 10-mer first stage below needs that)
+    L.codeShift = -1;
+    if (B == 2 && alphabet > 0) {
+        for (int sh = 0; sh <= 6 && L.codeShift < 0; sh++) {
+            bool seen[4] = {false, false, false, false}, ok = true;
+            for (int c = 0; c < kCharSet && ok; c++)
+                if (used[c]) { ok = !seen[(c >> sh) & 3]; seen[(c >> sh) & 3] = true; }
+            if (ok) L.codeShift = sh;
+        }
     }
+    for (int c = 0; c < kCharSet; c++) {
+        if (B == 8) { L.lut[c] = uint8_t(c); byteOfCode[c] = c; continue; }  // identity
+        if (!used[c]) { L.lut[c] = 0x80; continue; }
+        if (L.codeShift >= 0) {
+            L.lut[c] = uint8_t((c >> L.codeShift) & 3);
+            byteOfCode[L.lut[c]] = c;
+        } else {
+            byteOfCode[ncodes] = c;
+            L.lut[c] = uint8_t(ncodes++);
+        }
+    }
+    if (L.codeShift >= 0) ncodes = 4;   // codes may have gaps: byteOfCode = -1 there
     if (B == 8) ncodes = 256;
 
     // ---- hash edges with chain compression.  A run of >= kMinChain non-final single-child
@@ -364,7 +384,7 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
             if (dgt >= ncodes) { dgt = -1; depthNow--; continue; }
             idxNow = (idxNow & ((1u << (B * depthNow)) - 1u)) | (uint32_t(dgt) << (B * depthNow));
             const Frame& f = stack[size_t(depthNow)];
-            const Edge* e = (f.state >= 0) ? findEdge(f.state, byteOfCode[dgt]) : nullptr;
+            const Edge* e = (f.state >= 0 && byteOfCode[dgt] >= 0) ? findEdge(f.state, byteOfCode[dgt]) : nullptr;
             if (!e) {
                 // the walk dies here: every completion of this prefix reports f.best
                 if (f.best != 0) {
@@ -487,6 +507,51 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
         }
     }
 
+    // hashed 10-mer first stage for 2-bit alphabets with an arithmetic code (DNA): the exact 8-mer set of
+    // 5,000 patterns passes 7.3 % of all positions (4,794 of 65,536 8-mers), four walker batches per
+    // 1,536-position tile; ten symbols hashed into the same 256-Kbit table with two bits per gram (a
+    // blocked Bloom filter) pass the true matches plus well under 1 %.  x = the ten 2-bit codes, symbol i
+    // at bits 2i; word (x * kHashFilterMul) >> 19, bits 31 - ((x * kHashFilterMul2) >> 27) and
+    // 31 - ((x * kHashFilterMul3) >> 27), products taken mod 2^32.  A pattern shorter than ten symbols
+    // sets the bits of all its 4^(10-len) continuations, so neither bytes past the end of the input nor
+    // bytes outside the alphabet (which alias to some code) can hide a match; the walker re-checks
+    // survivors exactly (lut, pre2, next2) and takes the generic path when a window holds such a byte.
+    if (B == 2 && L.codeShift >= 0 && !frontier.empty() && hotBudgetBytes >= hfiltBytes && filterPolicy != kFilterExact) {
+        L.hfilt.assign(size_t(kHashFilterWords), 0u);
+        L.hfiltK = 2;
+        auto setGram = [&](uint32_t x) {
+            const uint32_t w = (uint32_t(x * kHashFilterMul) >> 19) & uint32_t(kHashFilterWords - 1);
+            L.hfilt[w] |= (0x80000000u >> (uint32_t(x * kHashFilterMul2) >> 27)) |
+                          (0x80000000u >> (uint32_t(x * kHashFilterMul3) >> 27));
+        };
+        struct Node { int state; uint32_t x; int d; };
+        std::vector<Node> todo;
+        todo.push_back(Node{m.initialState, 0u, 0});
+        while (!todo.empty()) {
+            const Node f = todo.back();
+            todo.pop_back();
+            for (const Edge& e : out[size_t(f.state)]) {
+                const uint32_t x = f.x | (uint32_t(L.lut[e.ch] & 3u) << (2 * f.d));
+                const int d = f.d + 1;
+                if (d == kDnaGram) { setGram(x); continue; }
+                if (isFinal(e.next)) {  // a pattern shorter than the gram: whatever follows must pass
+                    const uint32_t rest = 1u << (2 * (kDnaGram - d));
+                    for (uint32_t t = 0; t < rest; t++) setGram(x | (t << (2 * d)));
+                }
+                if (!out[size_t(e.next)].empty()) todo.push_back(Node{e.next, x, d});
+            }
+        }
+        L.hfiltBitsSet = 0;
+        for (uint32_t w : L.hfilt) L.hfiltBitsSet += __builtin_popcount(w);
+        if (L.hfiltBitsSet > kHashFilterWords * 32 / 2 && filterPolicy != kFilterHashed) {
+            L.hfilt.clear();   // saturated (many very short patterns): the exact 8-mer stage does better
+            L.hfiltK = 0;
+            L.hfiltBitsSet = 0;
+        } else {
+            hotBudgetBytes -= hfiltBytes;
+        }
+    }
+
     // deeper transitions (source depth >= K): hash rows, hot by depth
     for (size_t qi = 0; qi < sources.size(); qi++) {
         const int s = sources[qi];
@@ -594,7 +659,7 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
 namespace {
 
 constexpr char kFileMagic[8] = {'P', 'F', 'A', 'C', 'B', '2', '0', '0'};
-constexpr uint32_t kFileVersion = 3;  // bump whenever Machine / DeviceLayout or their meaning change
+constexpr uint32_t kFileVersion = 4;  // bump whenever Machine / DeviceLayout or their meaning change
 
 struct Writer {
     std::string buf;
@@ -687,7 +752,7 @@ void getMachine(Reader& r, Machine& m) {
 void putLayout(Writer& w, const DeviceLayout& L) {
     w.raw(L.root, sizeof(L.root));
     w.raw(L.lut, sizeof(L.lut));
-    w.pod(L.codeBits); w.pod(L.gramLen);
+    w.pod(L.codeBits); w.pod(L.gramLen); w.pod(L.codeShift);
     w.vec(L.pre2); w.vec(L.rank2); w.vec(L.next2); w.vec(L.best2); w.vec(L.chk2); w.vec(L.hfilt);
     w.pod(L.hfiltK); w.pod(L.hfiltBitsSet);
     w.pod<uint8_t>(L.next2Hot);
@@ -701,7 +766,7 @@ void putLayout(Writer& w, const DeviceLayout& L) {
 void getLayout(Reader& r, DeviceLayout& L) {
     r.raw(L.root, sizeof(L.root));
     r.raw(L.lut, sizeof(L.lut));
-    r.pod(L.codeBits); r.pod(L.gramLen);
+    r.pod(L.codeBits); r.pod(L.gramLen); r.pod(L.codeShift);
     r.vec(L.pre2); r.vec(L.rank2); r.vec(L.next2); r.vec(L.best2); r.vec(L.chk2); r.vec(L.hfilt);
     r.pod(L.hfiltK); r.pod(L.hfiltBitsSet);
     uint8_t b = 0;
@@ -759,7 +824,12 @@ bool validLayout(const DeviceLayout& L, const Machine& m) {
     if (L.next2.size() != std::max<size_t>(bits, 1)) PFAC_INVALID;
     if (!L.best2.empty() && L.best2.size() != L.next2.size()) PFAC_INVALID;
     if (!L.chk2.empty() && L.chk2.size() != L.next2.size()) PFAC_INVALID;
-    if (!L.hfilt.empty() && (L.hfilt.size() != size_t(kHashFilterWords) || L.hfiltK < 1 || L.hfiltK > 2 || L.codeBits != 8)) PFAC_INVALID;
+    if (L.codeShift < -1 || L.codeShift > 6 || (L.codeShift >= 0 && L.codeBits != 2)) PFAC_INVALID;
+    if (!L.hfilt.empty() && (L.hfilt.size() != size_t(kHashFilterWords) || L.hfiltK < 1 || L.hfiltK > 2 ||
+                             !(L.codeBits == 8 || (L.codeBits == 2 && L.codeShift >= 0 && L.hfiltK == 2)))) PFAC_INVALID;
+    if (L.codeShift >= 0)   // the kernels code text bytes arithmetically: lut must agree for every alphabet byte
+        for (int c = 0; c < kCharSet; c++)
+            if (!(L.lut[c] & 0x80) && L.lut[c] != uint8_t((c >> L.codeShift) & 3)) PFAC_INVALID;
     if (L.hot.size() != size_t(L.hotBuckets) * 4 || L.cold.size() != size_t(L.coldBuckets) * 4 || L.coldBuckets == 0) PFAC_INVALID;
     if ((L.chains.size() & 3) || (L.tails.size() & 15) || L.hotDepth < 1) PFAC_INVALID;
     if (L.numChains < 0 || size_t(L.numChains) > L.chains.size() / 4) PFAC_INVALID;

@@ -95,6 +95,7 @@ constexpr uint32_t kHashFilterMul = 0x9E3779B1u;
 constexpr uint32_t kHashFilterMul2 = 0x85EBCA6Bu;
 constexpr uint32_t kHashFilterMul3 = 0xC2B2AE35u;
 constexpr int kHashFilterWords = 8192;           // 32 KB of shared memory
+constexpr int kDnaGram = 10;                     // symbols hashed by the first stage of 2-bit alphabets
 enum FilterPolicy { kFilterAuto = 0, kFilterExact = 1, kFilterHashed = 2 };
 
 struct DeviceLayout {
@@ -102,6 +103,7 @@ struct DeviceLayout {
     uint8_t lut[kCharSet];           // symbol code | 0x80 if the byte occurs in no pattern
     int codeBits = 8;                // b
     int gramLen = 2;                 // K = 16 / b
+    int codeShift = -1;              // b = 2 only: code = (byte >> codeShift) & 3 for every alphabet byte, -1 = lut only
     std::vector<uint32_t> pre2;      // 2048 words, bit-reversed within each word
     std::vector<uint16_t> rank2;     // 2048 prefix popcounts
     std::vector<uint32_t> next2;     // one entry per set bit, in idx order

@@ -31,8 +31,48 @@ CONFIGS = {
 }
 
 
+def _patterns_an():
+    """a, aa, ..., a^32 on top of the C2 dictionary: over the text a^n every position walks 32 steps and
+    reports a^32 (the reference's own worst-case micro-benchmark, doc/PFAC_hash_draft.pdf p.9 Table 4)."""
+    return [b"a" * k for k in range(1, 33)] + synth.patterns_c2(1000)
+
+
+# adversarial texts (VERDICT r1 item 7; the reference publishes regular AND worst-case throughput):
+#   wprefix  the C2 dictionary over a text made of concatenated pattern prefixes (half to all-but-one
+#            byte of a random pattern each): every piece passes the first stage and walks deep, few match
+#   wan      the text a^n against a^1..a^32: every position matches after the longest possible walk
+CONFIGS.update({
+    "wprefix_dense": dict(patterns=lambda: synth.patterns_c2(1000), kind="pool:prefix", seed=synth.SEED_BASE + 6,
+                          bytes=GIB, every=0, api="dense"),
+    "wprefix_reduce": dict(patterns=lambda: synth.patterns_c2(1000), kind="pool:prefix", seed=synth.SEED_BASE + 6,
+                           bytes=GIB, every=0, api="reduce"),
+    "wan_dense": dict(patterns=_patterns_an, kind="pool:an", seed=synth.SEED_BASE + 7, bytes=GIB, every=0, api="dense"),
+    "wan_reduce": dict(patterns=_patterns_an, kind="pool:an", seed=synth.SEED_BASE + 7, bytes=GIB, every=0, api="reduce"),
+})
+
+
+def adversarial_pool(kind, pats, seed, size=4 << 20):
+    """`size` bytes of adversarial text (the stream is this pool repeated)."""
+    if kind == "pool:an":
+        return np.full(size, ord("a"), dtype=np.uint8)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pieces, have = [], 0
+    while have < size:
+        p = pats[int(rng.integers(0, len(pats)))]
+        cut = int(rng.integers(max(len(p) // 2, 1), max(len(p), 2)))
+        pieces.append(p[:cut])
+        have += cut
+    return np.frombuffer(b"".join(pieces)[:size], dtype=np.uint8).copy()
+
+
 def device_text(cfg, start, n, total_len, pats, device, out=None):
     """Stream bytes [start, start + n) of the config's text as a uint8 tensor on `device`."""
+    if cfg["kind"].startswith("pool:"):
+        import torch
+        pool = adversarial_pool(cfg["kind"], pats, cfg["seed"])
+        d_pool = torch.from_numpy(pool).to(device)
+        reps = (start % pool.size + n + pool.size - 1) // pool.size
+        return d_pool.repeat(reps)[start % pool.size:start % pool.size + n].contiguous()
     from workloads import devgen
     return devgen.make_text(cfg["kind"], cfg["seed"], start, n, total_len, pats, cfg["every"], device=device, out=out)
 

@@ -26,7 +26,19 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None, pad=0):
     lut = L["lut"]
     syms = [int(text[start + i]) if i < avail else 0 for i in range(K)]
     fast = B == 8 or (avail >= K and all(not (int(lut[c]) & 0x80) for c in syms))
-    if L["hfilt"].size:
+    if L["hfilt"].size and B == 2:
+        # hashed 10-mer first stage of 2-bit alphabets: arithmetic codes of whatever bytes are there
+        sh = L["code_shift"]
+        assert sh >= 0 and L["hfilt_k"] == 2
+        x = 0
+        for i in range(10):
+            c = int(text[start + i]) if i < avail else pad
+            x |= ((c >> sh) & 3) << (2 * i)
+        w = int(L["hfilt"][(((x * 0x9E3779B1) & 0xFFFFFFFF) >> 19) & 8191])
+        for m in (0x85EBCA6B, 0xC2B2AE35):
+            if not ((w << (((x * m) & 0xFFFFFFFF) >> 27)) >> 31) & 1:
+                return 0
+    elif L["hfilt"].size:
         assert B == 8
         x = sum((int(text[start + i]) if i < avail else pad) << (8 * i) for i in range(4))
         w = int(L["hfilt"][(((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191])   # word picked by (c0,c1)

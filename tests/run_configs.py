@@ -99,7 +99,7 @@ def main():
         d_out = torch.empty(owned, dtype=torch.int32, device=dev)
         run = lambda: pf.matchShardFromDevice(d_in, owned, total, d_out)  # noqa: E731
     else:
-        cap = owned if args.config == "c4dense" else max(owned // 8, 1 << 20)
+        cap = owned if args.config in ("c4dense", "wan_reduce") else max(owned // 8, 1 << 20)
         d_id = torch.empty(cap, dtype=torch.int32, device=dev)
         pos64 = api == "reduce64" or owned >= 2 ** 31
         d_pos = torch.empty(cap, dtype=torch.int64 if pos64 else torch.int32, device=dev)

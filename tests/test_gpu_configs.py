@@ -177,3 +177,27 @@ def test_c5_two_ranks_nccl_global_list(cuda, tmp_path):
     assert by_rank[0]["global_offset"] == 0 and by_rank[1]["global_offset"] == by_rank[0]["matches_rank"]
     assert by_rank[0]["matches_total"] == by_rank[0]["matches_rank"] + by_rank[1]["matches_rank"]
     assert by_rank[0].get("gather_ok") is True and by_rank[0].get("p2p_gather_ok") is True
+
+
+@pytest.mark.parametrize("name", ["wprefix_dense", "wan_dense"])
+def test_adversarial_texts(cuda, tmp_path, name):
+    """Worst cases: a text of concatenated pattern prefixes (every piece passes the first stage and walks
+    deep) and a^n against a^1..a^32 (every position matches after the longest walk; the parking and
+    spill rings of the reduce kernel run full): dense array and reduced list equal the oracle's."""
+    cfg, pats, orc, pf = _setup(name, tmp_path)
+    n = (96 << 20) + 333
+    d_text = configs.device_text(cfg, 0, n, n, pats, cuda)
+    d_out = torch.full((n,), -7, dtype=torch.int32, device=cuda)
+    ms_dense = _time_ms(lambda: pf.matchFromDevice(d_text, n, d_out), reps=2)
+    d_id = torch.full((n,), -7, dtype=torch.int32, device=cuda)
+    d_pos = torch.full((n,), -7, dtype=torch.int32, device=cuda)
+    ms_red = _time_ms(lambda: pf.matchFromDeviceReduce(d_text, n, d_id, d_pos), reps=2)
+    m = pf.matchFromDeviceReduce(d_text, n, d_id, d_pos)
+    mism, k, secs = _check_dense_and_list(orc, d_text, n, orc.max_pattern_len - 1, d_out, d_id, d_pos)
+    configs.append_result({"test": name, "bytes": n, "matches": m, "oracle": orc.kind, "oracle_s": round(secs, 1),
+                           "dense_ms": ms_dense, "dense_GBps": n / ms_dense / 1e6, "reduce_ms_call": ms_red,
+                           "reduce_GBps": n / ms_red / 1e6, "mismatches": mism})
+    assert m == k and mism == 0
+    if name == "wan_dense":
+        assert m == n   # every position matches
+    pf.destroy()

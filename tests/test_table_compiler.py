@@ -312,7 +312,8 @@ def test_random_dictionaries_both_first_stages(monkeypatch, seed):
                 tc = TableCompiler(patterns=pats, hot_budget_bytes=budget)
                 L = tc.layout()
                 info = tc.info()
-                assert bool(info["hashed_filter"]) == (policy == "hash" and info["code_bits"] == 8 and budget >= 32768)
+                hashable = info["code_bits"] == 8 or (info["code_bits"] == 2 and info["code_shift"] >= 0)
+                assert bool(info["hashed_filter"]) == (policy == "hash" and hashable and budget >= 32768)
                 got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=int(rng.integers(0, 256)))
                                 for i in range(n)], dtype=np.int32)
                 bad = np.flatnonzero(got != want)
@@ -453,3 +454,34 @@ def test_parser_fuzz_against_the_oracle(tmp_path):
         # the oracle and the layout reproduce that, the brute-force restatement does not)
         checked += 1
     assert checked > 100 and rejected > 30
+
+
+def test_dna_hashed_first_stage_keeps_every_match(golden_dir):
+    """2-bit alphabets with an arithmetic symbol code (ACGT: bits 1-2 of the byte) get the hashed 10-mer
+    first stage: no false negatives on DNA text with foreign bytes (N, n, newline, 0x00, 0xFF) and with
+    patterns shorter than the gram (all their continuations are set), whatever pads the end."""
+    from oracle import Oracle
+    rng = np.random.default_rng(77)
+    pats = synth.patterns_dna(400, short=12)      # lengths 8..24 plus a dozen of length 4..6
+    tc = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
+    info = tc.info()
+    assert info["code_bits"] == 2 and info["code_shift"] == 1 and info["hashed_filter"] == 2
+    assert 0 < info["hfilt_bits_set"] < 262144 // 2
+    L = tc.layout()
+    n = 6000
+    text = synth.dna_bytes(5, 0, n)
+    text[rng.integers(0, n, size=60)] = np.frombuffer(b"Nn\n\x00\xff-", dtype=np.uint8)[rng.integers(0, 6, size=60)]
+    for p in pats[:40]:
+        at = int(rng.integers(0, n - len(p) + 1))
+        text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    text[n - 5:] = np.frombuffer(pats[-1][:5].ljust(5, b"A"), dtype=np.uint8)
+    want = brute_force_match(pats, text)
+    assert (want > 0).sum() > 40
+    for pad in (0, ord("A"), ord("T"), 0xFF):
+        got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=pad) for i in range(n)], dtype=np.int32)
+        assert np.array_equal(got, want), pad
+    # lower-case alphabet: same bits; an alphabet whose bytes no two bits tell apart keeps the exact stage
+    low = [p.lower() for p in pats[:50]]
+    assert TableCompiler(patterns=low, hot_budget_bytes=64 * 1024).info()["code_shift"] == 1
+    odd = [bytes([0x10, 0x11, 0x12, 0x13, 0x30][c % 5] for c in p) for p in pats[:50]]   # 5 symbols -> 4-bit codes
+    assert TableCompiler(patterns=odd, hot_budget_bytes=64 * 1024).info()["hashed_filter"] == 0
