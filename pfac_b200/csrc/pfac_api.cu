@@ -298,6 +298,7 @@ struct PFAC_comm {
     size_t blockBytes = 0;
     size_t listCap = 0;        // entries of the list region
     unsigned char* peer[pfac::kKernelCommMaxRanks] = {};
+    size_t peerCap[pfac::kKernelCommMaxRanks] = {};   // list capacity of every rank's block (read from its header)
     bool ipcOpened[pfac::kKernelCommMaxRanks] = {};
     unsigned long long* d_scan = nullptr;   // 4 words, used when the caller passes no d_scan
     unsigned long long* h_scan = nullptr;   // pinned, 4 words
@@ -308,6 +309,7 @@ namespace {
 constexpr size_t kCommMailboxBytes = 4096;
 constexpr int kCommPlacedWord = 2 * pfac::kKernelCommMaxRanks;   // u64 index of placed[0][0]
 constexpr int kCommTicketWord = 4 * pfac::kKernelCommMaxRanks;
+constexpr int kCommCapWord = 4 * pfac::kKernelCommMaxRanks + 1;  // this block's list capacity, for the peers
 
 size_t commIdsBytes(size_t cap) { return ((cap * sizeof(int) + 255) / 256) * 256; }
 int* commListIds(unsigned char* block) { return reinterpret_cast<int*>(block + kCommMailboxBytes); }
@@ -1188,6 +1190,9 @@ static PFAC_status_t commAlloc(PFAC_comm* c, size_t list_capacity) {
     c->blockBytes = kCommMailboxBytes + commIdsBytes(list_capacity) + list_capacity * sizeof(long long) + 256;
     if (cudaMalloc(reinterpret_cast<void**>(&c->block), c->blockBytes) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
     if (cudaMemset(c->block, 0, kCommMailboxBytes) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    const unsigned long long cap64 = list_capacity;
+    if (cudaMemcpy(c->block + kCommCapWord * 8, &cap64, 8, cudaMemcpyHostToDevice) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+    c->peerCap[c->rank] = list_capacity;
     if (cudaMalloc(reinterpret_cast<void**>(&c->d_scan), 32) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
     if (cudaMallocHost(reinterpret_cast<void**>(&c->h_scan), 32) != cudaSuccess) return PFAC_STATUS_ALLOC_FAILED;
     if (cudaDeviceSynchronize() != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
@@ -1231,6 +1236,10 @@ PFAC_status_t PFAC_commConnect(PFAC_comm_t comm, const void* all_handles) {
         if (e != cudaSuccess) return PFAC_status_t(e);
         comm->peer[r] = static_cast<unsigned char*>(ptr);
         comm->ipcOpened[r] = true;
+        unsigned long long cap64 = 0;   // where that rank's position array starts depends on ITS capacity
+        e = cudaMemcpy(&cap64, comm->peer[r] + kCommCapWord * 8, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return PFAC_status_t(e);
+        comm->peerCap[r] = size_t(cap64);
     }
     return PFAC_STATUS_SUCCESS;
 }
@@ -1260,7 +1269,10 @@ PFAC_status_t PFAC_commCreateLocal(PFAC_comm_t* comms, const int* devices, int n
         }
     }
     for (int i = 0; i < num_devices && st == PFAC_STATUS_SUCCESS; i++)
-        for (int j = 0; j < num_devices; j++) comms[i]->peer[j] = comms[j]->block;
+        for (int j = 0; j < num_devices; j++) {
+            comms[i]->peer[j] = comms[j]->block;
+            comms[i]->peerCap[j] = comms[j]->listCap;
+        }
     cudaSetDevice(saved);
     if (st != PFAC_STATUS_SUCCESS)
         for (int i = 0; i < num_devices; i++) { if (comms[i]) PFAC_commDestroy(comms[i]); comms[i] = nullptr; }
@@ -1361,7 +1373,7 @@ PFAC_status_t PFAC_commGatherRuns(PFAC_handle_t handle, PFAC_comm_t comm, int ds
     unsigned long long* dstWords = reinterpret_cast<unsigned long long*>(dst);
     unsigned long long* ownWords = reinterpret_cast<unsigned long long*>(comm->block);
     cudaError_t e = pfac::launchPlaceRun(d_id, d_pos, d_scan ? d_scan : comm->d_scan, commListIds(dst),
-                                         commListPos(dst, comm->listCap), comm->listCap,
+                                         commListPos(dst, comm->peerCap[dst_rank]), comm->peerCap[dst_rank],
                                          dstWords + kCommPlacedWord + par + comm->rank, ownWords + kCommTicketWord, ep,
                                          handle->launch.numSMs, handle->stream);
     if (e == cudaSuccess && comm->rank == dst_rank)

@@ -855,15 +855,18 @@ constexpr int kRedStages = 2;                  // input stages per matcher warp
 constexpr int kRedSub = 3;                     // 512-position blocks per warp tile
 constexpr int kRedTile = kRedSub * kWarpTile;  // 1536 start positions per warp per round
 constexpr int kQueueCap = 256;                 // survivors walked per pass; denser tiles go block by block
-constexpr int kLag = 6;                        // a matcher may run this many rounds ahead of the scanner
+#ifndef PFAC_KLAG
+#define PFAC_KLAG 6
+#endif
+constexpr int kLag = PFAC_KLAG;                 // a matcher may run this many rounds ahead of the scanner
 // Ring slot reuse: a matcher that passed the lag wait of iteration j has written out every parked
 // record of rounds <= j-kLag (bases are posted in round order, and the flush that follows the wait
 // writes out everything whose base is there), so after iteration j it holds records > j-kLag only.
 // Slot r is rewritten by the first arrival at r+kRing, which needs ready(r+kRing-kLag), i.e. every
 // matcher finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
-constexpr int kRing = 16;                      // arrival ring slots
+constexpr int kRing = (PFAC_KLAG > 7) ? 32 : 16; // arrival ring slots
 constexpr int kPendCap = 128;                  // matches a warp can park in shared memory while bases are computed
-constexpr int kPendRecs = 8;                   // ... spread over at most this many rounds (power of two, > kLag)
+constexpr int kPendRecs = (PFAC_KLAG > 7) ? 16 : 8; // ... spread over at most this many rounds (power of two, > kLag)
 constexpr int kPendRecBytes = kPendRecs * 24;  // {round, n_smem, n_spill, tile start (u64)} per record
 constexpr int kSpillCap = 2048;                // per-warp spill ring in global memory (entries of 8 bytes)
 constexpr int kSlotBytes = 192;                // counts[32] | arrived | ready | base

@@ -614,9 +614,55 @@ def test_reference_test_programs_run_unchanged(cuda, tmp_path, golden_dir):
     out = run("simple_example_reduce")
     assert "number of matched = %d" % len(lines) in out
     assert [l for l in out.splitlines() if l.startswith("At position")] == lines
-    # omp_PFAC, SimpleMultiGPU_pthread and profiling are built and linked the same way (oracle/Makefile)
-    # but not run here: omp_PFAC sizes its segments with `((int)minGlobalMem) >> 3` (omp_PFAC.cpp:205),
-    # which overflows on a 180 GB device before the library is ever called.
+    # SimpleMultiGPU_pthread (reference test/SimpleMultiGPU_pthread.cpp:188-197): two host threads, one
+    # handle each (on one GPU both use device 0), two dictionaries at once; it writes match1/match2 and
+    # table1/table2 into its working directory
+    run("SimpleMultiGPU_pthread")
+    for k, pat, inp in ((1, "example_pattern", "example_input"), (2, "example_pattern2", "example_input2")):
+        o = _oracle(os.path.join(golden_dir, pat))
+        w = o.match(np.fromfile(os.path.join(golden_dir, inp), dtype=np.uint8))
+        got = open(str(tmp_path / "bin" / ("match%d" % k))).read().splitlines()
+        assert got == ["At position %4d, match pattern %d" % (i, w[i]) for i in np.flatnonzero(w)], k
+        o.dump(str(tmp_path / ("want_table%d" % k)))
+        assert open(str(tmp_path / "bin" / ("table%d" % k)), "rb").read() == \
+            open(str(tmp_path / ("want_table%d" % k)), "rb").read()
+    # omp_PFAC is built and linked the same way (oracle/Makefile) but not run: it sizes its segments with
+    # `((int)minGlobalMem) >> 3` (omp_PFAC.cpp:205), which overflows on a 180 GB device before the
+    # library is ever called.
+
+
+def test_reference_profiling_harness(cuda, tmp_path):
+    """The reference's own benchmark program (test/profiling.cpp: its metric is Gbps = 8 * input_size /
+    time, :296-322), compiled unchanged and linked to this library, on 128 MiB of the C2 workload:
+    device mode (-TD: PFAC_matchFromDevice between CUDA events) and host mode (-TH: PFAC_matchFromHost
+    on malloc'ed buffers), time-driven and space-driven.  Its match count must be the oracle's; its
+    Gbps lines go to gpurun_out/ for RESULTS.md."""
+    import re
+    import subprocess
+    prog = os.path.join(ROOT, "oracle", "_ref", "progs", "profiling")
+    if not os.path.exists(prog):
+        pytest.skip("oracle/_ref/progs not built (needs /root/reference at build time)")
+    n = 128 << 20   # the program computes input_size * 8 in an int: 128 MiB is the most it can report
+    pats = synth.patterns_c2(1000)
+    pfile = synth.write_pattern_file(str(tmp_path / "c2.pat"), pats)
+    text = synth.make_text("random", synth.SEED_BASE + 2, 0, n, n, pats, every=4096)
+    text.tofile(str(tmp_path / "c2.txt"))
+    want = int((_oracle(pfile).match(text) > 0).sum())
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "pfac_b200", "lib") + ":" +
+               os.environ.get("LD_LIBRARY_PATH", ""))
+    results = {}
+    for label, args in (("device", ["-TD"]), ("host", ["-TH"]), ("device_space_driven", ["-TD", "-S"])):
+        r = subprocess.run([prog, "-P", pfile, "-I", str(tmp_path / "c2.txt")] + args, env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0 and "Error" not in r.stdout, r.stdout + r.stderr
+        assert "The number of matched is %d" % want in r.stdout, r.stdout
+        gbps = float(re.search(r"The throughput is ([0-9.]+) Gbps", r.stdout).group(1))
+        assert gbps > 0
+        results[label] = {"Gbps": gbps, "GBps": gbps / 8.0}
+    from tests import configs
+    configs.append_result({"test": "reference_profiling_harness", "bytes": n, "matches": want, "results": results,
+                           "note": "one cold launch each (the program times a single call, table staging and "
+                                   "first-touch included)"})
 
 
 def test_multi_gpu_driver_one_process(cuda, tmp_path, monkeypatch):
