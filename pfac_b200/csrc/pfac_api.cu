@@ -250,8 +250,10 @@ struct HostPipe {  // cached buffers of the matchFromHost* pipelines
     int* s_out[2] = {nullptr, nullptr};
     size_t stageChunk = 0;               // owned bytes per staged chunk (<= chunk)
     size_t stageInCap = 0;
-    int* s_list[2] = {nullptr, nullptr};  // pinned (ids | positions) of the sparse result path
+    int* s_list[2] = {nullptr, nullptr};  // pinned (ids | positions) of the sparse result path: the kernel writes them
     size_t listCap = 0;                   // entries per slot
+    unsigned long long* h_cnt = nullptr;  // pinned: match count of the chunk in each slot (written by the kernel)
+    cudaEvent_t evH2D[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr};
     std::shared_ptr<CopyPool> pool;
     size_t lastH2D = 0, lastD2H = 0;      // bytes the last matchFromHost* call moved over PCIe
 };
@@ -274,7 +276,10 @@ struct PFAC_context {
     pfac::DeviceLayout layoutReduce;  // reduce kernel
     pfac::DeviceTable table;
     pfac::DeviceTable tableReduce;
-    std::vector<void*> d_arrays;      // every device array of both tables
+    std::vector<void*> d_arrays;      // the device slab holding every array of both tables
+    unsigned char* d_slab = nullptr;  // (one allocation: one L2 access-policy window covers all of them)
+    size_t slabBytes = 0, slabUsed = 0;
+    bool l2Window = false;            // a persisting-L2 window over the slab is set on the handle's streams
 
     std::mutex pipeMu;  // held for a whole matchFromHost* call (host pipeline buffers)
     std::mutex mu;      // guards the reduce workspace (several host threads may share a handle)
@@ -320,6 +325,9 @@ long long* commListPos(unsigned char* block, size_t cap) {
 void freeDeviceTable(PFAC_handle_t h) {
     for (void* p : h->d_arrays) cudaFree(p);
     h->d_arrays.clear();
+    h->d_slab = nullptr;
+    h->slabBytes = h->slabUsed = 0;
+    h->l2Window = false;
     h->table = pfac::DeviceTable();
     h->tableReduce = pfac::DeviceTable();
 }
@@ -343,6 +351,8 @@ void freeStage(HostPipe& p) {
         if (p.s_list[i]) cudaFreeHost(p.s_list[i]);
         p.s_list[i] = nullptr;
     }
+    if (p.h_cnt) cudaFreeHost(p.h_cnt);
+    p.h_cnt = nullptr;
     p.stageChunk = p.stageInCap = p.listCap = 0;
 }
 
@@ -353,15 +363,19 @@ void freePipe(HostPipe& p) {
         if (p.d_out[i]) cudaFree(p.d_out[i]);
         if (p.d_pos[i]) cudaFree(p.d_pos[i]);
         if (p.stream[i]) cudaStreamDestroy(p.stream[i]);
+        if (p.evH2D[i]) cudaEventDestroy(p.evH2D[i]);
+        if (p.evDone[i]) cudaEventDestroy(p.evDone[i]);
     }
     p = HostPipe();
 }
 
+size_t paddedTableBytes(size_t bytes) { return ((bytes + 15) / 16) * 16 + 256; }  // kernels copy tables in 16-byte pieces
+
 PFAC_status_t uploadArray(PFAC_handle_t h, const void** dst, const void* src, size_t bytes) {
-    void* d = nullptr;
-    const size_t padded = ((bytes + 15) / 16) * 16 + 16;  // kernels copy tables in 16-byte pieces
-    if (cudaMalloc(&d, padded) != cudaSuccess) return PFAC_STATUS_CUDA_ALLOC_FAILED;
-    h->d_arrays.push_back(d);
+    const size_t padded = paddedTableBytes(bytes);
+    if (h->slabUsed + padded > h->slabBytes) return PFAC_STATUS_INTERNAL_ERROR;
+    void* d = h->d_slab + h->slabUsed;
+    h->slabUsed += (padded + 255) & ~size_t(255);
     if (cudaMemset(d, 0xFF, padded) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     if (bytes && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
@@ -430,9 +444,42 @@ int filterPolicy() {
 // PFAC_bindTable, PFAC.cpp:321-343, which picks the dense 2-D table or the hash table)
 PFAC_status_t uploadTables(PFAC_handle_t h) {
     freeDeviceTable(h);
+    // one slab for all arrays of both layouts (14 arrays each, 512 B of padding and alignment per array)
+    h->slabBytes = h->layout.deviceBytes() + h->layoutReduce.deviceBytes() + 2 * 14 * 768 + 4096;
+    if (cudaMalloc(reinterpret_cast<void**>(&h->d_slab), h->slabBytes) != cudaSuccess) {
+        h->d_slab = nullptr;
+        h->slabBytes = 0;
+        return PFAC_STATUS_CUDA_ALLOC_FAILED;
+    }
+    h->d_arrays.push_back(h->d_slab);
     PFAC_status_t st = uploadLayout(h, h->layout, h->table);
     if (st != PFAC_STATUS_SUCCESS) return st;
     return uploadLayout(h, h->layoutReduce, h->tableReduce);
+}
+
+// Tables that do not fit shared memory are read through L2 by the walkers while gigabytes of text and
+// results stream through the same cache.  PFAC_B200_L2_PERSIST=1 asks for a persisting access-policy
+// window over the table slab on `stream` (and, once per device, for a persisting carve-out to hold
+// it); measured on C3 in profiles/r2_history.md.  Off by default: it changes a device-wide limit.
+void applyL2Window(PFAC_handle_t h, cudaStream_t stream) {
+    static const bool want = envBytes("PFAC_B200_L2_PERSIST", 0, 1) != 0;
+    if (!want || !h->d_slab || h->slabUsed < (size_t(256) << 10)) return;   // small tables live in shared memory
+    int maxWin = 0, maxPersist = 0;
+    cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    if (maxWin <= 0 || maxPersist <= 0) return;
+    const size_t bytes = std::min<size_t>(h->slabUsed, size_t(maxWin));
+    size_t cur = 0;
+    cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+    const size_t need = std::min<size_t>(((bytes + (size_t(1) << 20) - 1) >> 20) << 20, size_t(maxPersist));
+    if (cur < need) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, need);
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = h->d_slab;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
 PFAC_status_t bindTable(PFAC_handle_t h) {
@@ -525,15 +572,17 @@ PFAC_status_t ensureReduceWorkspace(PFAC_handle_t h, size_t words) {
 // scan run inside the same kernel.
 PFAC_status_t reduceShardEnqueue(PFAC_handle_t h, const unsigned char* d_in, size_t n_owned, size_t n_total,
                                  long long pos_base, int* d_id, void* d_pos, bool pos64, cudaStream_t stream,
-                                 const pfac::CommLaunch* comm, unsigned long long capacity = ~0ull) {
+                                 const pfac::CommLaunch* comm, unsigned long long capacity = ~0ull,
+                                 unsigned long long* total_out = nullptr) {
     const size_t words = pfac::reduceWorkspaceWords(n_owned);
     PFAC_status_t st = ensureReduceWorkspace(h, words);
     if (st != PFAC_STATUS_SUCCESS) return st;
+    applyL2Window(h, stream);
     if (cudaMemsetAsync(h->d_ws, 0, words * 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     if (cudaMemsetAsync(h->d_total, 0, 8, stream) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
     return cudaToStatus(pfac::launchMatchReduce(h->tableReduce, h->launch, d_in, n_owned, n_total, pos_base, d_id,
-                                                d_pos, pos64, h->d_ws, h->d_park, h->d_total, stream, comm, h->h_total + 8,
-                                                capacity));
+                                                d_pos, pos64, h->d_ws, h->d_park, total_out ? total_out : h->d_total, stream,
+                                                comm, h->h_total + 8, capacity));
 }
 
 // one fused match+compaction over a device shard; synchronous (returns the count)
@@ -568,6 +617,8 @@ PFAC_status_t ensurePipe(PFAC_handle_t h, size_t posBytes) {
     freePipe(p);
     for (int i = 0; i < 2; i++) {
         if (cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        if (cudaEventCreateWithFlags(&p.evH2D[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p.evDone[i], cudaEventDisableTiming) != cudaSuccess) { freePipe(p); return PFAC_STATUS_INTERNAL_ERROR; }
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_in[i]), inCap) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
         if (cudaMalloc(reinterpret_cast<void**>(&p.d_out[i]), chunk * 4) != cudaSuccess) { freePipe(p); return PFAC_STATUS_CUDA_ALLOC_FAILED; }
         // sized by the position width the caller asked for (4 B for the legacy int calls, 8 B for the
@@ -782,6 +833,7 @@ PFAC_status_t PFAC_matchShardFromDevice(PFAC_handle_t handle, const char* d_in, 
     if (!d_in || !d_out) return PFAC_STATUS_INVALID_PARAMETER;
     if (n_total < n_owned) return PFAC_STATUS_INVALID_PARAMETER;
     if (n_owned == 0) return PFAC_STATUS_SUCCESS;
+    applyL2Window(handle, handle->stream);
     return cudaToStatus(pfac::launchMatchDense(handle->table, handle->launch,
                                                reinterpret_cast<const unsigned char*>(d_in), n_owned,
                                                n_total, d_out, handle->stream));
@@ -794,6 +846,7 @@ PFAC_status_t PFAC_matchFromDevice(PFAC_handle_t handle, char* d_in, size_t size
     if (!d_in) return PFAC_STATUS_INVALID_PARAMETER;
     if (!d_out) return PFAC_STATUS_INVALID_PARAMETER;
     if (size == 0) return PFAC_STATUS_SUCCESS;
+    applyL2Window(handle, handle->stream);
     return cudaToStatus(pfac::launchMatchDense(handle->table, handle->launch,
                                                reinterpret_cast<const unsigned char*>(d_in), size, size,
                                                d_out, handle->stream));
@@ -838,6 +891,7 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
         }
         p.listCap = cap;
     }
+    if (!p.h_cnt && cudaMallocHost(reinterpret_cast<void**>(&p.h_cnt), 128) != cudaSuccess) return PFAC_STATUS_ALLOC_FAILED;
     const size_t nchunks = (n_owned + chunk - 1) / chunk;
     const size_t halo = size_t(handle->machine.maxPatternLen > 1 ? handle->machine.maxPatternLen - 1 : 0);
     auto ownedOf = [&](size_t c) { return (n_owned - c * chunk < chunk) ? n_owned - c * chunk : chunk; };
@@ -845,8 +899,17 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
         const size_t off = c * chunk, owned = ownedOf(c);
         return (n_total - off < owned + halo) ? n_total - off : owned + halo;
     };
-    // in flight: [host copy of chunk c+2 into pinned staging (pageable input only)] || [H2D of chunk
-    // c+1] || [match + compaction of chunk c on the GPU, zero fill of its h_out slice on the host]
+    // Nothing in the loop blocks on the GPU except the wait for a chunk's own kernel:
+    //   copy stream    : H2D of chunk c (after the kernel of chunk c-2 released the slot's input buffer)
+    //   compute stream : fused match + compaction of chunk c; the kernel stores the (id, position) pairs
+    //                    and the count straight into pinned host memory (zero-copy: a few bytes per match)
+    //   copy pool      : zero fill of the h_out slice of chunk c+2, host copy of pageable chunk c+3
+    //   this thread    : helps with the fill of chunk c, waits for its kernel, scatters its pairs,
+    //                    enqueues chunk c+2
+    // The kernels run one after the other on one stream, so they share the handle's reduce workspace;
+    // handle->mu is held for the whole call so that no other thread's reduce call gets in between.
+    std::lock_guard<std::mutex> wsLock(handle->mu);
+    cudaStream_t copyS = p.stream[0], compS = p.stream[1];
     CopyPool::Job jobs[3];
     CopyPool::Job zero[2];  // the fill runs two chunks ahead, so the workers never wait for the GPU
     auto hostStage = [&](size_t c) {
@@ -855,15 +918,6 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
     auto zeroFill = [&](size_t c) {
         if (c < nchunks) p.pool->startZero(zero[c % 2], h_out + c * chunk, ownedOf(c) * sizeof(int));
     };
-    auto h2d = [&](size_t c) -> cudaError_t {
-        const void* src = h_in + c * chunk;
-        if (stIn) {
-            p.pool->finish(jobs[c % 3]);
-            src = p.s_in[c % 3];
-        }
-        p.lastH2D += totalOf(c);
-        return cudaMemcpyAsync(p.d_in[c % 2], src, totalOf(c), cudaMemcpyHostToDevice, p.stream[c % 2]);
-    };
     auto bail = [&](PFAC_status_t st) {
         if (stIn) for (int j = 0; j < 3; j++) p.pool->finish(jobs[j]);
         p.pool->finish(zero[0]);
@@ -871,50 +925,74 @@ static PFAC_status_t hostDenseSparse(PFAC_handle_t handle, const char* h_in, siz
         cudaDeviceSynchronize();
         return st;
     };
+    auto enqueue = [&](size_t c) -> PFAC_status_t {
+        const int slot = int(c % 2);
+        if (c >= 2 && cudaStreamWaitEvent(copyS, p.evDone[slot], 0) != cudaSuccess) return PFAC_STATUS_INTERNAL_ERROR;
+        const void* src = h_in + c * chunk;
+        if (stIn) {
+            p.pool->finish(jobs[c % 3]);
+            src = p.s_in[c % 3];
+        }
+        p.lastH2D += totalOf(c);
+        if (cudaMemcpyAsync(p.d_in[slot], src, totalOf(c), cudaMemcpyHostToDevice, copyS) != cudaSuccess ||
+            cudaEventRecord(p.evH2D[slot], copyS) != cudaSuccess ||
+            cudaStreamWaitEvent(compS, p.evH2D[slot], 0) != cudaSuccess)
+            return PFAC_STATUS_INTERNAL_ERROR;
+        PFAC_status_t st = reduceShardEnqueue(handle, p.d_in[slot], ownedOf(c), totalOf(c), 0, p.s_list[slot],
+                                              p.s_list[slot] + cap, false, compS, nullptr, cap, p.h_cnt + slot * 8);
+        if (st != PFAC_STATUS_SUCCESS) return st;
+        return cudaEventRecord(p.evDone[slot], compS) == cudaSuccess ? PFAC_STATUS_SUCCESS : PFAC_STATUS_INTERNAL_ERROR;
+    };
     p.lastH2D = p.lastD2H = 0;
+    if (!p.pool) p.pool = acquireCopyPool();
     hostStage(0);
     hostStage(1);
+    hostStage(2);
     zeroFill(0);
     zeroFill(1);
-    if (h2d(0) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+    for (size_t c = 0; c < 2 && c < nchunks; c++) {
+        PFAC_status_t st = enqueue(c);
+        if (st != PFAC_STATUS_SUCCESS) return bail(st);
+    }
     for (size_t c = 0; c < nchunks; c++) {
         const int slot = int(c % 2);
         const size_t off = c * chunk, owned = ownedOf(c);
-        if (c + 1 < nchunks && h2d(c + 1) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
-        hostStage(c + 2);
-        unsigned long long count = 0;
-        PFAC_status_t st = reduceShard(handle, p.d_in[slot], owned, totalOf(c), 0, p.d_out[slot], p.d_pos[slot],
-                                       false, p.stream[slot], &count);
-        if (st != PFAC_STATUS_SUCCESS) return bail(st);
+        p.pool->finish(zero[slot]);                       // this thread fills too while the GPU works
+        if (cudaEventSynchronize(p.evDone[slot]) != cudaSuccess) {
+            const unsigned long long* d = handle->h_total + 8;
+            if (d[0])
+                fprintf(stderr, "libpfac: reduce kernel wait watchdog: site %llu block %llu thread %llu values %lld %lld %lld\n",
+                        d[1], d[2] >> 32, d[2] & 0xFFFFFFFFull, (long long)d[3], (long long)d[4], (long long)d[5]);
+            return bail(PFAC_STATUS_INTERNAL_ERROR);
+        }
+        hostStage(c + 3);                                 // its staging slot is that of chunk c, now on the device
+        const unsigned long long count = p.h_cnt[slot * 8];
         p.lastD2H += 8;
         if (count <= cap) {
-            int* ids = p.s_list[slot];
-            int* pos = p.s_list[slot] + cap;
-            if (count) {
-                if (cudaMemcpyAsync(ids, p.d_out[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess ||
-                    cudaMemcpyAsync(pos, p.d_pos[slot], count * 4, cudaMemcpyDeviceToHost, p.stream[slot]) != cudaSuccess)
-                    return bail(PFAC_STATUS_INTERNAL_ERROR);
-                p.lastD2H += count * 8;
-            }
-            p.pool->finish(zero[slot]);
-            if (cudaStreamSynchronize(p.stream[slot]) != cudaSuccess) return bail(PFAC_STATUS_INTERNAL_ERROR);
+            const int* ids = p.s_list[slot];
+            const int* pos = p.s_list[slot] + cap;
             int* dst = h_out + off;
             for (unsigned long long i = 0; i < count; i++) dst[pos[i]] = ids[i];
+            p.lastD2H += count * 8;
         } else {
-            // dense chunk: the position buffer (8 bytes per position) doubles as the dense result
-            p.pool->finish(zero[slot]);
-            int* d_dense = p.d_pos[slot];
+            // dense chunk (more than one match per 16 positions): the dense kernel + a plain D2H of its slice
+            int* d_dense = p.d_out[slot];
             cudaError_t e = pfac::launchMatchDense(handle->table, handle->launch, p.d_in[slot], owned, totalOf(c),
-                                                   d_dense, p.stream[slot]);
+                                                   d_dense, compS);
             if (e == cudaSuccess)
-                e = cudaMemcpyAsync(h_out + off, d_dense, owned * sizeof(int), cudaMemcpyDeviceToHost, p.stream[slot]);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(p.stream[slot]);
+                e = cudaMemcpyAsync(h_out + off, d_dense, owned * sizeof(int), cudaMemcpyDeviceToHost, compS);
+            if (e == cudaSuccess) e = cudaEventRecord(p.evDone[slot], compS);   // the slot's input is in use until here
+            if (e == cudaSuccess) e = cudaStreamSynchronize(compS);
             if (e != cudaSuccess) return bail(cudaToStatus(e));
             p.lastD2H += owned * sizeof(int);
         }
         zeroFill(c + 2);
+        if (c + 2 < nchunks) {
+            PFAC_status_t st = enqueue(c + 2);
+            if (st != PFAC_STATUS_SUCCESS) return bail(st);
+        }
     }
-    if (cudaStreamSynchronize(p.stream[0]) != cudaSuccess || cudaStreamSynchronize(p.stream[1]) != cudaSuccess)
+    if (cudaStreamSynchronize(copyS) != cudaSuccess || cudaStreamSynchronize(compS) != cudaSuccess)
         return PFAC_STATUS_INTERNAL_ERROR;
     return PFAC_STATUS_SUCCESS;
 }
