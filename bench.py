@@ -248,20 +248,26 @@ def run_c5(pf_factory, rank, local_rank, world, dev, dist, torch, barrier, max_o
     comm = (PFACComm.from_torch(total_m + 64 if rank == 0 else 0, device=dev) if world > 1
             else PFACComm(0, 1, total_m + 64))
 
-    def step():
+    def step(gather):
         pf.matchShardFromDeviceReduce64Global(comm, d_in, owned, total, start, d_id, d_pos, d_scan=d_scan, sync=False)
-        pf.gatherRuns(comm, 0, d_id, d_pos, d_scan=d_scan, sync=False)
+        if gather:
+            pf.gatherRuns(comm, 0, d_id, d_pos, d_scan=d_scan, sync=False)
 
-    for _ in range(3):
-        step()
-    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(steps):
-        step()
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / steps)
+
+    def timed(gather):
+        for _ in range(3):
+            step(gather)
+        barrier()
+        ev[0].record()
+        for _ in range(steps):
+            step(gather)
+        ev[1].record()
+        torch.cuda.synchronize()
+        return max_over_ranks(ev[0].elapsed_time(ev[1]) / steps)
+
+    ms = timed(False)          # the config: sharded reduce + global offset scan
+    ms_gather = timed(True)    # + the optional second step: every run stored into one list on rank 0
     # the same kernel with nobody to wait for (a one-rank comm) and no placement: what the cross-GPU
     # part of the step costs is the difference
     solo = PFACComm(0, 1, 0)
@@ -324,15 +330,18 @@ def run_c5(pf_factory, rank, local_rank, world, dev, dist, torch, barrier, max_o
     return {
         "workload": "C5: %d Snort-like patterns over %.0f GiB ASCII-weighted planted text regenerated on the GPUs, "
                     "%d contiguous shards + %d-byte tail halo, PFAC_matchShardFromDeviceReduce64Global (fused match + "
-                    "compaction + in-kernel cross-GPU count scan) + PFAC_commGatherRuns (one global list on rank 0)"
+                    "compaction + in-kernel cross-GPU count exchange and exclusive scan)"
                     % (len(pats), total_len / GIB, world, maxlen - 1),
         "value": total_len / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
         "per_gpu_GBps": owned / (ms * 1e-3) / 1e9, "bytes_per_gpu": owned, "total_bytes": total_len,
         "kernel_only_ms_per_call": ms_plain,
-        "cross_gpu_ms_per_step": max(ms - ms_plain, 0.0),
-        "cross_gpu": "count exchange + exclusive scan inside the reduce kernel over NVLink peer memory, then %d B "
-                     "per match stored into rank 0's list by P2P stores; no NCCL call, no host round trip in the step"
-                     % 12,
+        "count_scan_ms_per_step": max(ms - ms_plain, 0.0),
+        "cross_gpu": "count exchange + exclusive scan inside the reduce kernel over NVLink peer memory; no NCCL call, "
+                     "no host round trip in the step",
+        "with_gather": {"value": total_len / (ms_gather * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_gather,
+                        "gather_ms_per_step": max(ms_gather - ms, 0.0), "gather_bytes_into_rank0": 12 * (total_m - count) if rank == 0 else None,
+                        "what": "PFAC_commGatherRuns after every step: every rank's run stored into ONE list on rank 0 "
+                                "at its scanned offset by P2P stores (12 B per match over NVLink into one GPU)"},
         "matches_total": total_m, "matches_rank0": count if rank == 0 else None, "states": info["num_states"],
         "roofline": {"bound": "hbm", "kernel": "pfac_reduce_kernel<1, 8, %d>" % (info["hashed_filter"] + 1 if info["hashed_filter"] else 0),
                      "algorithmic_bytes_per_launch": int(algo), "achieved": algo / (ms_plain * 1e-3) / 1e9,

@@ -514,7 +514,21 @@ __device__ __forceinline__ int push_survivors(uint32_t cand, uint32_t slow, int 
 // Per survivor: root row (is c0 alone a match?) -> next2[rank of (c0,c1)] (the walk after two
 // bytes, no hashing) -> then per step either a chain (tail compared 4 bytes at a time) or a
 // hash probe (hot rows in shared memory below hot_depth, cold rows through L1/L2).
-template <int CODE, bool HASHED>
+// n (1..4) text bytes from local position `at` when the word is not wholly inside the staged bytes (a walk
+// running past the staged halo): byte-wise, staged or from global memory.  Out of line: rare, and
+// inlined it sat five times in the walker.
+__device__ __noinline__ uint32_t text_word_slow(const unsigned char* inb, int stage_bytes,
+                                                const unsigned char* __restrict__ gin, int at, int n) {
+    uint32_t x = 0;
+    const int nn = n < 4 ? n : 4;
+    for (int k = 0; k < nn; k++) {
+        const int q = at + k;
+        x |= static_cast<uint32_t>((q < stage_bytes) ? inb[q] : gin[q]) << (8 * k);
+    }
+    return x;
+}
+
+template <int CODE, bool HASHED, bool INLINE_SLOW = false>
 __device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* inb, int stage_bytes,
                                           const unsigned char* __restrict__ gin, int tile_rem, bool active,
                                           unsigned qe, int& pl_out) {
@@ -525,7 +539,9 @@ __device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* 
             const uint32_t* w = reinterpret_cast<const uint32_t*>(inb + (at & ~3));
             return __funnelshift_r(w[0], w[1], (at & 3) * 8);
         }
-        uint32_t x = 0;  // past the staged halo: byte-wise, never beyond the bytes that exist
+        // past the staged halo: byte-wise, never beyond the bytes that exist
+        if (!INLINE_SLOW) return text_word_slow(inb, stage_bytes, gin, at, n);
+        uint32_t x = 0;
         const int nn = n < 4 ? n : 4;
         for (int k = 0; k < nn; k++) x |= text_byte(at + k) << (8 * k);
         return x;
@@ -650,7 +666,7 @@ __device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* 
 
 // Dense kernel: walk the queued survivors of one warp 32 at a time; wres[local position] = id
 // (non-zero only).  Returns whether this lane produced a non-zero id.
-template <int CODE, bool HASHED>
+template <int CODE, bool HASHED, bool INLINE_SLOW>
 __device__ __forceinline__ bool walk_queue_dense(const Tables& T, const unsigned char* inb, int stage_bytes,
                                                  const unsigned char* __restrict__ gin, int tile_rem,
                                                  const unsigned short* q16, int wtotal, int* wres, int lane) {
@@ -660,7 +676,7 @@ __device__ __forceinline__ bool walk_queue_dense(const Tables& T, const unsigned
         const bool active = slot < wtotal;
         const unsigned qe = active ? q16[slot] : 0u;
         int pl;
-        const int best = walk_batch<CODE, HASHED>(T, inb, stage_bytes, gin, tile_rem, active, qe, pl);
+        const int best = walk_batch<CODE, HASHED, INLINE_SLOW>(T, inb, stage_bytes, gin, tile_rem, active, qe, pl);
         if (best) { wres[pl] = best; wrote = true; }
     }
     return wrote;
@@ -696,6 +712,14 @@ __device__ __forceinline__ void clip_windows(int tile_rem, int lb, uint32_t& can
         cand &= ~tail;
     }
 }
+
+// The walker's rare byte-wise text reads (walks past the staged halo) sit out of line in the kernels that
+// are bound by instruction issue and fetch: measured +6 % on C3 dense.  The sparse-table dense kernel
+// (one filter bit, C2) is bound by HBM and measured 1.5 % slower with the call in its walker, so it
+// keeps them inline.
+#ifndef PFAC_DENSE_INLINE_SLOW
+#define PFAC_DENSE_INLINE_SLOW(FILT) ((FILT) == 2)
+#endif
 
 template <int NSTAGE, int CODE, int FILT>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
@@ -790,7 +814,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KPar
             __syncwarp();
         }
         dirty = __any_sync(0xffffffffu,
-                           walk_queue_dense<CODE, FILT >= 2>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
+                           walk_queue_dense<CODE, FILT >= 2, PFAC_DENSE_INLINE_SLOW(FILT)>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
 
         int* gout = p.out + start;
         if (p.out_aligned && full) {
@@ -1212,11 +1236,27 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
             // ---- survivors of the three blocks, one scan for all three counts (10-bit fields)
             uint32_t cand[kRedSub], slow[kRedSub];
             uint32_t packed = 0;
+#ifndef PFAC_UNROLLED_PREFILTER
+            // one copy of the prefilter in the instruction stream, run three times: the kernel's instruction
+            // footprint decides how well 31 divergent warps share the instruction caches (unrolled three
+            // times it measured 3 % slower on C2, 7 % on C4 and C5: profiles/r2_history.md)
+            cand[0] = cand[1] = cand[2] = slow[0] = slow[1] = slow[2] = 0u;
+#pragma unroll 1
+            for (int j = 0; j < kRedSub; j++) {
+                uint32_t sl;
+                const uint32_t cd = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, sl);
+                if (j == 0) { cand[0] = cd; slow[0] = sl; }
+                else if (j == 1) { cand[1] = cd; slow[1] = sl; }
+                else { cand[2] = cd; slow[2] = sl; }
+                packed |= static_cast<uint32_t>(__popc(cd | sl)) << (10 * j);
+            }
+#else
 #pragma unroll
             for (int j = 0; j < kRedSub; j++) {
                 cand[j] = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, slow[j]);
                 packed |= static_cast<uint32_t>(__popc(cand[j] | slow[j])) << (10 * j);
             }
+#endif
             const uint32_t incl = warp_incl_scan(packed, lane);
             const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
             const int wtotal = static_cast<int>((tot & 1023u) + ((tot >> 10) & 1023u) + (tot >> 20));

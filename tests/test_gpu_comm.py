@@ -127,3 +127,29 @@ def test_buffers_on_a_peer_gpu(cuda, tmp_path):
     assert np.array_equal(d_out[:m].cpu().numpy(), want_ids)
     assert np.array_equal(d_pos[:m].cpu().numpy().astype(np.int64), want_pos)
     pf.destroy()
+
+
+def test_reduce_with_stated_capacity(cuda, tmp_path):
+    """PFAC_matchShardFromDeviceReduce64Cap: nothing is stored past the stated capacity, the full count
+    still comes back, and a capacity that was too small is an error status."""
+    from pfac_b200 import PFAC, PFACError, Status
+    n = (1 << 20) + 9
+    pfile, text, orc, want_ids, want_pos = _workload(tmp_path, n)
+    pf = PFAC()
+    pf.readPatternFromFile(pfile)
+    d_in = torch.from_numpy(text).to(cuda)
+    m = want_ids.size
+    d_id = torch.full((m + 7,), -7, dtype=torch.int32, device=cuda)
+    d_pos = torch.full((m + 7,), -7, dtype=torch.int64, device=cuda)
+    assert pf.matchShardFromDeviceReduce64Cap(d_in, n, n, 5, d_id, d_pos) == m
+    assert np.array_equal(d_id[:m].cpu().numpy(), want_ids) and np.array_equal(d_pos[:m].cpu().numpy(), want_pos + 5)
+    assert d_id[m:].eq(-7).all() and d_pos[m:].eq(-7).all()
+    small = m // 3
+    d_id.fill_(-7)
+    d_pos.fill_(-7)
+    with pytest.raises(PFACError) as e:
+        pf.matchShardFromDeviceReduce64Cap(d_in, n, n, 5, d_id[:small], d_pos[:small])
+    assert e.value.status == Status.INVALID_PARAMETER
+    assert np.array_equal(d_id[:small].cpu().numpy(), want_ids[:small])      # the first `capacity` entries are there
+    assert d_id[small:].eq(-7).all() and d_pos[small:].eq(-7).all()          # and nothing beyond them
+    pf.destroy()
