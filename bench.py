@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bytes", type=int, default=GIB, help="input bytes per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--reduce-steps", type=int, default=10)
     ap.add_argument("--c5-steps", type=int, default=5)
     ap.add_argument("--c5-bytes", type=int, default=C5_TOTAL, help="total bytes of the C5 leg (all ranks)")
@@ -382,7 +382,7 @@ def main():
     # pointing fd 1 at stderr while the ranks run and printing the line to the saved stdout
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     # the host copy pool is per process: share the box's cores among the ranks of this job
-    os.environ.setdefault("PFAC_B200_COPY_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // max(world, 1)))))
+    os.environ.setdefault("PFAC_B200_COPY_THREADS", str(max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))))
     sys.stdout.flush()
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)

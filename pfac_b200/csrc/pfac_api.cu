@@ -454,7 +454,10 @@ PFAC_status_t uploadTables(PFAC_handle_t h) {
     h->d_arrays.push_back(h->d_slab);
     PFAC_status_t st = uploadLayout(h, h->layout, h->table);
     if (st != PFAC_STATUS_SUCCESS) return st;
-    return uploadLayout(h, h->layoutReduce, h->tableReduce);
+    st = uploadLayout(h, h->layoutReduce, h->tableReduce);
+    if (st != PFAC_STATUS_SUCCESS) return st;
+    const cudaError_t e = pfac::prepareKernels(h->table, h->tableReduce);
+    return e == cudaSuccess ? PFAC_STATUS_SUCCESS : (e == cudaErrorMemoryAllocation ? PFAC_STATUS_CUDA_ALLOC_FAILED : PFAC_STATUS_INTERNAL_ERROR);
 }
 
 // Tables that do not fit shared memory are read through L2 by the walkers while gigabytes of text and

@@ -1511,6 +1511,25 @@ size_t reduceParkWords(const LaunchConfig& cfg) { return size_t(cfg.numSMs) * kR
 
 unsigned long long kernelLaunchCount() { return g_launches.load(); }
 
+namespace {
+const void* denseKernelFor(const DeviceTable& t, int nst);
+const void* reduceKernelFor(const DeviceTable& t, bool pos64);
+}  // namespace
+
+// CUDA loads a kernel's code on first use (lazy module loading): asking for the attribute now moves
+// that cost (about 2 ms per kernel) from the caller's first match call to the pattern load, where the
+// reference pays its own table upload.  One call per table.
+cudaError_t prepareKernels(const DeviceTable& dense, const DeviceTable& reduce) {
+    const void* ks[3] = {denseKernelFor(dense, denseStages(roundHalo(dense.maxPatternLen, kDenseMaxHalo))),
+                         reduceKernelFor(reduce, false), reduceKernelFor(reduce, true)};
+    for (const void* k : ks) {
+        if (!k) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                              size_t n_owned, size_t n_total, int* out, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
@@ -1529,31 +1548,16 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
     const size_t smem = denseFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
     const int nst = denseStages(halo);
-    void (*kernel)(KParams) = nullptr;
-    // the table compiler emits hfilt / chk2 for byte alphabets only
-    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
-    switch (t.codeBits) {
-        case 8:
-            if (filt == 3) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 3> : pfac_dense_kernel<2, 8, 3>;
-            else if (filt == 2) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 2> : pfac_dense_kernel<2, 8, 2>;
-            else if (filt == 1) kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 1> : pfac_dense_kernel<2, 8, 1>;
-            else kernel = (nst == 3) ? pfac_dense_kernel<3, 8, 0> : pfac_dense_kernel<2, 8, 0>;
-            break;
-        case 4: kernel = (nst == 3) ? pfac_dense_kernel<3, 4, 0> : pfac_dense_kernel<2, 4, 0>; break;
-        case 2:  // hashed 10-mer first stage when the table compiler built one (arithmetic symbol code)
-            if (t.hfiltBytes) kernel = (nst == 3) ? pfac_dense_kernel<3, 2, 4> : pfac_dense_kernel<2, 2, 4>;
-            else kernel = (nst == 3) ? pfac_dense_kernel<3, 2, 0> : pfac_dense_kernel<2, 2, 0>;
-            break;
-        default: return cudaErrorInvalidValue;
-    }
-    if (t.codeBits == 4 && filt) return cudaErrorInvalidValue;
-    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return cudaErrorInvalidValue;
+    const void* kernel = denseKernelFor(t, nst);
+    if (!kernel) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
     const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
     long long grid = cfg.numSMs;
     if (grid > ctaTiles) grid = ctaTiles;
-    kernel<<<int(grid), kDenseThreads, smem, stream>>>(p);
+    void* args[] = {&p};
+    e = cudaLaunchKernel(kernel, dim3(unsigned(grid)), dim3(kDenseThreads), args, smem, stream);
+    if (e != cudaSuccess) return e;
     g_launches++;
     return cudaGetLastError();
 }
@@ -1602,6 +1606,46 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
     }
     const size_t smem = reduceFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
+    const void* kernel = reduceKernelFor(t, pos64);
+    if (!kernel) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    const long long ctaTiles = (p.num_tiles + kRedSlots - 1) / kRedSlots;
+    long long grid = cfg.numSMs;
+    if (grid > ctaTiles) grid = ctaTiles;
+    // cooperative launch: every CTA is resident, so waiting on another CTA's aggregate is safe
+    void* args[] = {&p};
+    e = cudaLaunchCooperativeKernel(kernel, dim3(unsigned(grid)), dim3(kRedThreads), args, smem, stream);
+    if (e != cudaSuccess) return e;
+    g_launches++;
+    return cudaGetLastError();
+}
+
+namespace {
+// the kernel instantiation a table runs on (nullptr: a table the kernels were not built for)
+const void* denseKernelFor(const DeviceTable& t, int nst) {
+    const void* kernel = nullptr;
+    // the table compiler emits hfilt / chk2 for byte alphabets only
+    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
+    switch (t.codeBits) {
+        case 8:
+            if (filt == 3) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 3> : (const void*)pfac_dense_kernel<2, 8, 3>;
+            else if (filt == 2) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 2> : (const void*)pfac_dense_kernel<2, 8, 2>;
+            else if (filt == 1) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 1> : (const void*)pfac_dense_kernel<2, 8, 1>;
+            else kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 0> : (const void*)pfac_dense_kernel<2, 8, 0>;
+            break;
+        case 4: kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 4, 0> : (const void*)pfac_dense_kernel<2, 4, 0>; break;
+        case 2:  // hashed 10-mer first stage when the table compiler built one (arithmetic symbol code)
+            if (t.hfiltBytes) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 2, 4> : (const void*)pfac_dense_kernel<2, 2, 4>;
+            else kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 2, 0> : (const void*)pfac_dense_kernel<2, 2, 0>;
+            break;
+        default: return nullptr;
+    }
+    if (t.codeBits == 4 && filt) return nullptr;
+    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return nullptr;
+    return kernel;
+}
+const void* reduceKernelFor(const DeviceTable& t, bool pos64) {
     const void* kernel = nullptr;
     const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
@@ -1616,22 +1660,13 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
             if (t.hfiltBytes) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, 4> : (const void*)pfac_reduce_kernel<false, 2, 4>;
             else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 2, 0> : (const void*)pfac_reduce_kernel<false, 2, 0>;
             break;
-        default: return cudaErrorInvalidValue;
+        default: return nullptr;
     }
-    if (t.codeBits == 4 && filt) return cudaErrorInvalidValue;
-    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) return e;
-    const long long ctaTiles = (p.num_tiles + kRedSlots - 1) / kRedSlots;
-    long long grid = cfg.numSMs;
-    if (grid > ctaTiles) grid = ctaTiles;
-    // cooperative launch: every CTA is resident, so waiting on another CTA's aggregate is safe
-    void* args[] = {&p};
-    e = cudaLaunchCooperativeKernel(kernel, dim3(unsigned(grid)), dim3(kRedThreads), args, smem, stream);
-    if (e != cudaSuccess) return e;
-    g_launches++;
-    return cudaGetLastError();
+    if (t.codeBits == 4 && filt) return nullptr;
+    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return nullptr;
+    return kernel;
 }
+}  // namespace
 
 cudaError_t launchPlaceRun(const int* ids, const long long* pos, const unsigned long long* scan, int* g_ids,
                            long long* g_pos, unsigned long long capacity, unsigned long long* placed,

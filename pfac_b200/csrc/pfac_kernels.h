@@ -64,6 +64,9 @@ size_t reduceWorkspaceWords(size_t n_owned);
 // L2-resident in use); needs no initialisation.
 size_t reduceParkWords(const LaunchConfig& cfg);
 
+// Load the kernels the two tables run on now rather than at the first match call.
+cudaError_t prepareKernels(const DeviceTable& dense, const DeviceTable& reduce);
+
 // Dense result: out[i] for i in [0,n_owned); walks may read in[0,n_total).
 cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, const unsigned char* in,
                              size_t n_owned, size_t n_total, int* out, cudaStream_t stream);

@@ -30,6 +30,11 @@ def _built_libraries():
         if not os.path.exists(pbuild.LIB):
             raise
         print("warning: rebuild failed, using existing libpfac.so:", e)
+    try:
+        from workloads import build as wbuild
+        wbuild.build()
+    except Exception as e:
+        print("warning: devgen build failed:", e)
     if not os.path.exists(oracle.ORACLE_SO) or (
             os.path.getmtime(os.path.join(oracle.HERE, "pfac_oracle.c")) > os.path.getmtime(oracle.ORACLE_SO)):
         oracle.build()
