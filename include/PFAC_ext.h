@@ -53,9 +53,9 @@ PFAC_status_t PFAC_matchFromDeviceReduce64(PFAC_handle_t handle, const char *d_i
                                            unsigned long long *h_num_matched);
 
 /* shard + 64-bit reduce: emitted position = pos_base + local position (pos_base = global
- * offset of the shard's first byte).  Multi-GPU use: each rank calls this on its shard, the
- * ranks exchange *h_num_matched (one 8-byte all-gather) and an exclusive scan of the counts
- * gives each rank's offset into the global (ID, position) list. */
+ * offset of the shard's first byte).  Multi-GPU use: each rank calls this on its shard; an
+ * exclusive scan of the ranks' counts gives each rank's offset into the global (ID, position)
+ * list -- PFAC_matchShardFromDeviceReduce64Global below does that scan inside the kernel. */
 PFAC_status_t PFAC_matchShardFromDeviceReduce64(PFAC_handle_t handle, const char *d_inputString,
                                                 size_t n_owned, size_t n_total,
                                                 long long pos_base, int *d_matched_result,
@@ -207,7 +207,7 @@ PFAC_status_t PFAC_memoryUsage(PFAC_handle_t handle);
  * thread per GPU running the chunked host pipeline; the reduced form places each GPU's run at the
  * exclusive scan of the per-GPU counts.  h_matched_result / h_pos of the reduced call must hold `size`
  * entries (the reference asks the same of its reduce buffers).  For one process per GPU use the shard
- * entry points above with an NCCL all-gather of the counts (pfac_b200/sharding.py). */
+ * entry points above with the in-kernel count scan (PFAC_comm, above). */
 typedef struct PFAC_mgpu *PFAC_mgpu_t;
 PFAC_status_t PFAC_mgpuCreate(PFAC_mgpu_t *mg, const int *devices, int num_devices);
 PFAC_status_t PFAC_mgpuDestroy(PFAC_mgpu_t mg);

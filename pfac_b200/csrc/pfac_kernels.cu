@@ -5,8 +5,9 @@
 // PFAC_reduce_kernel.cu:639-867 are the 2012 GPU forms being replaced).  How it is computed
 // is new -- see DESIGN.md:
 //   * a prefilter in shared memory rejects most start positions with one LDS -- a 256-Kbit hashed
-//     4-gram filter for byte alphabets, an exact 64-Kbit K-gram set for symbol-coded small
-//     alphabets; survivors are compacted into a per-warp queue;
+//     4-gram filter for byte alphabets, a hashed 10-mer filter over arithmetic 2-bit codes for
+//     DNA-like alphabets, an exact 64-Kbit K-gram set for the other symbol-coded small alphabets;
+//     survivors are compacted into a per-warp queue;
 //   * survivors are walked 32 at a time (one per lane, until the batch's longest walk ends): root row and
 //     shallow ("hot") hash rows in shared memory, deep ("cold") rows through L1/L2, and
 //     path-compressed chains whose tail bytes are compared directly against the text;
@@ -14,8 +15,10 @@
 //     512-byte input tiles (+halo) arrive by 1-D TMA bulk copies on per-warp mbarriers, the
 //     warp's 2 KB of results leave by a TMA bulk store; no CTA-wide barrier in the loop, so
 //     one long walk delays one warp, not a block;
-//   * reduce kernel: ordered warp/CTA compaction + decoupled look-back across tiles writes
-//     (id, position) pairs in one pass.
+//   * reduce kernel: the same pipeline on 1,536-position warp tiles; matches are parked per walker
+//     batch (shared-memory ring + a spill ring in global memory) and written in position order by a
+//     round-structured look-back across CTAs, one pass; on several GPUs the same kernel exchanges
+//     the per-GPU match counts over peer memory (NVLink) and takes their exclusive prefix.
 #include "pfac_kernels.h"
 
 #include <algorithm>

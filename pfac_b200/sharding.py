@@ -3,8 +3,11 @@
 Every start position is independent (reference PFAC_CPU.cpp:76), so an N-byte stream is cut
 into contiguous shards; rank g owns start positions [s_g, e_g) and additionally holds the
 next H = maxPatternLen-1 bytes (tail halo; real bytes, or fewer when the stream ends).  The
-only exchange is the per-rank match count: an all-gather of one int64 per rank followed by a
-local exclusive scan gives each rank's offset into the global (ID, position) list.
+only exchange is the per-rank match count: an exclusive scan of the counts gives each rank's offset
+into the global (ID, position) list.  The library does that scan inside the reduce kernel over peer
+memory (PFAC_comm, include/PFAC_ext.h); the torch.distributed forms below (an all-gather of one int64
+per rank + a local scan; send/recv placement of the runs) are the host-side cross-check used by the
+tests (gloo on CPU) and by tests/run_configs.py.
 This is what the reference's test/omp_PFAC.cpp:316-383 does by hand with host threads
 (there with maxPatternLen+1 bytes of overlap and no reduced output).
 """
