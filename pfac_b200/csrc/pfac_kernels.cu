@@ -892,6 +892,18 @@ constexpr int kLag = PFAC_KLAG;                 // a matcher may run this many r
 // Slot r is rewritten by the first arrival at r+kRing, which needs ready(r+kRing-kLag), i.e. every
 // matcher finished iteration r+kRing-kLag-1 and holds records > r+kRing-2*kLag-1 only: kRing >= 2*kLag+1.
 constexpr int kRing = (PFAC_KLAG > 7) ? 32 : 16; // arrival ring slots
+// Polling intervals.  A poll is ~8 issued instructions and the kernel is bound by instruction issue: at
+// 40 / 100 ns a third of all executed instructions were polls; 500 / 1000 ns measured +1 % (C4, C5;
+// profiles/r2_history.md).  A matcher in the lag wait is 6 rounds (~30 us) ahead and a base is needed
+// ~5 us after its round: waking up a fraction of a microsecond late costs nothing.
+#ifndef PFAC_SCANNER_NAP
+#define PFAC_SCANNER_NAP 500
+#endif
+#ifndef PFAC_MATCHER_NAP
+#define PFAC_MATCHER_NAP 1000
+#endif
+constexpr unsigned kScannerNap = PFAC_SCANNER_NAP;   // ns between scanner polls without progress
+constexpr unsigned kMatcherNap = PFAC_MATCHER_NAP;   // ns between polls of a matcher waiting for a base
 constexpr int kPendCap = 128;                  // matches a warp can park in shared memory while bases are computed
 constexpr int kPendRecs = (PFAC_KLAG > 7) ? 16 : 8; // ... spread over at most this many rounds (power of two, > kLag)
 constexpr int kPendRecBytes = kPendRecs * 24;  // {round, n_smem, n_spill, tile start (u64)} per record
@@ -1093,7 +1105,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                 }
             }
             if (!progress) {
-                __nanosleep(40);
+                __nanosleep(kScannerNap);
                 if (lane == 0) { PFAC_SPIN_GUARD(idle, p.dbg, 4, (static_cast<long long>(pub_r) << 32) | res_r, my_rounds, ring[pub_r & (kRing - 1)].arrived) }
             } else {
                 idle = 0;
@@ -1105,7 +1117,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
                 unsigned long long v = ld_relaxed_u64(g_rs + (num_rounds - 1));
                 unsigned long long spins = 0;
                 while ((v >> kRoundShift) != round_size(num_rounds - 1)) {
-                    __nanosleep(40);
+                    __nanosleep(kScannerNap);
                     v = ld_relaxed_u64(g_rs + (num_rounds - 1));
                     PFAC_SPIN_GUARD(spins, p.dbg, 5, num_rounds, v >> kRoundShift, v & kRoundMask)
                 }
@@ -1150,7 +1162,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     auto wait_ready = [&](uint32_t r, int site) {
         unsigned long long spins = 0;
         while (!round_ready(r)) {
-            __nanosleep(100);
+            __nanosleep(kMatcherNap);
             PFAC_SPIN_GUARD(spins, p.dbg, site, r, ring[r & (kRing - 1)].ready, warp)
         }
     };
