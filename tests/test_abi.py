@@ -153,3 +153,16 @@ def test_headers_are_plain_c_and_the_example_links(tmp_path):
                     "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.startswith("PFAC_STATUS_INVALID_HANDLE")
+
+
+def test_multi_gpu_example_compiles_and_links(tmp_path):
+    """examples/multi_gpu_scan.cpp (the omp_PFAC.cpp shape on PFAC_comm) is written against the public
+    headers only: it must compile with warnings as errors and link with -lpfac -lcudart."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    libdir = os.path.dirname(library_path())
+    subprocess.run(["/usr/bin/g++", "-O1", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", cuda + "/include",
+                    os.path.join(root, "examples", "multi_gpu_scan.cpp"), "-L", libdir, "-lpfac", "-L", cuda + "/lib64",
+                    "-lcudart", "-Wl,-rpath," + libdir, "-o", str(tmp_path / "multi_gpu_scan")], check=True)

@@ -153,3 +153,27 @@ def test_reduce_with_stated_capacity(cuda, tmp_path):
     assert np.array_equal(d_id[:small].cpu().numpy(), want_ids[:small])      # the first `capacity` entries are there
     assert d_id[small:].eq(-7).all() and d_pos[small:].eq(-7).all()          # and nothing beyond them
     pf.destroy()
+
+
+def test_multi_gpu_example_program(cuda, tmp_path):
+    """examples/multi_gpu_scan.cpp: a C++ caller of the public headers only.  One process, every visible
+    GPU, in-kernel count scan, one global list on GPU 0; the program compares that list element by
+    element with a single-GPU run (as reference test/omp_PFAC.cpp:397-439 does) and exits non-zero on a
+    difference.  Here its printed total must also be the oracle's."""
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from pfac_b200 import library_path
+    libdir = os.path.dirname(library_path())
+    exe = str(tmp_path / "multi_gpu_scan")
+    subprocess.run(["/usr/bin/g++", "-O2", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                    os.path.join(ROOT, "examples", "multi_gpu_scan.cpp"), "-L", libdir, "-lpfac",
+                    "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    n = (5 << 20) + 321
+    pfile, text, orc, want_ids, want_pos = _workload(tmp_path, n)
+    text.tofile(str(tmp_path / "text.bin"))
+    r = subprocess.run([exe, pfile, str(tmp_path / "text.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gpus = torch.cuda.device_count()
+    assert "number of matched = %d on %d GPU(s); single-GPU check: identical" % (want_ids.size, gpus) in r.stdout, r.stdout
+    first = ["At position %4d, match pattern %d" % (want_pos[i], want_ids[i]) for i in range(min(10, want_ids.size))]
+    assert [l for l in r.stdout.splitlines() if l.startswith("At position")] == first
