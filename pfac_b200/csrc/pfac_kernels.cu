@@ -881,7 +881,13 @@ constexpr int kRedMaxHalo = kDenseMaxHalo;
 constexpr int kRedStages = 2;                  // input stages per matcher warp
 constexpr int kRedSub = 3;                     // 512-position blocks per warp tile
 constexpr int kRedTile = kRedSub * kWarpTile;  // 1536 start positions per warp per round
-constexpr int kQueueCap = 256;                 // survivors walked per pass; denser tiles go block by block
+#ifndef PFAC_QUEUE_CAP
+#define PFAC_QUEUE_CAP 256
+#endif
+#ifndef PFAC_PEND_CAP
+#define PFAC_PEND_CAP 128
+#endif
+constexpr int kQueueCap = PFAC_QUEUE_CAP;      // survivors walked per pass; denser tiles go block by block
 #ifndef PFAC_KLAG
 #define PFAC_KLAG 6
 #endif
@@ -904,7 +910,7 @@ constexpr int kRing = (PFAC_KLAG > 7) ? 32 : 16; // arrival ring slots
 #endif
 constexpr unsigned kScannerNap = PFAC_SCANNER_NAP;   // ns between scanner polls without progress
 constexpr unsigned kMatcherNap = PFAC_MATCHER_NAP;   // ns between polls of a matcher waiting for a base
-constexpr int kPendCap = 128;                  // matches a warp can park in shared memory while bases are computed
+constexpr int kPendCap = PFAC_PEND_CAP;        // matches a warp can park in shared memory while bases are computed
 constexpr int kPendRecs = (PFAC_KLAG > 7) ? 16 : 8; // ... spread over at most this many rounds (power of two, > kLag)
 constexpr int kPendRecBytes = kPendRecs * 24;  // {round, n_smem, n_spill, tile start (u64)} per record
 constexpr int kSpillCap = 2048;                // per-warp spill ring in global memory (entries of 8 bytes)
