@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """Parity + timing runner for the BASELINE.json configs (lives under tests/ because it loads the
-oracle).  Runs one config end to end: generate the synthetic workload, check the CUDA
-path bit-exactly against the oracle (chunked, so inputs >= 2^31 bytes work), time it, and print
-one JSON line (also appended to gpurun_out/configs.jsonl).
+oracle).  Runs one config end to end: regenerate the synthetic text on the GPU (workloads/devgen),
+check the CUDA path bit-exactly against the reference's CPU matcher (oracle/_ref when present, else the
+C port; chunked, so inputs >= 2^31 bytes work), time it, and print one JSON line (also appended to
+gpurun_out/configs.jsonl; tools/keep_results.py moves those lines into profiles/).  The same configs at
+full size are part of the GPU suite (tests/test_gpu_configs.py); this script is for timing and ncu runs.
 
-    python tests/run_configs.py --config c2|c3|c4|c4dense|c5 [--bytes N] [--check-bytes M] [--steps K]
-    python -m torch.distributed.run --nproc-per-node 8 ... tests/run_configs.py --config c5
+    python tests/run_configs.py --config c2|c3|c4|c4dense|c5|wprefix_*|wan_* [--bytes N] [--check-bytes M] [--steps K]
+    python -m torch.distributed.run --nproc-per-node 8 ... tests/run_configs.py --config c5 [--gather]
 
 Configs:
   c2       1,000 patterns len 4-32 (255-symbol alphabet), 1 GiB planted random text, dense
   c3       20,000 Snort-like patterns, 4 GiB ASCII-weighted text, dense (64-bit indexing)
   c4       DNA, 5,000 patterns len 8-24, 2e9 bytes, reduce (both perf modes), natural density
   c4dense  c4 + 64 short patterns (len 4-6): high match density compaction
-  c5       10,000 Snort-like patterns, 32 GiB sharded over the ranks, reduce + global offset scan
+  c5       10,000 Snort-like patterns, 32 GiB sharded over the ranks, reduce + global offset scan (both the
+           NCCL all-gather cross-check and the in-kernel scan over peer memory, PFAC_comm)
+  wprefix_dense / wprefix_reduce, wan_dense / wan_reduce   adversarial texts (tests/configs.py)
 The oracle is test infrastructure (oracle/); the timed path is libpfac.so only.
 """
 import argparse
