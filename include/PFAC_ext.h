@@ -139,13 +139,14 @@ typedef struct {
     int hot_max_probe, cold_max_probe;
     int pre2_bits_set;     /* of 65536: (c0,c1) pairs that survive the prefilter */
     int root_fanout;       /* valid first bytes */
-    int hashed_filter;     /* 1 / 2: the per-position test is the hashed 4-gram filter (8192 words), 1 or 2 bits per lookup */
-    int hfilt_bits_set;    /* of 262144 */
+    int hashed_filter;     /* 1 / 2: the per-position test is the hashed 4-gram filter (hfilt_words words), 1 or 2 bits per lookup */
+    int hfilt_bits_set;    /* of 32 * hfilt_words */
     int code_shift;        /* b = 2 with an arithmetic symbol code: code = (byte >> code_shift) & 3; else -1.  With
                               hashed_filter == 2 and code_bits == 2 the first stage hashes ten symbols (20 bits):
                               word ((x * 0x9E3779B1) >> 19) & 8191, bits 31 - ((x * 0x85EBCA6B) >> 27) and
                               31 - ((x * 0xC2B2AE35) >> 27), products mod 2^32 */
     size_t device_bytes;   /* total bytes uploaded */
+    unsigned hfilt_words;  /* words of the hashed filter: 0, 8192, or 16384 (hashed_filter == 2, byte alphabet, budget >= 64 KB) */
 } PFAC_tableInfo_t;
 
 PFAC_status_t PFAC_tableCompile(const char *image, size_t size, size_t hot_budget_bytes,
@@ -175,9 +176,11 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
                                    const unsigned **best2, const unsigned short **chk2);
 
 /* hashed 4-gram first stage, used instead of pre2 as the per-position test for byte alphabets
- * (b = 8) whenever the shared-memory budget holds its 32 KB: 8192 unsigned, NULL when
- * hashed_filter == 0.  x = c0|c1<<8|c2<<16|c3<<24, word ((x * 0x9E3779B1) >> 2) & 8191, bit
- * 31 - (umulhi(x, 0x85EBCA6B) & 31) and, when hashed_filter == 2 (dense tables), also bit
+ * (b = 8) whenever the shared-memory budget holds its 32 KB: hfilt_words unsigned, NULL when
+ * hashed_filter == 0.  x = c0|c1<<8|c2<<16|c3<<24.  hashed_filter == 1 (sparse tables): word
+ * ((x * 0x9E3779B1) >> 2) & 8191, bit 31 - (umulhi(x, 0x85EBCA6B) & 31).  hashed_filter == 2 (dense
+ * tables): word x & (hfilt_words - 1), i.e. picked by c0 and the low bits of c1 themselves (a 1-byte
+ * pattern then fills the words of its own first byte only), that bit and bit
  * 31 - (umulhi(x, 0xC2B2AE35) & 31); survivors are re-checked exactly against pre2 / chk2 by the walker.
  * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
 PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);

@@ -64,7 +64,7 @@ class TableInfo(ctypes.Structure):
                 ("cold_max_probe", ctypes.c_int), ("pre2_bits_set", ctypes.c_int),
                 ("root_fanout", ctypes.c_int), ("hashed_filter", ctypes.c_int),
                 ("hfilt_bits_set", ctypes.c_int), ("code_shift", ctypes.c_int),
-                ("device_bytes", ctypes.c_size_t)]
+                ("device_bytes", ctypes.c_size_t), ("hfilt_words", ctypes.c_uint)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -583,7 +583,7 @@ class TableCompiler:
             "lut": arr(p2[0], 256, np.uint8),
             "best2": arr(p2[1], max(info["pre2_bits_set"], 1) * 4 if info["has_best2"] else 0, np.uint32),
             "chk2": arr(p2[2], max(info["pre2_bits_set"], 1) * 2 if info["has_chk2"] else 0, np.uint16),
-            "hfilt": arr(pf, 32768 if info["hashed_filter"] else 0, np.uint32),
+            "hfilt": arr(pf, 4 * info["hfilt_words"], np.uint32),
             "hfilt_k": info["hashed_filter"], "code_shift": info["code_shift"],
             "code_bits": info["code_bits"], "gram_len": info["gram_len"],
             "hot_depth": info["hot_depth"], "mul": info["hash_mul"],

@@ -1647,6 +1647,7 @@ static void fillInfo(const pfac::Machine& m, const pfac::DeviceLayout& L, PFAC_t
     info->hfilt_bits_set = L.hfiltBitsSet;
     info->code_shift = L.codeShift;
     info->device_bytes = L.deviceBytes();
+    info->hfilt_words = unsigned(L.hfilt.size());
 }
 
 PFAC_status_t PFAC_tableCompile(const char* image, size_t size, size_t hot_budget_bytes, PFAC_table_t* table) {

@@ -24,6 +24,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace pfac {
 
@@ -82,7 +84,7 @@ struct KParams {
     const uint4* cold;
     const uint4* chains;
     const unsigned char* tails;
-    uint32_t hfilt_bytes;       // 0 or kHashFilterWords * 4 (hashed 4-gram first stage, always staged in smem)
+    uint32_t hfilt_bytes;       // 0, kHashFilterWords * 4 or (row-indexed filter) twice that (hashed 4-gram first stage, always staged in smem)
     uint32_t chk2_bytes;        // multiple of 16, 0 = no second prefilter stage (always staged in smem)
     uint32_t next2_bytes;       // multiple of 16 (copied to smem when next2_hot; best2 has the same size)
     int has_best2;
@@ -117,6 +119,7 @@ struct Tables {
     const uint32_t* best2;      // smem or global; nullptr when no pattern is shorter than K
     const unsigned short* chk2; // smem; nullptr when the second prefilter stage is off
     const uint32_t* hfilt;      // smem; nullptr unless the first stage is the hashed 4-gram filter
+    uint32_t hfilt_mask;        // byte-offset mask of the row-indexed filter (FILT 3): words * 4 - 4
     const uint4* hot;           // smem
     const uint4* cold;          // global
     const uint4* chains;        // smem or global
@@ -179,6 +182,7 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_but_newest() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
@@ -304,6 +308,7 @@ __device__ __forceinline__ Tables stage_tables(const KParams& p, unsigned char* 
         t.hfilt = reinterpret_cast<const uint32_t*>(var);
         var += p.hfilt_bytes / 16;
     }
+    t.hfilt_mask = p.hfilt_bytes ? p.hfilt_bytes - 4u : 0u;
     t.chk2 = nullptr;
     if (p.chk2_bytes) {
 #pragma unroll 1
@@ -374,6 +379,7 @@ struct FilterView {
     const unsigned short* chk2;
     const unsigned char* lut;
     int code_shift;
+    uint32_t hfilt_mask;
 };
 template <typename TT>
 __device__ __forceinline__ bool second_stage(const TT& T, uint32_t idx, uint32_t word, uint32_t next_byte) {
@@ -426,11 +432,13 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
             for (int j = 3; j >= 0; j--) {
                 const uint32_t x = (j == 0) ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);  // c0 | c1<<8 | ..
                 if (FILT >= 2) {
-                    // word picked by (c0,c1) -- bits 2..14 of the product are its byte offset -- two bits
-                    // by all four bytes; the multiplies run on the FMA pipe, the ALU pipe is the busy one
-                    const uint32_t h = x * kHashFilterMul;
+                    // word picked by (c0,c1), bits by all four bytes.  Sparse tables (FILT 2): bits 2..14 of
+                    // the product are the word's byte offset; dense tables (FILT 3): row-indexed, word
+                    // x & (words - 1).  The multiplies run on the FMA pipe, the ALU pipe is the busy one
+                    const uint32_t off = (FILT == 3) ? ((x << 2) & T.hfilt_mask)
+                                                     : ((x * kHashFilterMul) & static_cast<uint32_t>(kHashFilterWords * 4 - 4));
                     const uint32_t hw = *reinterpret_cast<const uint32_t*>(
-                        reinterpret_cast<const unsigned char*>(T.hfilt) + (h & static_cast<uint32_t>(kHashFilterWords * 4 - 4)));
+                        reinterpret_cast<const unsigned char*>(T.hfilt) + off);
                     // rotate the bit to the top; dense tables (FILT 3) test a second one
                     uint32_t rot = __funnelshift_l(hw, hw, __umulhi(x, kHashFilterMul2));
                     if (FILT == 3) rot &= __funnelshift_l(hw, hw, __umulhi(x, kHashFilterMul3));
@@ -1147,7 +1155,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     unsigned char* s_in = mine + kRedWarpFixed;
     // this warp's spill ring in global memory (L2-resident): entry = id | position in tile << 32
     unsigned long long* spill = p.park + (static_cast<size_t>(b) * kRedMatchers + warp) * kSpillCap;
-    const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut, T.code_shift};
+    const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut, T.code_shift, T.hfilt_mask};
 
     auto issue_load = [&](uint32_t t, int st) {
         if (t < p.bulk_tiles) {
@@ -1395,6 +1403,251 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
     }
 }
 
+// =================================================================================================
+// Dense kernel, second form: zero-fill by bulk stores + patches.
+//
+// The dense result is zeros but for one int per match, and matches are few.  The first form builds
+// every 512-position slice of the result in shared memory (clear, patch, bulk store): 2 KB of shared
+// memory per warp, four STS.128 per lane and tile, and a walker entry per 512 positions.  Here a warp
+// tile is kD2Sub = 3 consecutive 512-position blocks (1536 positions, one bulk load, as in the reduce
+// kernel); its 6 KB of results are written by ONE bulk store from a zero buffer the whole CTA shares,
+// issued before the tile's input is even waited for, and the walker's matches are stored straight to
+// global memory once that bulk store has completed (cp.async.bulk.wait_group by the issuing lane: its
+// writes are then visible to that thread; __syncwarp orders the other lanes' stores after it).  Nobody
+// waits for a store that has just been issued: a tile's matches are parked in a 64-entry list and
+// written at the start of the next tile, one tile time (microseconds) after their zeros left
+// (wait_group 1: everything but the newest store); only a tile with more matches than the list holds
+// waits for its own zeros.  (Patching right after the walk measured 11 % slower on C2: a third of its
+// tiles hold a match, and each made its warp sit out the write queue of an HBM-bound kernel.)
+// The patches land on lines the zero store has just put into L2, so DRAM still sees 4 bytes per
+// position.  What this buys: the walker is entered once per 1536 positions (with the row-indexed filter
+// a batch of 32 lanes is then two thirds full on the 20,000-pattern dictionary instead of every tile
+// needing its own batch), no per-tile clearing, 64 KB of shared memory for the tables (the 64 KB filter,
+// or chains and tails of a 1,000-pattern dictionary), and 6 KB bulk stores.
+// shared memory: [mbarriers][root | pre2 | rank2 | lut][zeros 6 KB][per warp: queue 512 B | parked ids 256 B |
+// parked positions 128 B | 2 input stages][hfilt][chk2][next2][hot][chains][tails]
+// =================================================================================================
+constexpr int kD2Sub = kRedSub;
+constexpr int kD2Tile = kD2Sub * kWarpTile;    // 1536 start positions per warp per iteration
+constexpr int kD2Stages = 2;
+constexpr int kD2Pend = 64;                    // matches a warp parks until their tile's zeros have landed
+constexpr int kD2WarpFixed = kQueueCap * 2 + kD2Pend * 6;
+static_assert((kD2WarpFixed & 15) == 0, "input stages are 16-byte aligned (bulk copies)");
+static_assert(kD2Sub == 3, "the survivor scan below packs three 10-bit counts");
+
+template <int CODE, int FILT>
+__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KParams p) {
+    constexpr int NSTAGE = kD2Stages;
+    constexpr bool HASHED = FILT >= 2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int stage = kD2Tile + p.halo;
+    const int per_warp = kD2WarpFixed + NSTAGE * stage;
+    constexpr int kBarBytes = ((kDenseWarps * NSTAGE * 8 + 127) / 128) * 128;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
+    unsigned char* s_fixed = smem + kBarBytes;
+    unsigned char* s_zero = s_fixed + kFixedTableBytes;
+    unsigned char* s_warp = s_zero + kD2Tile * 4;
+    unsigned char* s_var = s_warp + kDenseWarps * per_warp;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tid) >> 5, 0);
+
+    const Tables T = stage_tables(p, s_fixed, s_var, tid, kDenseThreads);
+#pragma unroll 1
+    for (int i = tid; i < kD2Tile * 4 / 16; i += kDenseThreads) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();  // the zeros are read by bulk stores (async proxy) only
+    unsigned long long* bar = s_bar + warp * NSTAGE;
+    if (lane == 0) {
+        for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide barrier
+
+    unsigned char* mine = s_warp + warp * per_warp;
+    unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
+    int* pend_id = reinterpret_cast<int*>(mine + kQueueCap * 2);
+    unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kQueueCap * 2 + kD2Pend * 4);
+    unsigned char* s_in = mine + kD2WarpFixed;
+    const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut, T.code_shift, T.hfilt_mask};
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // consecutive warps of a CTA take consecutive tiles; tiles advance by the grid
+    const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
+    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kD2Tile);  // tiles with 1536 owned positions
+    const uint32_t tstride = gridDim.x * kDenseWarps;
+    uint32_t tile = blockIdx.x * kDenseWarps + warp;
+
+    auto issue_load = [&](uint32_t t, int st) {  // one elected lane; tiles beyond bulk_tiles are copied at use
+        if (t < p.bulk_tiles) {
+            mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
+            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kD2Tile, static_cast<uint32_t>(stage),
+                        &bar[st]);
+        }
+    };
+    if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < NSTAGE; i++) issue_load(tile + i * tstride, i);
+    }
+
+    uint32_t parity = 0u;  // bit s = phase of bar[s]
+    int st = 0;
+    int npend = 0;            // parked matches, all of the previous tile (of the current one while it is walked)
+    auto write_parked = [&](uint32_t t) {  // t: the tile they belong to
+        int* o = p.out + static_cast<size_t>(t) * kD2Tile;
+#pragma unroll 1
+        for (int i = lane; i < npend; i += 32) o[pend_pos[i]] = pend_id[i];
+        npend = 0;
+    };
+    for (; tile < num_tiles; tile += tstride) {
+        const unsigned char* inb = s_in + st * stage;
+        const size_t start = static_cast<size_t>(tile) * kD2Tile;
+        int* gout = p.out + start;
+        const long long owned_left = p.n_owned - static_cast<long long>(start);
+        const int tile_valid = owned_left > kD2Tile ? kD2Tile : static_cast<int>(owned_left);
+        // ---- the tile's zeros leave first: one 6 KB bulk store, in flight while the tile is matched
+        const bool bulk_out = p.out_aligned && tile < full_tiles;
+        if (bulk_out) {
+            if (elect_one()) {
+                tma_store_1d(gout, s_zero, kD2Tile * 4);
+                tma_store_commit();
+            }
+        } else {  // odd pointers and the tail tile: plain stores
+#pragma unroll 1
+            for (int i = lane; i < tile_valid; i += 32) gout[i] = 0;
+        }
+        __syncwarp();
+        // ---- the previous tile's matches: its zeros left a whole tile ago
+        if (npend > 0) {  // (parked matches imply that tile's zeros left by a bulk store)
+            if (elect_one()) {  // everything but the store just issued (if one was) has been written
+                if (bulk_out) tma_store_wait_but_newest();
+                else tma_store_wait_all();
+            }
+            __syncwarp();
+            write_parked(tile - tstride);
+        }
+        if (tile < p.bulk_tiles) {
+            mbar_wait(&bar[st], (parity >> st) & 1u);
+            parity ^= 1u << st;
+        } else {
+            // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
+            unsigned char* w = s_in + st * stage;
+#pragma unroll 1
+            for (int i = lane; i < stage; i += 32) {
+                const long long g = static_cast<long long>(start) + i;
+                w[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
+            }
+            __syncwarp();
+        }
+        const long long total_left = p.n_total - static_cast<long long>(start);
+        const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
+
+        // ---- survivors of the three blocks (one copy of the prefilter, run three times), one scan for
+        // all three counts (10-bit fields)
+        uint32_t cand[kD2Sub], slow[kD2Sub];
+        uint32_t packed = 0;
+        cand[0] = cand[1] = cand[2] = slow[0] = slow[1] = slow[2] = 0u;
+#pragma unroll 1
+        for (int j = 0; j < kD2Sub; j++) {
+            uint32_t sl;
+            const uint32_t cd = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, sl);
+            if (j == 0) { cand[0] = cd; slow[0] = sl; }
+            else if (j == 1) { cand[1] = cd; slow[1] = sl; }
+            else { cand[2] = cd; slow[2] = sl; }
+            packed |= static_cast<uint32_t>(__popc(cd | sl)) << (10 * j);
+        }
+        const uint32_t incl = warp_incl_scan(packed, lane);
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const int wtotal = static_cast<int>((tot & 1023u) + ((tot >> 10) & 1023u) + (tot >> 20));
+        // normally one segment: the whole tile's survivors.  Dense survivors are walked one block at a
+        // time, or 8 lanes of a block at a time (<= 128 survivors) when a block alone overflows the
+        // queue, the block's prefilter recomputed out of line; one walker call site either way.
+        int nseg = 0, seg_total = wtotal;
+        if (wtotal > 0 && wtotal <= kQueueCap) {
+            nseg = 1;
+            const uint32_t excl = incl - packed;
+            int qbase = 0;
+#pragma unroll
+            for (int j = 0; j < kD2Sub; j++) {
+                uint32_t all = cand[j] | slow[j];
+                int o = qbase + static_cast<int>((excl >> (10 * j)) & 1023u);
+                const int lb = j * kWarpTile + lane * kPosPerThread;
+                while (all) {
+                    const int bit = __ffs(all) - 1;
+                    all &= all - 1;
+                    q16[o++] = static_cast<unsigned short>((lb + bit) | (((slow[j] >> bit) & 1u) ? kSlowFlag : 0u));
+                }
+                qbase += static_cast<int>((tot >> (10 * j)) & 1023u);
+            }
+        } else if (wtotal > 0) {
+            const bool by_block = (tot & 1023u) <= kQueueCap && ((tot >> 10) & 1023u) <= kQueueCap && (tot >> 20) <= kQueueCap;
+            nseg = by_block ? kD2Sub : kD2Sub * 4;
+        }
+        bool zeros_landed = !bulk_out;  // plain zero stores are ordered before the patches by the __syncwarp above
+        for (int seg = 0; seg < nseg; seg++) {
+            if (nseg > 1) {
+                __syncwarp();  // the previous segment's queue has been read
+                const int j = (nseg == kD2Sub) ? seg : (seg >> 2);
+                const uint32_t both = block_survivors_cold<CODE, FILT>(fv, inb, j, lane, tile_rem, tile_valid);
+                const uint32_t sl = both >> 16;
+                uint32_t all = (both & 0xFFFFu) | sl;
+                const uint32_t cnt = static_cast<uint32_t>(__popc(all));
+                const uint32_t inc = warp_incl_scan(cnt, lane);
+                uint32_t lo = 0, hi = __shfl_sync(0xffffffffu, inc, 31);
+                if (nseg != kD2Sub) {
+                    const int g = seg & 3;
+                    lo = g ? __shfl_sync(0xffffffffu, inc, 8 * g - 1) : 0u;
+                    hi = __shfl_sync(0xffffffffu, inc, 8 * g + 7);
+                    if ((lane >> 3) != g) all = 0;
+                }
+                int o = static_cast<int>(inc - cnt - lo);
+                const int lb = j * kWarpTile + lane * kPosPerThread;
+                while (all) {
+                    const int bit = __ffs(all) - 1;
+                    all &= all - 1;
+                    q16[o++] = static_cast<unsigned short>((lb + bit) | (((sl >> bit) & 1u) ? kSlowFlag : 0u));
+                }
+                seg_total = static_cast<int>(hi - lo);
+            }
+            __syncwarp();
+            // ---- walk the queue 32 survivors at a time; a batch's matches go straight to the result
+            for (int base = 0; base < seg_total; base += 32) {
+                const int qslot = base + lane;
+                const bool active = qslot < seg_total;
+                const unsigned qe = active ? q16[qslot] : 0u;
+                int pl;
+                const int best = walk_batch<CODE, HASHED>(T, inb, stage, p.in + start, tile_rem, active, qe, pl);
+                const unsigned m = __ballot_sync(0xffffffffu, best != 0);
+                if (m == 0) continue;
+                const int c = __popc(m);
+                if (bulk_out && !zeros_landed && npend + c <= kD2Pend) {
+                    if (best) {
+                        const int e = npend + __popc(m & lt_mask);
+                        pend_id[e] = best;
+                        pend_pos[e] = static_cast<unsigned short>(pl);
+                    }
+                    npend += c;
+                    continue;
+                }
+                // more matches than the list holds (or plain zero stores): straight to the result from here on
+                if (!zeros_landed) {
+                    if (elect_one()) tma_store_wait_all();   // this tile's zeros (and all earlier ones) are written
+                    zeros_landed = true;
+                }
+                __syncwarp();
+                write_parked(tile);
+                if (best) gout[pl] = best;
+            }
+        }
+        __syncwarp();
+        if (elect_one()) issue_load(tile + NSTAGE * tstride, st);  // every lane is done with this stage
+        st = (st + 1 == NSTAGE) ? 0 : st + 1;
+    }
+    if (elect_one()) tma_store_wait_all();  // shared memory must outlive the bulk stores
+    __syncwarp();
+    write_parked(tile - tstride);
+}
+
 // a rank whose shard is empty still takes part in the exchange
 __global__ void pfac_comm_scan_kernel(const KParams p) { comm_exchange_scan(p, 0ull, threadIdx.x & 31); }
 
@@ -1462,6 +1715,22 @@ size_t denseFixedBytes(int halo) {
            size_t(kDenseWarps) * (kWarpTile * 2 + kWarpTile * 4 + nst * (kWarpTile + halo));
 }
 
+size_t dense2FixedBytes(int halo) {
+    const size_t bar = size_t((kDenseWarps * kD2Stages * 8 + 127) / 128) * 128;
+    return bar + kFixedTableBytes + size_t(kD2Tile) * 4 +
+           size_t(kDenseWarps) * (kD2WarpFixed + kD2Stages * (kD2Tile + halo));
+}
+
+// PFAC_B200_DENSE=v1 keeps the first form of the dense kernel (results built in shared memory per
+// 512-position tile); read once, before the first table is compiled (the budgets differ)
+bool denseFirstForm() {
+    static const bool v1 = [] {
+        const char* v = getenv("PFAC_B200_DENSE");
+        return v && !strcmp(v, "v1");
+    }();
+    return v1;
+}
+
 size_t reduceFixedBytes(int halo) {
     const size_t bar = size_t((kRedWarps * kRedStages * 8 + 127) / 128) * 128;
     return bar + kFixedTableBytes + kRingBytes +
@@ -1516,7 +1785,7 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
 
 size_t tableSmemBudget(int maxPatternLen, bool reduceKernel) {
     const int halo = roundHalo(maxPatternLen, kDenseMaxHalo);
-    const size_t fixed = reduceKernel ? reduceFixedBytes(halo) : denseFixedBytes(halo);
+    const size_t fixed = reduceKernel ? reduceFixedBytes(halo) : (denseFirstForm() ? denseFixedBytes(halo) : dense2FixedBytes(halo));
     return fixed < size_t(kMaxSmem) ? size_t(kMaxSmem) - fixed : 0;
 }
 
@@ -1534,6 +1803,7 @@ unsigned long long kernelLaunchCount() { return g_launches.load(); }
 
 namespace {
 const void* denseKernelFor(const DeviceTable& t, int nst);
+const void* dense2KernelFor(const DeviceTable& t);
 const void* reduceKernelFor(const DeviceTable& t, bool pos64);
 }  // namespace
 
@@ -1541,7 +1811,8 @@ const void* reduceKernelFor(const DeviceTable& t, bool pos64);
 // that cost (about 2 ms per kernel) from the caller's first match call to the pattern load, where the
 // reference pays its own table upload.  One call per table.
 cudaError_t prepareKernels(const DeviceTable& dense, const DeviceTable& reduce) {
-    const void* ks[3] = {denseKernelFor(dense, denseStages(roundHalo(dense.maxPatternLen, kDenseMaxHalo))),
+    const void* ks[3] = {denseFirstForm() ? denseKernelFor(dense, denseStages(roundHalo(dense.maxPatternLen, kDenseMaxHalo)))
+                                          : dense2KernelFor(dense),
                          reduceKernelFor(reduce, false), reduceKernelFor(reduce, true)};
     for (const void* k : ks) {
         if (!k) return cudaErrorInvalidValue;
@@ -1555,6 +1826,33 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
                              size_t n_owned, size_t n_total, int* out, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
     const int halo = roundHalo(t.maxPatternLen, kDenseMaxHalo);
+    if (!denseFirstForm()) {
+        KParams p = baseParams(t, in, n_owned, n_total, halo, kD2Tile);
+        if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+        p.out = out;
+        p.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+        {   // tile t is staged by TMA iff the pointer is 16-byte aligned and t*1536 + stage <= n_total
+            const long long stage = kD2Tile + halo;
+            long long bulk = 0;
+            if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kD2Tile + 1;
+            if (bulk > p.num_tiles) bulk = p.num_tiles;
+            p.bulk_tiles = static_cast<uint32_t>(bulk);
+        }
+        const size_t smem = dense2FixedBytes(halo) + tableSmemBytes(t);
+        if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
+        const void* kernel = dense2KernelFor(t);
+        if (!kernel) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e != cudaSuccess) return e;
+        const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
+        long long grid = cfg.numSMs;
+        if (grid > ctaTiles) grid = ctaTiles;
+        void* args[] = {&p};
+        e = cudaLaunchKernel(kernel, dim3(unsigned(grid)), dim3(kDenseThreads), args, smem, stream);
+        if (e != cudaSuccess) return e;
+        g_launches++;
+        return cudaGetLastError();
+    }
     KParams p = baseParams(t, in, n_owned, n_total, halo, kWarpTile);
     if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;  // 1 TiB per launch
     p.out = out;
@@ -1659,6 +1957,27 @@ const void* denseKernelFor(const DeviceTable& t, int nst) {
         case 2:  // hashed 10-mer first stage when the table compiler built one (arithmetic symbol code)
             if (t.hfiltBytes) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 2, 4> : (const void*)pfac_dense_kernel<2, 2, 4>;
             else kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 2, 0> : (const void*)pfac_dense_kernel<2, 2, 0>;
+            break;
+        default: return nullptr;
+    }
+    if (t.codeBits == 4 && filt) return nullptr;
+    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return nullptr;
+    return kernel;
+}
+const void* dense2KernelFor(const DeviceTable& t) {
+    const void* kernel = nullptr;
+    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
+    switch (t.codeBits) {
+        case 8:
+            if (filt == 3) kernel = (const void*)pfac_dense2_kernel<8, 3>;
+            else if (filt == 2) kernel = (const void*)pfac_dense2_kernel<8, 2>;
+            else if (filt == 1) kernel = (const void*)pfac_dense2_kernel<8, 1>;
+            else kernel = (const void*)pfac_dense2_kernel<8, 0>;
+            break;
+        case 4: kernel = (const void*)pfac_dense2_kernel<4, 0>; break;
+        case 2:
+            if (t.hfiltBytes) kernel = (const void*)pfac_dense2_kernel<2, 4>;
+            else kernel = (const void*)pfac_dense2_kernel<2, 0>;
             break;
         default: return nullptr;
     }

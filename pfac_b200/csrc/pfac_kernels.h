@@ -26,7 +26,7 @@ struct DeviceTable {
     const unsigned short* chk2 = nullptr;  // second prefilter stage (chk2Bytes > 0), always staged in smem
     uint32_t chk2Bytes = 0;           // multiple of 16; 0 = stage off
     const uint32_t* hfilt = nullptr;  // hashed 4-gram first stage (hfiltBytes > 0), always staged in smem
-    uint32_t hfiltBytes = 0;          // 0 or kHashFilterWords * 4
+    uint32_t hfiltBytes = 0;          // 0, 32 KB, or 64 KB (hfiltK == 2, byte alphabets: row-indexed)
     int hfiltK = 0;                   // bits tested per lookup (1 or 2)
     uint32_t next2Bytes = 0;
     bool next2Hot = false;            // kernels copy next2 (+ best2) into shared memory

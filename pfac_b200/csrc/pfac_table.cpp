@@ -456,15 +456,25 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
     // hashed 4-gram first stage (see pfac_table.h) for every byte-alphabet dictionary whose
     // shared-memory budget holds its 32 KB: measured faster than the exact 2-gram stage from 1,000
     // random patterns (+11 %) to 20,000 Snort-like ones (+29 %)
-    const size_t hfiltBytes = size_t(kHashFilterWords) * 4;
+    size_t hfiltBytes = size_t(kHashFilterWords) * 4;
     if (B == 8 && !frontier.empty() && hotBudgetBytes >= hfiltBytes && filterPolicy != kFilterExact) {
-        // one bit per 4-gram first; a table that comes out dense (> 2 % of its bits, whole words of short
-        // patterns aside) is rebuilt with two
+        // one bit per 4-gram first, word picked by a hash of (c0, c1 & 127): sparse dictionaries.  A table
+        // that comes out dense (> 2 % of its bits, whole words of short patterns aside) is rebuilt with two
+        // bits per gram, twice the words when the budget holds them, and the word picked by the text bits
+        // themselves, x & (words - 1) = c0 | (c1 & 63 or 31) << 8: the words one first byte can reach are
+        // then its own (64 or 32 of them), so a 1-byte pattern fills those and nothing else.  Hashed, its
+        // 128 all-ones words are shared with three other (c0, c1) pairs each: on the 20,000-pattern
+        // Snort-like dictionary 11 of the 25 survivors per 512 positions were such collisions, and the
+        // 32 KB table passed 9 false 4-grams more (64 KB, row-indexed: 11 survivors, 4 of them true).
         for (L.hfiltK = 1; L.hfiltK <= 2; L.hfiltK++) {
-            L.hfilt.assign(size_t(kHashFilterWords), 0u);
+            size_t words = size_t(kHashFilterWords);
+            if (L.hfiltK == 2 && hotBudgetBytes >= size_t(kHashFilterWordsMax) * 4) words = size_t(kHashFilterWordsMax);
+            L.hfilt.assign(words, 0u);
             L.hfiltBitsSet = 0;
+            const bool rows = L.hfiltK == 2;
             auto word = [&](uint32_t x) -> uint32_t& {
-                return L.hfilt[((x * kHashFilterMul) >> 2) & uint32_t(kHashFilterWords - 1)];
+                return rows ? L.hfilt[x & uint32_t(words - 1)]
+                            : L.hfilt[((x * kHashFilterMul) >> 2) & uint32_t(kHashFilterWords - 1)];
             };
             auto setGram = [&](uint32_t x) {
                 const uint32_t b1 = uint32_t((uint64_t(x) * kHashFilterMul2) >> 32) & 31u;
@@ -496,9 +506,10 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
             }
             if (L.hfiltK == 2 || gramBits <= kHashFilterWords * 32 / 50) break;
         }
-        if (L.hfiltBitsSet > kHashFilterWords * 32 / 2 && filterPolicy != kFilterHashed) {
-            // saturated (e.g. dozens of 1-byte patterns, each filling 256 words): it would pass most
-            // positions to the walker; the exact 2-gram stage with its inline second stage does better
+        hfiltBytes = L.hfilt.size() * 4;
+        if (size_t(L.hfiltBitsSet) > L.hfilt.size() * 32 / 2 && filterPolicy != kFilterHashed) {
+            // saturated (e.g. dozens of 1-byte patterns): it would pass most positions to the walker; the
+            // exact 2-gram stage with its inline second stage does better
             L.hfilt.clear();
             L.hfiltK = 0;
             L.hfiltBitsSet = 0;
@@ -506,6 +517,7 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
             hotBudgetBytes -= hfiltBytes;
         }
     }
+    hfiltBytes = size_t(kHashFilterWords) * 4;
 
     // hashed 10-mer first stage for 2-bit alphabets with an arithmetic code (DNA): the exact 8-mer set of
     // 5,000 patterns passes 7.3 % of all positions (4,794 of 65,536 8-mers), four walker batches per
@@ -659,7 +671,7 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
 namespace {
 
 constexpr char kFileMagic[8] = {'P', 'F', 'A', 'C', 'B', '2', '0', '0'};
-constexpr uint32_t kFileVersion = 4;  // bump whenever Machine / DeviceLayout or their meaning change
+constexpr uint32_t kFileVersion = 5;  // bump whenever Machine / DeviceLayout or their meaning change
 
 struct Writer {
     std::string buf;
@@ -778,7 +790,7 @@ void getLayout(Reader& r, DeviceLayout& L) {
     r.pod(L.hotMaxProbe); r.pod(L.coldMaxProbe); r.pod(L.pre2BitsSet); r.pod(L.rootFanout);
     // sizes the kernels rely on
     if (r.ok && (L.pre2.size() != 2048 || L.rank2.size() != 2048 || L.next2.empty() ||
-                 (!L.hfilt.empty() && L.hfilt.size() != size_t(kHashFilterWords)) ||
+                 (!L.hfilt.empty() && L.hfilt.size() != size_t(kHashFilterWords) && L.hfilt.size() != size_t(kHashFilterWordsMax)) ||
                  L.hot.size() != size_t(L.hotBuckets) * 4 || L.cold.size() != size_t(L.coldBuckets) * 4 ||
                  (L.chains.size() & 3) || (L.tails.size() & 15)))
         r.ok = false;
@@ -825,8 +837,11 @@ bool validLayout(const DeviceLayout& L, const Machine& m) {
     if (!L.best2.empty() && L.best2.size() != L.next2.size()) PFAC_INVALID;
     if (!L.chk2.empty() && L.chk2.size() != L.next2.size()) PFAC_INVALID;
     if (L.codeShift < -1 || L.codeShift > 6 || (L.codeShift >= 0 && L.codeBits != 2)) PFAC_INVALID;
-    if (!L.hfilt.empty() && (L.hfilt.size() != size_t(kHashFilterWords) || L.hfiltK < 1 || L.hfiltK > 2 ||
+    if (!L.hfilt.empty() && (L.hfiltK < 1 || L.hfiltK > 2 ||
                              !(L.codeBits == 8 || (L.codeBits == 2 && L.codeShift >= 0 && L.hfiltK == 2)))) PFAC_INVALID;
+    // 64 KB only for the row-indexed two-bit filter of byte alphabets
+    if (!L.hfilt.empty() && L.hfilt.size() != size_t(kHashFilterWords) &&
+        !(L.hfilt.size() == size_t(kHashFilterWordsMax) && L.codeBits == 8 && L.hfiltK == 2)) PFAC_INVALID;
     if (L.codeShift >= 0)   // the kernels code text bytes arithmetically: lut must agree for every alphabet byte
         for (int c = 0; c < kCharSet; c++)
             if (!(L.lut[c] & 0x80) && L.lut[c] != uint8_t((c >> L.codeShift) & 3)) PFAC_INVALID;

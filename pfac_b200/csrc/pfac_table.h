@@ -79,15 +79,21 @@ constexpr uint32_t kLeafPlain = 0x40000000u;  // plain state value: no out-edges
 
 //   hfilt (byte alphabets, when the shared-memory budget holds it): with tens of thousands of
 //     patterns the exact 2-gram set passes a third of all text positions, and even with 1,000 it
-//     passes 1.5 %.  A hashed 4-gram filter takes its place as the per-position test: x = c0|c1<<8|c2<<16|c3<<24, word ((x * kHashFilterMul) >> 2) & 8191,
-//     bits 31 - (umulhi(x, kHashFilterMul2) & 31) and 31 - (umulhi(x, kHashFilterMul3) & 31), the
-//     second only when the table is dense (hfiltK = 2: two hash functions into one word, a blocked
-//     Bloom filter; it takes C3 from 43 to 25 survivors per 512 positions, +16 % throughput, but its
-//     three extra instructions per position cost C2, whose one-bit table passes 0.4 %, 10 %).  Bits 2..14 of the product depend on c0,c1 only
-//     (and x -> product mod 2^16 is a bijection, so every word serves exactly eight 2-grams): the
-//     word is chosen by the 2-gram, the bits by all four bytes.  A 4-byte prefix of a pattern sets its
-//     two bits, a 3-byte pattern the bits of its 256 continuations, a 2-byte pattern its whole word, a 1-byte pattern
-//     the 256 words of (c0,*).  Bytes past the end of the input therefore never hide a short match.
+//     passes 1.5 %.  A hashed 4-gram filter takes its place as the per-position test:
+//     x = c0|c1<<8|c2<<16|c3<<24 picks one word and one or two bits of it,
+//     31 - (umulhi(x, kHashFilterMul2) & 31) and 31 - (umulhi(x, kHashFilterMul3) & 31).
+//       hfiltK = 1 (sparse tables, C2: 0.4 % of the positions pass): 8192 words, word
+//     ((x * kHashFilterMul) >> 2) & 8191 -- bits 2..14 of the product depend on c0 and seven bits of c1
+//     only -- and the first bit.
+//       hfiltK = 2 (dense tables): both bits (two hash functions into one word, a blocked Bloom filter)
+//     and the word is x & (words - 1) = c0 | (c1 & 63) << 8 with 16384 words (64 KB) when the budget
+//     holds them, c0 | (c1 & 31) << 8 with 8192.  Row-indexed: the words a first byte can reach are its
+//     own, so the all-ones words of a 1-byte pattern catch that byte and nothing else (hashed, each was
+//     shared with three other 2-grams: 11 of C3's 25 survivors per 512 positions).
+//     Either way the word is chosen by (c0, c1), the bits by all four bytes.  A 4-byte prefix of a
+//     pattern sets its bits, a 3-byte pattern the bits of its 256 continuations, a 2-byte pattern its
+//     whole word, a 1-byte pattern every word of (c0,*).  Bytes past the end of the input therefore
+//     never hide a short match.
 //     The walker re-checks survivors against pre2 (+ chk2) exactly.  (One IMAD + one LOP3 give the
 //     byte offset of the word, one IMAD.HI each bit: the multiplies run on the FMA pipe, which the
 //     kernels otherwise leave idle, instead of the ALU pipe that bounds them.)
@@ -95,6 +101,7 @@ constexpr uint32_t kHashFilterMul = 0x9E3779B1u;
 constexpr uint32_t kHashFilterMul2 = 0x85EBCA6Bu;
 constexpr uint32_t kHashFilterMul3 = 0xC2B2AE35u;
 constexpr int kHashFilterWords = 8192;           // 32 KB of shared memory
+constexpr int kHashFilterWordsMax = 16384;       // row-indexed two-bit filter when the budget holds 64 KB
 constexpr int kDnaGram = 10;                     // symbols hashed by the first stage of 2-bit alphabets
 enum FilterPolicy { kFilterAuto = 0, kFilterExact = 1, kFilterHashed = 2 };
 
@@ -112,8 +119,9 @@ struct DeviceLayout {
     // when the K-gram alone already yields a result.  Used as a second prefilter stage (in shared
     // memory) when the first one lets many positions through; empty = stage off.
     std::vector<uint16_t> chk2;
-    std::vector<uint32_t> hfilt;     // kHashFilterWords words, or empty (exact 2-gram first stage)
-    int hfiltK = 0;                  // bits tested per lookup: 1 (sparse table) or 2 (see compileLayout)
+    std::vector<uint32_t> hfilt;     // kHashFilterWords (or, hfiltK == 2, kHashFilterWordsMax) words, or empty (exact 2-gram first stage)
+    int hfiltK = 0;                  // bits tested per lookup: 1 (sparse table, hashed word index) or 2 (dense table, byte
+                                     // alphabets: word index x & (words - 1); see compileLayout)
     int hfiltBitsSet = 0;
     bool next2Hot = false;           // next2 (+ best2) fit the shared-memory budget
     std::vector<uint32_t> hot;       // edges with source depth in [K,hotDepth)  -> smem

@@ -41,7 +41,10 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None, pad=0):
     elif L["hfilt"].size:
         assert B == 8
         x = sum((int(text[start + i]) if i < avail else pad) << (8 * i) for i in range(4))
-        w = int(L["hfilt"][(((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191])   # word picked by (c0,c1)
+        if L["hfilt_k"] == 2:   # dense tables: row-indexed, the word is picked by c0 and the low bits of c1 themselves
+            w = int(L["hfilt"][x & (L["hfilt"].size - 1)])
+        else:
+            w = int(L["hfilt"][(((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191])   # word picked by a hash of (c0,c1)
         for m in (0x85EBCA6B, 0xC2B2AE35)[:L["hfilt_k"]]:                     # one or two bits by all four bytes
             if not ((w << (((x * m) >> 32) & 31)) >> 31) & 1:
                 return 0

@@ -244,9 +244,9 @@ def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
     tc = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
     info = tc.info()
     assert info["hashed_filter"] == (1 if policy == "hash" else 2)   # 310 / 9,010 patterns: sparse / dense table
-    assert 0 < info["hfilt_bits_set"] < 262144 * 0.6
     L = tc.layout()
-    assert L["hfilt"].size == 8192
+    assert L["hfilt"].size == info["hfilt_words"] == (8192 if policy == "hash" else 16384)
+    assert 0 < info["hfilt_bits_set"] < 32 * info["hfilt_words"] * 0.6
     n = 20000
     text = synth.make_text("ascii", 99, 0, n, n, pats, 64)
     for p in (b"q", b"zq", b"xyz", b"th", b"the", b"them", b"\xff", b"\x00\x01\x02"):   # shorts at the end
@@ -263,7 +263,10 @@ def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
     # the filter does reject: most positions never reach the exact tables
     t = text.astype(np.uint64)
     x = t[:-3] | (t[1:-2] << 8) | (t[2:-1] << 16) | (t[3:] << 24)
-    w = L["hfilt"][((((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191).astype(np.int64)].astype(np.uint64)
+    if info["hashed_filter"] == 2:
+        w = L["hfilt"][(x & (info["hfilt_words"] - 1)).astype(np.int64)].astype(np.uint64)
+    else:
+        w = L["hfilt"][((((x * 0x9E3779B1) & 0xFFFFFFFF) >> 2) & 8191).astype(np.int64)].astype(np.uint64)
     passed = ((w << (((x * 0x85EBCA6B) >> 32) & 31)) >> 31) & 1
     if info["hashed_filter"] == 2:
         passed &= ((w << (((x * 0xC2B2AE35) >> 32) & 31)) >> 31) & 1
