@@ -465,10 +465,7 @@ def main():
     achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic()
     filt = (3 if info["hashed_filter"] == 2 else 2) if info["hashed_filter"] else (1 if info["has_chk2"] else 0)
-    if os.environ.get("PFAC_B200_DENSE") == "v1":   # first form of the dense kernel (kept for A/B runs)
-        kernel_name = "pfac_dense_kernel<3, %d, %d>" % (info["code_bits"], filt)
-    else:
-        kernel_name = "pfac_dense2_kernel<%d, %d>" % (info["code_bits"], filt)
+    kernel_name = "pfac_dense_kernel<%d, %d>" % (info["code_bits"], filt)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_ms,

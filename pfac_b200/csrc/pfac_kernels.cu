@@ -12,9 +12,10 @@
 //     shallow ("hot") hash rows in shared memory, deep ("cold") rows through L1/L2, and
 //     path-compressed chains whose tail bytes are compared directly against the text;
 //   * dense kernel: one persistent 32-warp CTA per SM, every warp runs its own pipeline --
-//     512-byte input tiles (+halo) arrive by 1-D TMA bulk copies on per-warp mbarriers, the
-//     warp's 2 KB of results leave by a TMA bulk store; no CTA-wide barrier in the loop, so
-//     one long walk delays one warp, not a block;
+//     1,536-byte input tiles (+halo) arrive by 1-D TMA bulk copies on per-warp mbarriers, the tile's
+//     6 KB of zeros leave at once (one TMA bulk store from a shared zero buffer, or plain 16-byte stores
+//     in the HBM-bound sparse-table kernel) and the few matches are stored over them; no CTA-wide
+//     barrier in the loop, so one long walk delays one warp, not a block;
 //   * reduce kernel: the same pipeline on 1,536-position warp tiles; matches are parked per walker
 //     batch (shared-memory ring + a spill ring in global memory) and written in position order by a
 //     round-structured look-back across CTAs, one pass; on several GPUs the same kernel exchanges
@@ -495,26 +496,6 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
     }
 }
 
-// exclusive offset of this lane's survivors in the warp queue + warp total; pushes positions
-__device__ __forceinline__ int push_survivors(uint32_t cand, uint32_t slow, int lb, unsigned short* q16, int lane) {
-    uint32_t all = cand | slow;
-    const int cnt = __popc(all);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-    }
-    const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
-    int off = incl - cnt;
-    while (all) {
-        const int b = __ffs(all) - 1;
-        all &= all - 1;
-        q16[off++] = static_cast<unsigned short>((lb + b) | (((slow >> b) & 1u) ? kSlowFlag : 0u));
-    }
-    return wtotal;
-}
-
 // Walk one batch of queued survivors, one per lane, until the batch's longest walk ends (most
 // survivors die at their first step, so a batch is usually one trip through the loop).  inb: staged
 // text of the tile (stage_bytes bytes, local position 0 = first byte), gin: the same bytes in global
@@ -675,29 +656,7 @@ __device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* 
     return best;
 }
 
-// Dense kernel: walk the queued survivors of one warp 32 at a time; wres[local position] = id
-// (non-zero only).  Returns whether this lane produced a non-zero id.
-template <int CODE, bool HASHED, bool INLINE_SLOW>
-__device__ __forceinline__ bool walk_queue_dense(const Tables& T, const unsigned char* inb, int stage_bytes,
-                                                 const unsigned char* __restrict__ gin, int tile_rem,
-                                                 const unsigned short* q16, int wtotal, int* wres, int lane) {
-    bool wrote = false;
-    for (int base = 0; base < wtotal; base += 32) {
-        const int slot = base + lane;
-        const bool active = slot < wtotal;
-        const unsigned qe = active ? q16[slot] : 0u;
-        int pl;
-        const int best = walk_batch<CODE, HASHED, INLINE_SLOW>(T, inb, stage_bytes, gin, tile_rem, active, qe, pl);
-        if (best) { wres[pl] = best; wrote = true; }
-    }
-    return wrote;
-}
-
-// =================================================================================================
-// Dense kernel: one persistent CTA of 32 autonomous warps per SM.
-// shared memory: [mbarriers 32*NSTAGE*8][root 1K | pre2 8K | rank2 4K][per warp: queue 1K | res 2K |
-// NSTAGE input stages][next2][hot buckets][chains][tails]
-// =================================================================================================
+// ---- helpers shared by the dense and the reduce kernel -------------------------------------------
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -722,129 +681,6 @@ __device__ __forceinline__ void clip_windows(int tile_rem, int lb, uint32_t& can
         slow |= tail;
         cand &= ~tail;
     }
-}
-
-// The walker's rare byte-wise text reads (walks past the staged halo) sit out of line in the kernels that
-// are bound by instruction issue and fetch: measured +6 % on C3 dense.  The sparse-table dense kernel
-// (one filter bit, C2) is bound by HBM and measured 1.5 % slower with the call in its walker, so it
-// keeps them inline.
-#ifndef PFAC_DENSE_INLINE_SLOW
-#define PFAC_DENSE_INLINE_SLOW(FILT) ((FILT) == 2)
-#endif
-
-template <int NSTAGE, int CODE, int FILT>
-__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int stage = kWarpTile + p.halo;
-    const int per_warp = kWarpTile * 2 + kWarpTile * 4 + NSTAGE * stage;
-    constexpr int kBarBytes = ((kDenseWarps * NSTAGE * 8 + 127) / 128) * 128;
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
-    unsigned char* s_fixed = smem + kBarBytes;
-    unsigned char* s_warp = s_fixed + kFixedTableBytes;
-    unsigned char* s_var = s_warp + kDenseWarps * per_warp;
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    // warp-uniform by construction, so addresses derived from it can live in uniform registers
-    const uint32_t warp = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tid) >> 5, 0);
-
-    const Tables T = stage_tables(p, s_fixed, s_var, tid, kDenseThreads);
-    unsigned long long* bar = s_bar + warp * NSTAGE;
-    if (lane == 0) {
-        for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();  // the only CTA-wide barrier
-
-    unsigned char* mine = s_warp + warp * per_warp;
-    unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
-    int* wres = reinterpret_cast<int*>(mine + kWarpTile * 2);
-    unsigned char* s_in = mine + kWarpTile * 2 + kWarpTile * 4;
-
-    // consecutive warps of a CTA take consecutive 512-byte tiles; tiles advance by the grid
-    const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
-    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kWarpTile);  // tiles with 512 owned positions
-    const uint32_t tstride = gridDim.x * kDenseWarps;
-    uint32_t tile = blockIdx.x * kDenseWarps + warp;
-
-    auto issue_load = [&](uint32_t t, int st) {  // one elected lane; tiles beyond bulk_tiles are copied at use
-        if (t < p.bulk_tiles) {
-            mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
-            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kWarpTile, static_cast<uint32_t>(stage),
-                        &bar[st]);
-        }
-    };
-
-    if (elect_one()) {
-#pragma unroll
-        for (int i = 0; i < NSTAGE; i++) issue_load(tile + i * tstride, i);
-    }
-
-    uint32_t parity = 0u;  // bit s = phase of bar[s]
-    int st = 0;
-    bool dirty = true;     // wres holds non-zeros (or was never cleared): zero it before the walk
-    for (; tile < num_tiles; tile += tstride) {
-        unsigned char* inb = s_in + st * stage;
-        const size_t start = static_cast<size_t>(tile) * kWarpTile;
-        if (tile < p.bulk_tiles) {
-            mbar_wait(&bar[st], (parity >> st) & 1u);
-            parity ^= 1u << st;
-        } else {
-            // odd pointers and tail tiles: guarded copy, zero fill past the end of the input
-            for (int i = lane; i < stage; i += 32) {
-                const long long g = static_cast<long long>(start) + i;
-                inb[i] = (g < p.n_total) ? p.in[g] : static_cast<unsigned char>(0);
-            }
-            __syncwarp();
-        }
-        const long long total_left = p.n_total - static_cast<long long>(start);
-        const int tile_rem = total_left > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(total_left);
-        const bool full = tile < full_tiles;
-
-        const int lb = lane * kPosPerThread;
-        uint32_t cand, slow;
-        prefilter16<CODE, FILT>(inb, lb, T, cand, slow);
-        if (FILT != 4) clip_windows<CODE>(tile_rem, lb, cand, slow);
-        int valid = kWarpTile;
-        if (!full) {  // tail tile: drop positions we do not own
-            valid = static_cast<int>(p.n_owned - static_cast<long long>(start));
-            int nv = valid - lb;
-            nv = nv < 0 ? 0 : (nv > kPosPerThread ? kPosPerThread : nv);
-            cand &= (1u << nv) - 1u;
-            slow &= (1u << nv) - 1u;
-        }
-        const int wtotal = push_survivors(cand, slow, lb, q16, lane);
-
-        // the previous bulk store of this warp must have finished reading wres before it is
-        // patched again; wres is all-zero here unless the previous tile had matches
-        if (elect_one()) tma_store_wait_read();
-        __syncwarp();
-        if (dirty) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(wres)[lane + 32 * k] = make_uint4(0u, 0u, 0u, 0u);
-            __syncwarp();
-        }
-        dirty = __any_sync(0xffffffffu,
-                           walk_queue_dense<CODE, FILT >= 2, PFAC_DENSE_INLINE_SLOW(FILT)>(T, inb, stage, p.in + start, tile_rem, q16, wtotal, wres, lane));
-
-        int* gout = p.out + start;
-        if (p.out_aligned && full) {
-            fence_proxy_async();
-            __syncwarp();
-            if (elect_one()) {
-                tma_store_1d(gout, wres, kWarpTile * 4);
-                tma_store_commit();
-                issue_load(tile + NSTAGE * tstride, st);  // every lane is done with this stage
-            }
-        } else {
-            __syncwarp();
-            for (int i = lane; i < valid; i += 32) gout[i] = wres[i];
-            __syncwarp();
-            if (elect_one()) issue_load(tile + NSTAGE * tstride, st);
-        }
-        st = (st + 1 == NSTAGE) ? 0 : st + 1;
-    }
-    if (elect_one()) tma_store_wait_all();  // shared memory must outlive the bulk stores
 }
 
 // =================================================================================================
@@ -1404,59 +1240,69 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
 }
 
 // =================================================================================================
-// Dense kernel, second form: zero-fill by bulk stores + patches.
+// Dense kernel: one persistent CTA of 32 autonomous warps per SM.
 //
-// The dense result is zeros but for one int per match, and matches are few.  The first form builds
-// every 512-position slice of the result in shared memory (clear, patch, bulk store): 2 KB of shared
-// memory per warp, four STS.128 per lane and tile, and a walker entry per 512 positions.  Here a warp
-// tile is kD2Sub = 3 consecutive 512-position blocks (1536 positions, one bulk load, as in the reduce
-// kernel); its 6 KB of results are written by ONE bulk store from a zero buffer the whole CTA shares,
-// issued before the tile's input is even waited for, and the walker's matches are stored straight to
-// global memory once that bulk store has completed (cp.async.bulk.wait_group by the issuing lane: its
-// writes are then visible to that thread; __syncwarp orders the other lanes' stores after it).  Nobody
-// waits for a store that has just been issued: a tile's matches are parked in a 64-entry list and
-// written at the start of the next tile, one tile time (microseconds) after their zeros left
-// (wait_group 1: everything but the newest store); only a tile with more matches than the list holds
-// waits for its own zeros.  (Patching right after the walk measured 11 % slower on C2: a third of its
-// tiles hold a match, and each made its warp sit out the write queue of an HBM-bound kernel.)
-// The patches land on lines the zero store has just put into L2, so DRAM still sees 4 bytes per
-// position.  What this buys: the walker is entered once per 1536 positions (with the row-indexed filter
-// a batch of 32 lanes is then two thirds full on the 20,000-pattern dictionary instead of every tile
-// needing its own batch), no per-tile clearing, 64 KB of shared memory for the tables (the 64 KB filter,
-// or chains and tails of a 1,000-pattern dictionary), and 6 KB bulk stores.
+// The dense result is zeros but for one int per match, and matches are few, so the result is not
+// built in shared memory (round 1 and most of round 2 did: clear a 2 KB slice per 512 positions, patch
+// it, bulk-store it).  A warp tile is kDenseSub = 3 consecutive 512-position blocks (1536 positions,
+// one bulk load, the survivor scan and the walker entry paid once, as in the reduce kernel).  The
+// tile's 6 KB of zeros leave first, then the walker's matches are stored over them, 4 bytes each:
+//   * kZeroByTma (every table but the sparse hashed one): ONE bulk store from a zero buffer the whole
+//     CTA shares, issued before the tile's input is even waited for.  A patch may only follow once that
+//     store has completed (cp.async.bulk.wait_group by the issuing lane: its writes are then visible to
+//     that thread; __syncwarp orders the other lanes' stores after it), and nobody waits for a store
+//     just issued: a tile's matches are parked in a 64-entry list and written at the start of the next
+//     tile, one tile time after their zeros left (wait_group 1: everything but the newest store); only
+//     a tile with more matches than the list holds waits for its own zeros.
+//   * otherwise (FILT 2, the 1,000-pattern headline config): twelve st.global.v4 of zeros per lane,
+//     then the patches, ordered by __syncwarp.  That kernel is bound by HBM, and with its zeros on the
+//     bulk-copy queue it measured 12 % slower (1.03 ms instead of 0.914 ms per GiB; a third of the
+//     stall samples sat on the bulk-copy issue slots, loads included; splitting the store, issuing it a
+//     tile early, throttling it and separate zero buffers all measured the same), while the kernels
+//     bound by issue and walker latency measured 3 % faster with the bulk store than with the plain ones.
+// The patches land on lines the zeros have just put into L2, so DRAM still sees 4 bytes per position.
+// What the form buys: the walker is entered once per 1536 positions (with the row-indexed filter a batch
+// of 32 lanes is two thirds full on the 20,000-pattern dictionary), no per-tile clearing, and 64 KB of
+// shared memory for the tables (the 64 KB filter, or chains and tails of a 1,000-pattern dictionary):
+// C3 774 -> 945 GB/s; C2 unchanged at the HBM bound (profiles/r2_history.md).
 // shared memory: [mbarriers][root | pre2 | rank2 | lut][zeros 6 KB][per warp: queue 512 B | parked ids 256 B |
 // parked positions 128 B | 2 input stages][hfilt][chk2][next2][hot][chains][tails]
 // =================================================================================================
-constexpr int kD2Sub = kRedSub;
-constexpr int kD2Tile = kD2Sub * kWarpTile;    // 1536 start positions per warp per iteration
-constexpr int kD2Stages = 2;
-constexpr int kD2Pend = 64;                    // matches a warp parks until their tile's zeros have landed
-constexpr int kD2WarpFixed = kQueueCap * 2 + kD2Pend * 6;
-static_assert((kD2WarpFixed & 15) == 0, "input stages are 16-byte aligned (bulk copies)");
-static_assert(kD2Sub == 3, "the survivor scan below packs three 10-bit counts");
+constexpr int kDenseSub = kRedSub;
+constexpr int kDenseTile = kDenseSub * kWarpTile;    // 1536 start positions per warp per iteration
+constexpr int kDenseStages = 2;
+constexpr int kDenseZeroBytes = kDenseTile * 4;
+constexpr int kDensePend = 64;                       // matches a warp parks until their tile's zeros have landed
+constexpr int kDenseWarpFixed = kQueueCap * 2 + kDensePend * 6;
+static_assert((kDenseWarpFixed & 15) == 0, "input stages are 16-byte aligned (bulk copies)");
+static_assert(kDenseSub == 3, "the survivor scan below packs three 10-bit counts");
 
 template <int CODE, int FILT>
-__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KParams p) {
-    constexpr int NSTAGE = kD2Stages;
+__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
+    constexpr int NSTAGE = kDenseStages;
     constexpr bool HASHED = FILT >= 2;
+    constexpr bool kZeroByTma = FILT != 2;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int stage = kD2Tile + p.halo;
-    const int per_warp = kD2WarpFixed + NSTAGE * stage;
+    const int stage = kDenseTile + p.halo;
+    const int per_warp = kDenseWarpFixed + NSTAGE * stage;
     constexpr int kBarBytes = ((kDenseWarps * NSTAGE * 8 + 127) / 128) * 128;
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem);
     unsigned char* s_fixed = smem + kBarBytes;
     unsigned char* s_zero = s_fixed + kFixedTableBytes;
-    unsigned char* s_warp = s_zero + kD2Tile * 4;
+    unsigned char* s_warp = s_zero + kDenseZeroBytes;
     unsigned char* s_var = s_warp + kDenseWarps * per_warp;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    // warp-uniform by construction, so addresses derived from it can live in uniform registers
     const uint32_t warp = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tid) >> 5, 0);
 
     const Tables T = stage_tables(p, s_fixed, s_var, tid, kDenseThreads);
+    if (kZeroByTma) {
 #pragma unroll 1
-    for (int i = tid; i < kD2Tile * 4 / 16; i += kDenseThreads) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();  // the zeros are read by bulk stores (async proxy) only
+        for (int i = tid; i < kDenseZeroBytes / 16; i += kDenseThreads) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();  // the zeros are read by bulk stores (async proxy) only
+    }
     unsigned long long* bar = s_bar + warp * NSTAGE;
     if (lane == 0) {
         for (int i = 0; i < NSTAGE; i++) mbar_init(&bar[i], 1);
@@ -1467,21 +1313,21 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
     unsigned char* mine = s_warp + warp * per_warp;
     unsigned short* q16 = reinterpret_cast<unsigned short*>(mine);
     int* pend_id = reinterpret_cast<int*>(mine + kQueueCap * 2);
-    unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kQueueCap * 2 + kD2Pend * 4);
-    unsigned char* s_in = mine + kD2WarpFixed;
+    unsigned short* pend_pos = reinterpret_cast<unsigned short*>(mine + kQueueCap * 2 + kDensePend * 4);
+    unsigned char* s_in = mine + kDenseWarpFixed;
     const FilterView fv{T.pre2, T.hfilt, T.rank2, T.chk2, T.lut, T.code_shift, T.hfilt_mask};
     const unsigned lt_mask = (1u << lane) - 1u;
 
     // consecutive warps of a CTA take consecutive tiles; tiles advance by the grid
     const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
-    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kD2Tile);  // tiles with 1536 owned positions
+    const uint32_t full_tiles = static_cast<uint32_t>(p.n_owned / kDenseTile);  // tiles with 1536 owned positions
     const uint32_t tstride = gridDim.x * kDenseWarps;
     uint32_t tile = blockIdx.x * kDenseWarps + warp;
 
     auto issue_load = [&](uint32_t t, int st) {  // one elected lane; tiles beyond bulk_tiles are copied at use
         if (t < p.bulk_tiles) {
             mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(stage));
-            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kD2Tile, static_cast<uint32_t>(stage),
+            tma_load_1d(s_in + st * stage, p.in + static_cast<size_t>(t) * kDenseTile, static_cast<uint32_t>(stage),
                         &bar[st]);
         }
     };
@@ -1492,33 +1338,37 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
 
     uint32_t parity = 0u;  // bit s = phase of bar[s]
     int st = 0;
-    int npend = 0;            // parked matches, all of the previous tile (of the current one while it is walked)
+    int npend = 0;         // parked matches, all of the previous tile (of the current one while it is walked)
     auto write_parked = [&](uint32_t t) {  // t: the tile they belong to
-        int* o = p.out + static_cast<size_t>(t) * kD2Tile;
+        int* o = p.out + static_cast<size_t>(t) * kDenseTile;
 #pragma unroll 1
         for (int i = lane; i < npend; i += 32) o[pend_pos[i]] = pend_id[i];
         npend = 0;
     };
     for (; tile < num_tiles; tile += tstride) {
         const unsigned char* inb = s_in + st * stage;
-        const size_t start = static_cast<size_t>(tile) * kD2Tile;
+        const size_t start = static_cast<size_t>(tile) * kDenseTile;
         int* gout = p.out + start;
         const long long owned_left = p.n_owned - static_cast<long long>(start);
-        const int tile_valid = owned_left > kD2Tile ? kD2Tile : static_cast<int>(owned_left);
-        // ---- the tile's zeros leave first: one 6 KB bulk store, in flight while the tile is matched
-        const bool bulk_out = p.out_aligned && tile < full_tiles;
+        const int tile_valid = owned_left > kDenseTile ? kDenseTile : static_cast<int>(owned_left);
+        // ---- the tile's zeros leave first
+        const bool whole = p.out_aligned && tile < full_tiles;
+        const bool bulk_out = kZeroByTma && whole;
         if (bulk_out) {
             if (elect_one()) {
-                tma_store_1d(gout, s_zero, kD2Tile * 4);
+                tma_store_1d(gout, s_zero, kDenseTile * 4);
                 tma_store_commit();
             }
-        } else {  // odd pointers and the tail tile: plain stores
+        } else if (whole) {
+#pragma unroll
+            for (int k = 0; k < kDenseTile * 4 / 512; k++) reinterpret_cast<uint4*>(gout)[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        } else {  // odd pointers and the tail tile
 #pragma unroll 1
             for (int i = lane; i < tile_valid; i += 32) gout[i] = 0;
         }
         __syncwarp();
         // ---- the previous tile's matches: its zeros left a whole tile ago
-        if (npend > 0) {  // (parked matches imply that tile's zeros left by a bulk store)
+        if (kZeroByTma && npend > 0) {  // (parked matches imply that tile's zeros left by a bulk store)
             if (elect_one()) {  // everything but the store just issued (if one was) has been written
                 if (bulk_out) tma_store_wait_but_newest();
                 else tma_store_wait_all();
@@ -1544,11 +1394,11 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
 
         // ---- survivors of the three blocks (one copy of the prefilter, run three times), one scan for
         // all three counts (10-bit fields)
-        uint32_t cand[kD2Sub], slow[kD2Sub];
+        uint32_t cand[kDenseSub], slow[kDenseSub];
         uint32_t packed = 0;
         cand[0] = cand[1] = cand[2] = slow[0] = slow[1] = slow[2] = 0u;
 #pragma unroll 1
-        for (int j = 0; j < kD2Sub; j++) {
+        for (int j = 0; j < kDenseSub; j++) {
             uint32_t sl;
             const uint32_t cd = block_survivors<CODE, FILT>(T, inb, j, lane, tile_rem, tile_valid, sl);
             if (j == 0) { cand[0] = cd; slow[0] = sl; }
@@ -1568,7 +1418,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
             const uint32_t excl = incl - packed;
             int qbase = 0;
 #pragma unroll
-            for (int j = 0; j < kD2Sub; j++) {
+            for (int j = 0; j < kDenseSub; j++) {
                 uint32_t all = cand[j] | slow[j];
                 int o = qbase + static_cast<int>((excl >> (10 * j)) & 1023u);
                 const int lb = j * kWarpTile + lane * kPosPerThread;
@@ -1581,20 +1431,20 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
             }
         } else if (wtotal > 0) {
             const bool by_block = (tot & 1023u) <= kQueueCap && ((tot >> 10) & 1023u) <= kQueueCap && (tot >> 20) <= kQueueCap;
-            nseg = by_block ? kD2Sub : kD2Sub * 4;
+            nseg = by_block ? kDenseSub : kDenseSub * 4;
         }
         bool zeros_landed = !bulk_out;  // plain zero stores are ordered before the patches by the __syncwarp above
         for (int seg = 0; seg < nseg; seg++) {
             if (nseg > 1) {
                 __syncwarp();  // the previous segment's queue has been read
-                const int j = (nseg == kD2Sub) ? seg : (seg >> 2);
+                const int j = (nseg == kDenseSub) ? seg : (seg >> 2);
                 const uint32_t both = block_survivors_cold<CODE, FILT>(fv, inb, j, lane, tile_rem, tile_valid);
                 const uint32_t sl = both >> 16;
                 uint32_t all = (both & 0xFFFFu) | sl;
                 const uint32_t cnt = static_cast<uint32_t>(__popc(all));
                 const uint32_t inc = warp_incl_scan(cnt, lane);
                 uint32_t lo = 0, hi = __shfl_sync(0xffffffffu, inc, 31);
-                if (nseg != kD2Sub) {
+                if (nseg != kDenseSub) {
                     const int g = seg & 3;
                     lo = g ? __shfl_sync(0xffffffffu, inc, 8 * g - 1) : 0u;
                     hi = __shfl_sync(0xffffffffu, inc, 8 * g + 7);
@@ -1610,17 +1460,21 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
                 seg_total = static_cast<int>(hi - lo);
             }
             __syncwarp();
-            // ---- walk the queue 32 survivors at a time; a batch's matches go straight to the result
+            // ---- walk the queue 32 survivors at a time
             for (int base = 0; base < seg_total; base += 32) {
                 const int qslot = base + lane;
                 const bool active = qslot < seg_total;
                 const unsigned qe = active ? q16[qslot] : 0u;
                 int pl;
                 const int best = walk_batch<CODE, HASHED>(T, inb, stage, p.in + start, tile_rem, active, qe, pl);
+                if (!kZeroByTma) {  // zeros and patches are plain stores of this warp, in order
+                    if (best) gout[pl] = best;
+                    continue;
+                }
                 const unsigned m = __ballot_sync(0xffffffffu, best != 0);
                 if (m == 0) continue;
                 const int c = __popc(m);
-                if (bulk_out && !zeros_landed && npend + c <= kD2Pend) {
+                if (!zeros_landed && npend + c <= kDensePend) {
                     if (best) {
                         const int e = npend + __popc(m & lt_mask);
                         pend_id[e] = best;
@@ -1643,9 +1497,11 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense2_kernel(const KPa
         if (elect_one()) issue_load(tile + NSTAGE * tstride, st);  // every lane is done with this stage
         st = (st + 1 == NSTAGE) ? 0 : st + 1;
     }
-    if (elect_one()) tma_store_wait_all();  // shared memory must outlive the bulk stores
-    __syncwarp();
-    write_parked(tile - tstride);
+    if (kZeroByTma) {
+        if (elect_one()) tma_store_wait_all();  // shared memory must outlive the bulk stores
+        __syncwarp();
+        write_parked(tile - tstride);
+    }
 }
 
 // a rank whose shard is empty still takes part in the exchange
@@ -1706,29 +1562,10 @@ int roundHalo(int maxPatternLen, int cap) {
     return h;
 }
 
-int denseStages(int halo) { return halo > 256 ? 2 : 3; }
-
 size_t denseFixedBytes(int halo) {
-    const int nst = denseStages(halo);
-    const size_t bar = size_t((kDenseWarps * nst * 8 + 127) / 128) * 128;
-    return bar + kFixedTableBytes +
-           size_t(kDenseWarps) * (kWarpTile * 2 + kWarpTile * 4 + nst * (kWarpTile + halo));
-}
-
-size_t dense2FixedBytes(int halo) {
-    const size_t bar = size_t((kDenseWarps * kD2Stages * 8 + 127) / 128) * 128;
-    return bar + kFixedTableBytes + size_t(kD2Tile) * 4 +
-           size_t(kDenseWarps) * (kD2WarpFixed + kD2Stages * (kD2Tile + halo));
-}
-
-// PFAC_B200_DENSE=v1 keeps the first form of the dense kernel (results built in shared memory per
-// 512-position tile); read once, before the first table is compiled (the budgets differ)
-bool denseFirstForm() {
-    static const bool v1 = [] {
-        const char* v = getenv("PFAC_B200_DENSE");
-        return v && !strcmp(v, "v1");
-    }();
-    return v1;
+    const size_t bar = size_t((kDenseWarps * kDenseStages * 8 + 127) / 128) * 128;
+    return bar + kFixedTableBytes + size_t(kDenseZeroBytes) +
+           size_t(kDenseWarps) * (kDenseWarpFixed + kDenseStages * (kDenseTile + halo));
 }
 
 size_t reduceFixedBytes(int halo) {
@@ -1785,7 +1622,7 @@ KParams baseParams(const DeviceTable& t, const unsigned char* in, size_t n_owned
 
 size_t tableSmemBudget(int maxPatternLen, bool reduceKernel) {
     const int halo = roundHalo(maxPatternLen, kDenseMaxHalo);
-    const size_t fixed = reduceKernel ? reduceFixedBytes(halo) : (denseFirstForm() ? denseFixedBytes(halo) : dense2FixedBytes(halo));
+    const size_t fixed = reduceKernel ? reduceFixedBytes(halo) : denseFixedBytes(halo);
     return fixed < size_t(kMaxSmem) ? size_t(kMaxSmem) - fixed : 0;
 }
 
@@ -1802,8 +1639,7 @@ size_t reduceParkWords(const LaunchConfig& cfg) { return size_t(cfg.numSMs) * kR
 unsigned long long kernelLaunchCount() { return g_launches.load(); }
 
 namespace {
-const void* denseKernelFor(const DeviceTable& t, int nst);
-const void* dense2KernelFor(const DeviceTable& t);
+const void* denseKernelFor(const DeviceTable& t);
 const void* reduceKernelFor(const DeviceTable& t, bool pos64);
 }  // namespace
 
@@ -1811,9 +1647,7 @@ const void* reduceKernelFor(const DeviceTable& t, bool pos64);
 // that cost (about 2 ms per kernel) from the caller's first match call to the pattern load, where the
 // reference pays its own table upload.  One call per table.
 cudaError_t prepareKernels(const DeviceTable& dense, const DeviceTable& reduce) {
-    const void* ks[3] = {denseFirstForm() ? denseKernelFor(dense, denseStages(roundHalo(dense.maxPatternLen, kDenseMaxHalo)))
-                                          : dense2KernelFor(dense),
-                         reduceKernelFor(reduce, false), reduceKernelFor(reduce, true)};
+    const void* ks[3] = {denseKernelFor(dense), reduceKernelFor(reduce, false), reduceKernelFor(reduce, true)};
     for (const void* k : ks) {
         if (!k) return cudaErrorInvalidValue;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -1826,48 +1660,20 @@ cudaError_t launchMatchDense(const DeviceTable& t, const LaunchConfig& cfg, cons
                              size_t n_owned, size_t n_total, int* out, cudaStream_t stream) {
     if (n_owned == 0) return cudaSuccess;
     const int halo = roundHalo(t.maxPatternLen, kDenseMaxHalo);
-    if (!denseFirstForm()) {
-        KParams p = baseParams(t, in, n_owned, n_total, halo, kD2Tile);
-        if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-        p.out = out;
-        p.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-        {   // tile t is staged by TMA iff the pointer is 16-byte aligned and t*1536 + stage <= n_total
-            const long long stage = kD2Tile + halo;
-            long long bulk = 0;
-            if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kD2Tile + 1;
-            if (bulk > p.num_tiles) bulk = p.num_tiles;
-            p.bulk_tiles = static_cast<uint32_t>(bulk);
-        }
-        const size_t smem = dense2FixedBytes(halo) + tableSmemBytes(t);
-        if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
-        const void* kernel = dense2KernelFor(t);
-        if (!kernel) return cudaErrorInvalidValue;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e != cudaSuccess) return e;
-        const long long ctaTiles = (p.num_tiles + kDenseWarps - 1) / kDenseWarps;
-        long long grid = cfg.numSMs;
-        if (grid > ctaTiles) grid = ctaTiles;
-        void* args[] = {&p};
-        e = cudaLaunchKernel(kernel, dim3(unsigned(grid)), dim3(kDenseThreads), args, smem, stream);
-        if (e != cudaSuccess) return e;
-        g_launches++;
-        return cudaGetLastError();
-    }
-    KParams p = baseParams(t, in, n_owned, n_total, halo, kWarpTile);
-    if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;  // 1 TiB per launch
+    KParams p = baseParams(t, in, n_owned, n_total, halo, kDenseTile);
+    if (p.num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.out = out;
     p.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    {   // tile t is staged by TMA iff the pointer is 16-byte aligned and t*512 + stage <= n_total
-        const long long stage = kWarpTile + halo;
+    {   // tile t is staged by TMA iff the pointer is 16-byte aligned and t*1536 + stage <= n_total
+        const long long stage = kDenseTile + halo;
         long long bulk = 0;
-        if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kWarpTile + 1;
+        if (p.in_aligned && p.n_total >= stage) bulk = (p.n_total - stage) / kDenseTile + 1;
         if (bulk > p.num_tiles) bulk = p.num_tiles;
         p.bulk_tiles = static_cast<uint32_t>(bulk);
     }
     const size_t smem = denseFixedBytes(halo) + tableSmemBytes(t);
     if (smem > size_t(kMaxSmem)) return cudaErrorInvalidConfiguration;
-    const int nst = denseStages(halo);
-    const void* kernel = denseKernelFor(t, nst);
+    const void* kernel = denseKernelFor(t);
     if (!kernel) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
@@ -1942,42 +1748,20 @@ cudaError_t launchMatchReduce(const DeviceTable& t, const LaunchConfig& cfg, con
 
 namespace {
 // the kernel instantiation a table runs on (nullptr: a table the kernels were not built for)
-const void* denseKernelFor(const DeviceTable& t, int nst) {
-    const void* kernel = nullptr;
-    // the table compiler emits hfilt / chk2 for byte alphabets only
-    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
-    switch (t.codeBits) {
-        case 8:
-            if (filt == 3) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 3> : (const void*)pfac_dense_kernel<2, 8, 3>;
-            else if (filt == 2) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 2> : (const void*)pfac_dense_kernel<2, 8, 2>;
-            else if (filt == 1) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 1> : (const void*)pfac_dense_kernel<2, 8, 1>;
-            else kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 8, 0> : (const void*)pfac_dense_kernel<2, 8, 0>;
-            break;
-        case 4: kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 4, 0> : (const void*)pfac_dense_kernel<2, 4, 0>; break;
-        case 2:  // hashed 10-mer first stage when the table compiler built one (arithmetic symbol code)
-            if (t.hfiltBytes) kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 2, 4> : (const void*)pfac_dense_kernel<2, 2, 4>;
-            else kernel = (nst == 3) ? (const void*)pfac_dense_kernel<3, 2, 0> : (const void*)pfac_dense_kernel<2, 2, 0>;
-            break;
-        default: return nullptr;
-    }
-    if (t.codeBits == 4 && filt) return nullptr;
-    if (t.codeBits == 2 && (t.chk2Bytes || (t.hfiltBytes && (t.hfiltK != 2 || t.codeShift < 0)))) return nullptr;
-    return kernel;
-}
-const void* dense2KernelFor(const DeviceTable& t) {
+const void* denseKernelFor(const DeviceTable& t) {
     const void* kernel = nullptr;
     const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (filt == 3) kernel = (const void*)pfac_dense2_kernel<8, 3>;
-            else if (filt == 2) kernel = (const void*)pfac_dense2_kernel<8, 2>;
-            else if (filt == 1) kernel = (const void*)pfac_dense2_kernel<8, 1>;
-            else kernel = (const void*)pfac_dense2_kernel<8, 0>;
+            if (filt == 3) kernel = (const void*)pfac_dense_kernel<8, 3>;
+            else if (filt == 2) kernel = (const void*)pfac_dense_kernel<8, 2>;
+            else if (filt == 1) kernel = (const void*)pfac_dense_kernel<8, 1>;
+            else kernel = (const void*)pfac_dense_kernel<8, 0>;
             break;
-        case 4: kernel = (const void*)pfac_dense2_kernel<4, 0>; break;
+        case 4: kernel = (const void*)pfac_dense_kernel<4, 0>; break;
         case 2:
-            if (t.hfiltBytes) kernel = (const void*)pfac_dense2_kernel<2, 4>;
-            else kernel = (const void*)pfac_dense2_kernel<2, 0>;
+            if (t.hfiltBytes) kernel = (const void*)pfac_dense_kernel<2, 4>;
+            else kernel = (const void*)pfac_dense_kernel<2, 0>;
             break;
         default: return nullptr;
     }

@@ -20,7 +20,7 @@ src=open(os.path.join(os.path.dirname(lib), '..', 'csrc', 'pfac_kernels.cu')).re
 def find(s):
     for i,l in enumerate(src):
         if s in l: return i+1
-marks=[("helpers(mbar/tma/ld/st)",1),("comm",find("comm_exchange_scan(const KParams")),("probe_hot/cold",find("__device__ __forceinline__ uint32_t home_bucket")),("stage_tables",find("__device__ __forceinline__ Tables stage_tables")),("prefilter16",find("struct FilterView")),("push_survivors",find("__device__ __forceinline__ int push_survivors")),("text_word_slow",find("__device__ __noinline__ uint32_t text_word_slow")),("walk_batch",find("__device__ __forceinline__ int walk_batch")),("walk_queue_dense",find("__device__ __forceinline__ bool walk_queue_dense")),("elect/clip",find("__device__ __forceinline__ bool elect_one")),("dense kernel body",find("__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel")),("reduce helpers",find("// Reduce kernel: fused match")),("reduce kernel",find("__global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel")),("matcher",find("// ============================ matcher warps"))]
+marks=[("helpers(mbar/tma/ld/st)",1),("comm",find("comm_exchange_scan(const KParams")),("probe_hot/cold",find("__device__ __forceinline__ uint32_t home_bucket")),("stage_tables",find("__device__ __forceinline__ Tables stage_tables")),("prefilter16",find("struct FilterView")),("text_word_slow",find("__device__ __noinline__ uint32_t text_word_slow")),("walk_batch",find("__device__ __forceinline__ int walk_batch")),("elect/clip",find("__device__ __forceinline__ bool elect_one")),("reduce helpers",find("// Reduce kernel: fused match")),("reduce kernel",find("__global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel")),("matcher",find("// ============================ matcher warps")),("dense kernel",find("// Dense kernel: one persistent CTA of 32 autonomous warps"))]
 marks=[m for m in marks if m[1]]; marks.sort(key=lambda m:m[1])
 def num(d,k):
     try: return float((d.get(k) or "0").replace(",",""))
