@@ -229,7 +229,7 @@ def run_c5(pf_factory, rank, local_rank, world, dev, dist, torch, barrier, max_o
     pfile = synth.write_pattern_file(os.path.join(tmp, "c5_rank%d.pat" % rank), pats)
     pf = pf_factory()
     pf.readPatternFromFile(pfile)
-    info = pf.tableInfo()
+    info = pf.tableInfo(reduce=True)
     maxlen = info["max_pattern_len"]
     start, owned, total = shard_bounds(total_len, world, rank, maxlen)
     t0 = time.perf_counter()
@@ -343,7 +343,7 @@ def run_c5(pf_factory, rank, local_rank, world, dev, dist, torch, barrier, max_o
                         "what": "PFAC_commGatherRuns after every step: every rank's run stored into ONE list on rank 0 "
                                 "at its scanned offset by P2P stores (12 B per match over NVLink into one GPU)"},
         "matches_total": total_m, "matches_rank0": count if rank == 0 else None, "states": info["num_states"],
-        "roofline": {"bound": "hbm", "kernel": "pfac_reduce_kernel<1, 8, %d>" % (info["hashed_filter"] + 1 if info["hashed_filter"] else 0),
+        "roofline": {"bound": "hbm", "kernel": "pfac_reduce_kernel<1, 8, %d>" % ({0: 0, 1: 2, 2: 3, 3: 5}[info["hashed_filter"]]),
                      "algorithmic_bytes_per_launch": int(algo), "achieved": algo / (ms_plain * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": algo / (ms_plain * 1e-3) / 1e9 / peak,
                      "note": "rank 0, N + 12 M bytes per launch; issue-bound, not HBM-bound"},
@@ -464,7 +464,7 @@ def main():
     algo_bytes = 5 * owned  # 1 B read + 4 B written per position
     achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic()
-    filt = (3 if info["hashed_filter"] == 2 else 2) if info["hashed_filter"] else (1 if info["has_chk2"] else 0)
+    filt = {1: 2, 2: 3, 3: 5}[info["hashed_filter"]] if info["hashed_filter"] else (1 if info["has_chk2"] else 0)
     kernel_name = "pfac_dense_kernel<%d, %d>" % (info["code_bits"], filt)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
@@ -580,6 +580,7 @@ def main():
                        "matches_total": total_m, "rank0_offset": my_off if rank == 0 else None,
                        "count_scan_ms_per_step": max(dt / args.reduce_steps * 1e3 - t_call / args.reduce_steps * 1e3, 0.0),
                        "algorithmic_bytes_per_step": int(owned + 12 * m), "steps": args.reduce_steps,
+                       "kernel": "pfac_reduce_kernel<1, 8, %d>" % ({0: 0, 1: 2, 2: 3, 3: 5}[pf.tableInfo(reduce=True)["hashed_filter"]]),
                        "roofline_frac": (owned + 12 * m) / (ms_global * 1e-3) / 1e9 / peak}
         del d_id, d_pos
 
@@ -614,8 +615,12 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args.bytes, world),
             "table": {"states": info["num_states"], "hot_depth": info["hot_depth"], "hot_buckets": info["hot_buckets"],
-                      "first_stage": ("hashed 4-gram filter, %d bit(s) per lookup, %d of 262144 bits set"
-                                      % (info["hashed_filter"], info["hfilt_bits_set"]) if info["hashed_filter"] else
+                      "first_stage": ("pair filter: one lookup per two start positions, keyed by the three bytes they "
+                                      "share, %d of %d bits set" % (info["hfilt_bits_set"], 32 * info["hfilt_words"])
+                                      if info["hashed_filter"] == 3 else
+                                      "hashed 4-gram filter, %d bit(s) per lookup, %d of %d bits set"
+                                      % (info["hashed_filter"], info["hfilt_bits_set"], 32 * info["hfilt_words"])
+                                      if info["hashed_filter"] else
                                       "exact 2-gram set, %d of 65536 bits set" % info["pre2_bits_set"]),
                       "device_bytes": info["device_bytes"], "matches_per_gpu": n_matches},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reduce": reduce_info, "c5": c5,

@@ -139,7 +139,8 @@ typedef struct {
     int hot_max_probe, cold_max_probe;
     int pre2_bits_set;     /* of 65536: (c0,c1) pairs that survive the prefilter */
     int root_fanout;       /* valid first bytes */
-    int hashed_filter;     /* 1 / 2: the per-position test is the hashed 4-gram filter (hfilt_words words), 1 or 2 bits per lookup */
+    int hashed_filter;     /* 1 / 2: the per-position test is the hashed 4-gram filter (hfilt_words words), 1 or 2 bits per lookup;
+                              3: pair filter, one lookup per two start positions (PFAC_tableGetFilter) */
     int hfilt_bits_set;    /* of 32 * hfilt_words */
     int code_shift;        /* b = 2 with an arithmetic symbol code: code = (byte >> code_shift) & 3; else -1.  With
                               hashed_filter == 2 and code_bits == 2 the first stage hashes ten symbols (20 bits):
@@ -181,8 +182,13 @@ PFAC_status_t PFAC_tableGetLayout2(PFAC_table_t table, const unsigned char **lut
  * ((x * 0x9E3779B1) >> 2) & 8191, bit 31 - (umulhi(x, 0x85EBCA6B) & 31).  hashed_filter == 2 (dense
  * tables): word x & (hfilt_words - 1), i.e. picked by c0 and the low bits of c1 themselves (a 1-byte
  * pattern then fills the words of its own first byte only), that bit and bit
- * 31 - (umulhi(x, 0xC2B2AE35) & 31); survivors are re-checked exactly against pre2 / chk2 by the walker.
- * PFAC_B200_FILTER=exact keeps the exact 2-gram stage (read at table compile time). */
+ * 31 - (umulhi(x, 0xC2B2AE35) & 31).  hashed_filter == 3 (sparse tables, no pattern shorter than three
+ * bytes): one lookup for the start positions q and q+1, keyed by the bytes they share,
+ * y = text[q+1] | text[q+2]<<8 | text[q+3]<<16, h = (y * 0x9E3779B1) mod 2^24, word (h >> 2) & 8191, bit
+ * 31 - (h >> 19); the table holds bytes 0..2 and bytes 1..3 of every pattern.  Survivors are re-checked
+ * exactly against pre2 / chk2 by the walker.
+ * PFAC_B200_FILTER=exact keeps the exact 2-gram stage, =nopair the per-position hashed filter (read at
+ * table compile time). */
 PFAC_status_t PFAC_tableGetFilter(PFAC_table_t table, const unsigned **hfilt);
 
 /* ---- compiled-table files: parse, sort, number and lay out a large dictionary once, later
@@ -198,7 +204,10 @@ PFAC_status_t PFAC_tableSave(PFAC_table_t table, const char *filename);      /* 
 PFAC_status_t PFAC_tableLoad(const char *filename, PFAC_table_t *table);     /* host only */
 
 /* info / dump-to-path for a live handle */
-PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);
+PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t *info);        /* layout of the dense kernel */
+PFAC_status_t PFAC_getTableInfoReduce(PFAC_handle_t handle, PFAC_tableInfo_t *info);  /* layout of the reduce kernel: its
+                                                                                         own shared-memory budget, and the pair
+                                                                                         filter where the dictionary allows it */
 PFAC_status_t PFAC_dumpTransitionTableToFile(PFAC_handle_t handle, const char *filename);
 
 /* ---- table-size report to stdout, counterpart of the reference's PFAC_memoryUsage

@@ -133,6 +133,7 @@ def load_library():
         "PFAC_saveCompiledPatterns": [vp, cp],
         "PFAC_loadCompiledPatterns": [vp, cp],
         "PFAC_getTableInfo": [vp, ctypes.POINTER(TableInfo)],
+        "PFAC_getTableInfoReduce": [vp, ctypes.POINTER(TableInfo)],
         "PFAC_memoryUsage": [vp],
         "PFAC_hostCopy": [vp, vp, sz],
         "PFAC_hostZero": [vp, sz],
@@ -267,9 +268,14 @@ class PFAC:
         _check(self._L.PFAC_dumpTransitionTableToFile(self._h, os.fsencode(filename)),
                "PFAC_dumpTransitionTable")
 
-    def tableInfo(self):
+    def tableInfo(self, reduce=False):
+        """Compiled-table facts of the dense kernel's layout (reduce=True: the reduce kernel's, which has its own
+        shared-memory budget and first stage)."""
         info = TableInfo()
-        _check(self._L.PFAC_getTableInfo(self._h, ctypes.byref(info)), "PFAC_getTableInfo")
+        if reduce:
+            _check(self._L.PFAC_getTableInfoReduce(self._h, ctypes.byref(info)), "PFAC_getTableInfoReduce")
+        else:
+            _check(self._L.PFAC_getTableInfo(self._h, ctypes.byref(info)), "PFAC_getTableInfo")
         return info.as_dict()
 
     # -- matching: device buffers ----------------------------------------------------------------

@@ -437,7 +437,17 @@ int filterPolicy() {
     const char* v = getenv("PFAC_B200_FILTER");
     if (v && !strcmp(v, "exact")) return pfac::kFilterExact;
     if (v && !strcmp(v, "hash")) return pfac::kFilterHashed;
+    if (v && !strcmp(v, "nopair")) return pfac::kFilterNoPair;
     return pfac::kFilterAuto;
+}
+
+// The pair filter halves the first stage's instructions: +18 % for the reduce kernel, which is bound by
+// instruction issue (C2: 1,333 -> 1,575 GB/s per call), but its twice as many survivors cost the dense
+// kernel, which is bound by HBM, 5-7 % (0.918 -> 0.97 ms per GiB): the dense layout keeps the
+// per-position filter unless PFAC_B200_FILTER says otherwise.
+int filterPolicyFor(bool reduceKernel) {
+    const int p = filterPolicy();
+    return (!reduceKernel && p == pfac::kFilterAuto) ? pfac::kFilterNoPair : p;
 }
 
 // compile the device layouts for the current perf mode and upload them (reference
@@ -489,7 +499,7 @@ PFAC_status_t bindTable(PFAC_handle_t h) {
     // the two layouts are independent functions of the (read-only) automaton: compile them side by side.
     // Large dictionaries allocate by the number of states: an allocation failure must come back as
     // PFAC_STATUS_ALLOC_FAILED (as the reference does), not unwind through the C ABI or a std::thread.
-    const int policy = filterPolicy();
+    const int policy = filterPolicyFor(true);
     const size_t budgetReduce = hotBudget(h, true);
     std::atomic<bool> failed{false};
     auto reduceSide = [&] {
@@ -505,7 +515,7 @@ PFAC_status_t bindTable(PFAC_handle_t h) {
     } catch (...) {  // no thread to be had: one after the other
     }
     try {
-        pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, policy);
+        pfac::compileLayout(h->machine, hotBudget(h, false), h->layout, filterPolicyFor(false));
     } catch (...) {
         failed = true;
     }
@@ -1737,7 +1747,8 @@ PFAC_status_t PFAC_saveCompiledPatterns(PFAC_handle_t handle, const char* filena
     pfac::CompiledLayout a, b;
     a.budget = hotBudget(handle, false);
     b.budget = hotBudget(handle, true);
-    a.policy = b.policy = filterPolicy();
+    a.policy = filterPolicyFor(false);
+    b.policy = filterPolicyFor(true);
     a.layout = handle->layout;
     b.layout = handle->layoutReduce;
     return pfac::saveCompiled(filename, handle->machine, {&a, &b}) ? PFAC_STATUS_SUCCESS
@@ -1764,9 +1775,9 @@ PFAC_status_t PFAC_loadCompiledPatterns(PFAC_handle_t handle, const char* filena
     handle->patternFile[0] = 0;
     handle->machine = std::move(m);
     handle->patternsReady = true;
-    const int policy = filterPolicy();
     auto take = [&](bool reduceKernel, pfac::DeviceLayout& dst) {
         const size_t budget = hotBudget(handle, reduceKernel);
+        const int policy = filterPolicyFor(reduceKernel);
         for (pfac::CompiledLayout& c : ls)
             if (c.budget == budget && c.policy == policy && !c.layout.pre2.empty()) {
                 dst = c.layout;
@@ -1847,6 +1858,14 @@ PFAC_status_t PFAC_getTableInfo(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
     if (!info) return PFAC_STATUS_INVALID_PARAMETER;
     if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
     fillInfo(handle->machine, handle->layout, info);
+    return PFAC_STATUS_SUCCESS;
+}
+
+PFAC_status_t PFAC_getTableInfoReduce(PFAC_handle_t handle, PFAC_tableInfo_t* info) {
+    if (!handle) return PFAC_STATUS_INVALID_HANDLE;
+    if (!info) return PFAC_STATUS_INVALID_PARAMETER;
+    if (!handle->patternsReady) return PFAC_STATUS_PATTERNS_NOT_READY;
+    fillInfo(handle->machine, handle->layoutReduce, info);
     return PFAC_STATUS_SUCCESS;
 }
 

@@ -389,7 +389,8 @@ __device__ __forceinline__ bool second_stage(const TT& T, uint32_t idx, uint32_t
 }
 
 // FILT: 0 = exact K-gram set only, 1 = + inline second stage (chk2), 2 / 3 = hashed 4-gram filter
-// testing one / two bits (byte alphabets; pfac_table.h) whose survivors the walker re-checks exactly
+// testing one / two bits (byte alphabets; pfac_table.h) whose survivors the walker re-checks exactly,
+// 4 = hashed 10-mer filter (2-bit alphabets), 5 = pair filter: one lookup per two start positions
 template <int CODE, int FILT, typename TT>
 __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, const TT& T, uint32_t& cand,
                                             uint32_t& slow) {
@@ -419,6 +420,29 @@ __device__ __forceinline__ void prefilter16(const unsigned char* inb, int lb, co
             const uint32_t rot = __funnelshift_l(hw, hw, (x * kHashFilterMul2) >> 27) &
                                  __funnelshift_l(hw, hw, (x * kHashFilterMul3) >> 27);
             cand = __funnelshift_l(rot, cand, 1);
+        }
+        return;
+    }
+    if (CODE == 8 && FILT == 5) {
+        // pair filter (pfac_table.cpp): the start positions q and q+1 share text[q+1..q+3]; the low 24 bits of
+        // (those three bytes and the next) * multiplier do not depend on the fourth byte: bits 2..14 are the
+        // word's byte offset, bits 19..23 the bit (the rotate takes its amount mod 32).  A pair that passes
+        // sets both its positions.  7 instructions per pair.
+        uint32_t w[5];
+        const uint4 v = *reinterpret_cast<const uint4*>(inb + lb);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        w[4] = *reinterpret_cast<const uint32_t*>(inb + lb + 16);
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {
+#pragma unroll
+            for (int j = 3; j >= 1; j -= 2) {   // positions 4k+j-1 and 4k+j: shared bytes start at byte j of word k
+                const uint32_t h = __funnelshift_r(w[k], w[k + 1], 8 * j) * kHashFilterMul;
+                const uint32_t hw = *reinterpret_cast<const uint32_t*>(
+                    reinterpret_cast<const unsigned char*>(T.hfilt) + (h & static_cast<uint32_t>(kHashFilterWords * 4 - 4)));
+                const uint32_t rot = __funnelshift_l(hw, hw, h >> 19);
+                cand = __funnelshift_l(rot, cand, 1);
+                cand = __funnelshift_l(rot, cand, 1);
+            }
         }
         return;
     }
@@ -1254,7 +1278,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
 //     just issued: a tile's matches are parked in a 64-entry list and written at the start of the next
 //     tile, one tile time after their zeros left (wait_group 1: everything but the newest store); only
 //     a tile with more matches than the list holds waits for its own zeros.
-//   * otherwise (FILT 2, the 1,000-pattern headline config): twelve st.global.v4 of zeros per lane,
+//   * otherwise (FILT 2 and 5, sparse dictionaries: the 1,000-pattern headline config): twelve st.global.v4 of zeros per lane,
 //     then the patches, ordered by __syncwarp.  That kernel is bound by HBM, and with its zeros on the
 //     bulk-copy queue it measured 12 % slower (1.03 ms instead of 0.914 ms per GiB; a third of the
 //     stall samples sat on the bulk-copy issue slots, loads included; splitting the store, issuing it a
@@ -1281,7 +1305,7 @@ template <int CODE, int FILT>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const KParams p) {
     constexpr int NSTAGE = kDenseStages;
     constexpr bool HASHED = FILT >= 2;
-    constexpr bool kZeroByTma = FILT != 2;
+    constexpr bool kZeroByTma = FILT != 2 && FILT != 5;
     extern __shared__ __align__(128) unsigned char smem[];
     const int stage = kDenseTile + p.halo;
     const int per_warp = kDenseWarpFixed + NSTAGE * stage;
@@ -1750,10 +1774,11 @@ namespace {
 // the kernel instantiation a table runs on (nullptr: a table the kernels were not built for)
 const void* denseKernelFor(const DeviceTable& t) {
     const void* kernel = nullptr;
-    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
+    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : t.hfiltK == 3 ? 5 : 2) : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (filt == 3) kernel = (const void*)pfac_dense_kernel<8, 3>;
+            if (filt == 5) kernel = (const void*)pfac_dense_kernel<8, 5>;
+            else if (filt == 3) kernel = (const void*)pfac_dense_kernel<8, 3>;
             else if (filt == 2) kernel = (const void*)pfac_dense_kernel<8, 2>;
             else if (filt == 1) kernel = (const void*)pfac_dense_kernel<8, 1>;
             else kernel = (const void*)pfac_dense_kernel<8, 0>;
@@ -1771,10 +1796,11 @@ const void* denseKernelFor(const DeviceTable& t) {
 }
 const void* reduceKernelFor(const DeviceTable& t, bool pos64) {
     const void* kernel = nullptr;
-    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : 2) : (t.chk2Bytes ? 1 : 0);
+    const int filt = t.hfiltBytes ? (t.hfiltK == 2 ? 3 : t.hfiltK == 3 ? 5 : 2) : (t.chk2Bytes ? 1 : 0);
     switch (t.codeBits) {
         case 8:
-            if (filt == 3) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 3> : (const void*)pfac_reduce_kernel<false, 8, 3>;
+            if (filt == 5) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 5> : (const void*)pfac_reduce_kernel<false, 8, 5>;
+            else if (filt == 3) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 3> : (const void*)pfac_reduce_kernel<false, 8, 3>;
             else if (filt == 2) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 2> : (const void*)pfac_reduce_kernel<false, 8, 2>;
             else if (filt == 1) kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 1> : (const void*)pfac_reduce_kernel<false, 8, 1>;
             else kernel = pos64 ? (const void*)pfac_reduce_kernel<true, 8, 0> : (const void*)pfac_reduce_kernel<false, 8, 0>;

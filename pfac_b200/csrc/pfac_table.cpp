@@ -457,7 +457,55 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
     // shared-memory budget holds its 32 KB: measured faster than the exact 2-gram stage from 1,000
     // random patterns (+11 %) to 20,000 Snort-like ones (+29 %)
     size_t hfiltBytes = size_t(kHashFilterWords) * 4;
-    if (B == 8 && !frontier.empty() && hotBudgetBytes >= hfiltBytes && filterPolicy != kFilterExact) {
+    // Pair filter (hfiltK = 3) for sparse dictionaries without 1- and 2-byte patterns: ONE lookup decides two
+    // start positions.  The positions q and q+1 share the text bytes c1 c2 c3 = text[q+1..q+3]: a pattern that
+    // starts at q+1 shows its bytes 0..2 there, one that starts at q its bytes 1..3 (a 3-byte pattern its
+    // bytes 1..2 and anything).  Both kinds of 3-grams of every pattern go into the same 256-Kbit table, keyed by
+    // y = c1 | c2<<8 | c3<<16 through h = (y * kHashFilterMul) mod 2^24 -- the low 24 bits of the product of
+    // the 4-byte text window with the multiplier, which the fourth byte cannot reach: word (h >> 2) & 8191
+    // (c1 and seven bits of c2), bit 31 - (h >> 19).  A pair that passes sends both its positions to the
+    // walker.  3.5 instead of 7 instructions per start position; 1,000 patterns set 2,000 bits, 0.8 % of the
+    // pairs pass.
+    bool minLen3 = !frontier.empty();
+    for (const Edge& e : out[size_t(m.initialState)]) {
+        if (isFinal(e.next)) minLen3 = false;
+        for (const Edge& e2 : out[size_t(e.next)]) if (isFinal(e2.next)) minLen3 = false;
+    }
+    if (B == 8 && minLen3 && hotBudgetBytes >= hfiltBytes && (filterPolicy == kFilterAuto || filterPolicy == kFilterHashed)) {
+        L.hfilt.assign(size_t(kHashFilterWords), 0u);
+        auto setKey = [&](uint32_t y) {
+            const uint32_t h = (y * kHashFilterMul) & 0xFFFFFFu;
+            L.hfilt[(h >> 2) & uint32_t(kHashFilterWords - 1)] |= 0x80000000u >> (h >> 19);
+        };
+        struct Node { int state; uint32_t x; int d; };
+        std::vector<Node> todo;
+        todo.push_back(Node{m.initialState, 0u, 0});
+        while (!todo.empty()) {
+            const Node f = todo.back();
+            todo.pop_back();
+            for (const Edge& e : out[size_t(f.state)]) {
+                const uint32_t x = f.x | (uint32_t(e.ch) << (8 * f.d));
+                const int d = f.d + 1;
+                if (d == 3) {
+                    setKey(x);                                      // starts at q+1: bytes 0..2
+                    if (isFinal(e.next))                            // a 3-byte pattern starting at q: bytes 1..2, any c3
+                        for (uint32_t c = 0; c < 256; c++) setKey((x >> 8) | (c << 16));
+                }
+                if (d == 4) { setKey(x >> 8); continue; }           // starts at q: bytes 1..3
+                if (!out[size_t(e.next)].empty()) todo.push_back(Node{e.next, x, d});
+            }
+        }
+        L.hfiltBitsSet = 0;
+        for (uint32_t w : L.hfilt) L.hfiltBitsSet += __builtin_popcount(w);
+        if (L.hfiltBitsSet <= kHashFilterWords * 32 / 64) {   // <= 1.6 % of the pairs pass by chance
+            L.hfiltK = 3;
+            hotBudgetBytes -= hfiltBytes;
+        } else {
+            L.hfilt.clear();
+            L.hfiltBitsSet = 0;
+        }
+    }
+    if (L.hfiltK == 0 && B == 8 && !frontier.empty() && hotBudgetBytes >= hfiltBytes && filterPolicy != kFilterExact) {
         // one bit per 4-gram first, word picked by a hash of (c0, c1 & 127): sparse dictionaries.  A table
         // that comes out dense (> 2 % of its bits, whole words of short patterns aside) is rebuilt with two
         // bits per gram, twice the words when the budget holds them, and the word picked by the text bits
@@ -671,7 +719,7 @@ void compileLayout(const Machine& m, size_t hotBudgetBytes, DeviceLayout& L, int
 namespace {
 
 constexpr char kFileMagic[8] = {'P', 'F', 'A', 'C', 'B', '2', '0', '0'};
-constexpr uint32_t kFileVersion = 5;  // bump whenever Machine / DeviceLayout or their meaning change
+constexpr uint32_t kFileVersion = 6;  // bump whenever Machine / DeviceLayout or their meaning change
 
 struct Writer {
     std::string buf;
@@ -837,7 +885,7 @@ bool validLayout(const DeviceLayout& L, const Machine& m) {
     if (!L.best2.empty() && L.best2.size() != L.next2.size()) PFAC_INVALID;
     if (!L.chk2.empty() && L.chk2.size() != L.next2.size()) PFAC_INVALID;
     if (L.codeShift < -1 || L.codeShift > 6 || (L.codeShift >= 0 && L.codeBits != 2)) PFAC_INVALID;
-    if (!L.hfilt.empty() && (L.hfiltK < 1 || L.hfiltK > 2 ||
+    if (!L.hfilt.empty() && (L.hfiltK < 1 || L.hfiltK > 3 ||
                              !(L.codeBits == 8 || (L.codeBits == 2 && L.codeShift >= 0 && L.hfiltK == 2)))) PFAC_INVALID;
     // 64 KB only for the row-indexed two-bit filter of byte alphabets
     if (!L.hfilt.empty() && L.hfilt.size() != size_t(kHashFilterWords) &&

@@ -90,7 +90,9 @@ constexpr uint32_t kLeafPlain = 0x40000000u;  // plain state value: no out-edges
 //     holds them, c0 | (c1 & 31) << 8 with 8192.  Row-indexed: the words a first byte can reach are its
 //     own, so the all-ones words of a 1-byte pattern catch that byte and nothing else (hashed, each was
 //     shared with three other 2-grams: 11 of C3's 25 survivors per 512 positions).
-//     Either way the word is chosen by (c0, c1), the bits by all four bytes.  A 4-byte prefix of a
+//       hfiltK = 3 (sparse tables whose patterns all have three bytes or more): the pair filter, one lookup
+//     per two start positions, keyed by the three text bytes they share (compileLayout).
+//     With hfiltK = 1, 2 the word is chosen by (c0, c1), the bits by all four bytes.  A 4-byte prefix of a
 //     pattern sets its bits, a 3-byte pattern the bits of its 256 continuations, a 2-byte pattern its
 //     whole word, a 1-byte pattern every word of (c0,*).  Bytes past the end of the input therefore
 //     never hide a short match.
@@ -103,7 +105,7 @@ constexpr uint32_t kHashFilterMul3 = 0xC2B2AE35u;
 constexpr int kHashFilterWords = 8192;           // 32 KB of shared memory
 constexpr int kHashFilterWordsMax = 16384;       // row-indexed two-bit filter when the budget holds 64 KB
 constexpr int kDnaGram = 10;                     // symbols hashed by the first stage of 2-bit alphabets
-enum FilterPolicy { kFilterAuto = 0, kFilterExact = 1, kFilterHashed = 2 };
+enum FilterPolicy { kFilterAuto = 0, kFilterExact = 1, kFilterHashed = 2, kFilterNoPair = 3 };
 
 struct DeviceLayout {
     int32_t root[kCharSet];          // next state from the initial state, -1 = trap
@@ -120,8 +122,9 @@ struct DeviceLayout {
     // memory) when the first one lets many positions through; empty = stage off.
     std::vector<uint16_t> chk2;
     std::vector<uint32_t> hfilt;     // kHashFilterWords (or, hfiltK == 2, kHashFilterWordsMax) words, or empty (exact 2-gram first stage)
-    int hfiltK = 0;                  // bits tested per lookup: 1 (sparse table, hashed word index) or 2 (dense table, byte
-                                     // alphabets: word index x & (words - 1); see compileLayout)
+    int hfiltK = 0;                  // 1: one bit per lookup (sparse table, hashed word index); 2: two bits (dense table; byte
+                                     // alphabets: word index x & (words - 1)); 3: pair filter, one bit per TWO start
+                                     // positions keyed by the three text bytes they share (see compileLayout)
     int hfiltBitsSet = 0;
     bool next2Hot = false;           // next2 (+ best2) fit the shared-memory budget
     std::vector<uint32_t> hot;       // edges with source depth in [K,hotDepth)  -> smem

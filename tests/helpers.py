@@ -38,6 +38,15 @@ def emulate_layout_walk(L, num_final, text, start, n_total=None, pad=0):
         for m in (0x85EBCA6B, 0xC2B2AE35):
             if not ((w << (((x * m) & 0xFFFFFFFF) >> 27)) >> 31) & 1:
                 return 0
+    elif L["hfilt"].size and L["hfilt_k"] == 3:
+        # pair filter: the positions q and q+1 (q even) are decided together by the three bytes they share
+        assert B == 8
+        q = start & ~1
+        y = sum((int(text[q + 1 + i]) if q + 1 + i < n_total else pad) << (8 * i) for i in range(3))
+        h = (y * 0x9E3779B1) & 0xFFFFFF
+        w = int(L["hfilt"][(h >> 2) & 8191])
+        if not ((w << (h >> 19)) >> 31) & 1:
+            return 0
     elif L["hfilt"].size:
         assert B == 8
         x = sum((int(text[start + i]) if i < avail else pad) << (8 * i) for i in range(4))

@@ -85,6 +85,7 @@ def test_null_handle_is_invalid_handle_first():
     assert L.PFAC_matchFromDeviceReduce64(None, None, 0, None, None, ctypes.byref(m)) == Status.INVALID_HANDLE
     assert L.PFAC_matchShardFromDeviceReduce64(None, None, 0, 0, 0, None, None, ctypes.byref(m)) == Status.INVALID_HANDLE
     assert L.PFAC_getTableInfo(None, None) == Status.INVALID_HANDLE
+    assert L.PFAC_getTableInfoReduce(None, None) == Status.INVALID_HANDLE
     assert L.PFAC_memoryUsage(None) == Status.INVALID_HANDLE
     assert L.PFAC_dumpTransitionTableToFile(None, b"x") == Status.INVALID_HANDLE
     assert L.PFAC_saveCompiledPatterns(None, b"x") == Status.INVALID_HANDLE

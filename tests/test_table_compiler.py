@@ -281,6 +281,50 @@ def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
     assert TableCompiler(patterns=pats, hot_budget_bytes=16 * 1024).info()["hashed_filter"] == 0
 
 
+def test_pair_filter_never_hides_a_match(monkeypatch):
+    """Sparse byte dictionaries whose patterns all have three bytes or more get the pair filter: one lookup
+    for the start positions q and q+1, keyed by the three text bytes they share (pfac_table.cpp).  It may pass
+    too much, never too little: 3-byte patterns, matches at either parity, adjacent and overlapping matches,
+    matches at the very end of the input whatever bytes lie behind it."""
+    monkeypatch.delenv("PFAC_B200_FILTER", raising=False)
+    pats = synth.patterns_c2(600) + [b"xyz", b"abc", b"bcd", b"\x00\x01\x02", b"\xff\xff\xff", b"abcd", b"zzzz", b"zzz"]
+    pats = list(dict.fromkeys(pats))
+    tc = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
+    info = tc.info()
+    assert info["hashed_filter"] == 3 and info["hfilt_words"] == 8192
+    assert 0 < info["hfilt_bits_set"] <= 8192 * 32 // 64
+    L = tc.layout()
+    rng = np.random.default_rng(5)
+    n = 30000
+    text = synth.make_text("random", 77, 0, n, n, pats, 97)     # odd period: both parities get planted patterns
+    for at, p in ((100, b"abcd"), (103, b"xyz"), (201, b"abc"), (202, b"bcd"), (300, b"zzzzzzz"), (401, b"\xff\xff\xff\xff")):
+        text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    for p in (b"xyz", b"abcd", b"zzz", b"\x00\x01\x02"):        # at the very end, both parities of the start
+        for shift in (0, 1):
+            t = text[:n - shift].copy()
+            t[len(t) - len(p):] = np.frombuffer(p, dtype=np.uint8)
+            want = brute_force_match(pats, t[len(t) - 8:])
+            for pad in (0, 0xA5, 0xFF):
+                got = [emulate_layout_walk(L, len(pats), t[len(t) - 8:], i, pad=pad) for i in range(8)]
+                assert got == want.tolist(), (p, shift, pad)
+    want = brute_force_match(pats, text)
+    got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=0x5A) for i in range(n)], dtype=np.int32)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "first mismatch at %d: got %d want %d" % (bad[0], got[bad[0]], want[bad[0]])
+    assert (want > 0).sum() > 250
+    # the filter does reject: few pairs pass
+    t = text.astype(np.uint64)
+    y = t[1:n - 3:2] | (t[2:n - 2:2] << 8) | (t[3:n - 1:2] << 16)
+    h = (y * 0x9E3779B1) & 0xFFFFFF
+    w = L["hfilt"][((h >> 2) & 8191).astype(np.int64)].astype(np.uint64)
+    assert (((w << (h >> 19)) >> 31) & 1).mean() < 0.05
+    # a 1- or 2-byte pattern rules the pair filter out; so does the nopair policy
+    assert TableCompiler(patterns=pats + [b"q"], hot_budget_bytes=64 * 1024).info()["hashed_filter"] == 1
+    assert TableCompiler(patterns=pats + [b"qr"], hot_budget_bytes=64 * 1024).info()["hashed_filter"] == 1
+    monkeypatch.setenv("PFAC_B200_FILTER", "nopair")
+    assert TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024).info()["hashed_filter"] == 1
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_dictionaries_both_first_stages(monkeypatch, seed):
     """Property check of the compiled layout against the brute-force semantics on random dictionaries:
