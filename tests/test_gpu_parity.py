@@ -207,6 +207,59 @@ def test_first_stage_filters_agree(cuda, tmp_path, monkeypatch, policy):
         _check_all(pf, orc, text, cuda)
 
 
+def test_pair_filter_in_both_kernels(cuda, tmp_path, monkeypatch):
+    """Sparse dictionaries without 1- and 2-byte patterns: the reduce kernel's layout uses the pair filter (one
+    lookup per two start positions), the dense kernel's the per-position filter; PFAC_B200_FILTER=hash puts the
+    pair filter into the dense kernel too.  3-byte patterns, matches at either parity and in the last bytes."""
+    from pfac_b200 import PFAC
+    pats = synth.patterns_c2(700, seed=91) + [b"xyz", b"abc", b"bcd", b"zzz", b"zzzz", b"\xff\xff\xff", b"\x00\x01\x02"]
+    pats = list(dict.fromkeys(pats))
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    for policy, dense_stage in ((None, 1), ("hash", 3), ("nopair", 1)):
+        if policy:
+            monkeypatch.setenv("PFAC_B200_FILTER", policy)
+        else:
+            monkeypatch.delenv("PFAC_B200_FILTER", raising=False)
+        with PFAC() as pf:
+            pf.readPatternFromFile(pfile)
+            assert pf.tableInfo()["hashed_filter"] == dense_stage
+            assert pf.tableInfo(reduce=True)["hashed_filter"] == (1 if policy == "nopair" else 3)
+            for n in [3, 4, 5, 6, 7, 511, 512, 513, 1535, 1536, 1537, 1539, 70_001, 400_003]:
+                text = synth.make_text("random", 900 + n, 0, n, n, pats, 61)   # odd period: both parities
+                _check_all(pf, orc, text, cuda)
+                for tail in (b"xyz", b"zzzz", b"abc", b"\xff\xff\xff"):
+                    for back in (0, 1):
+                        if len(tail) + back <= n:
+                            t = text.copy()
+                            t[n - back - len(tail):n - back] = np.frombuffer(tail, dtype=np.uint8)
+                            _check_all(pf, orc, t, cuda)
+            text = synth.make_text("random", 9191, 0, 300_001, 300_001, pats, 37)
+            for owned in [1, 2, 1535, 1536, 1537, 150_001, 299_999, 300_000, 300_001]:
+                _check_all(pf, orc, text, cuda, n_owned=owned)
+
+
+def test_dense_dictionary_with_many_matches_per_tile(cuda, tmp_path):
+    """A large byte dictionary (row-indexed two-bit filter, zeros of the dense result by bulk stores) on a text
+    with more matches per 1,536-position tile than a warp parks (64): the dense kernel's wait-and-patch path,
+    the reduce kernel's spill ring."""
+    from pfac_b200 import PFAC
+    pats = synth.patterns_snort_like(12000, seed=15) + [b"e", b"t", b"a", b"o", b" ", b"n", b"th", b"he "]
+    pats = list(dict.fromkeys(pats))
+    pfile = synth.write_pattern_file(str(tmp_path / "p.txt"), pats)
+    orc = _oracle(pfile)
+    n = (1 << 21) + 1234
+    text = synth.make_text("ascii", 515, 0, n, n, pats, 48)
+    with PFAC() as pf:
+        pf.readPatternFromFile(pfile)
+        info = pf.tableInfo()
+        assert info["hashed_filter"] == 2 and info["hfilt_words"] == 16384, info
+        _check_all(pf, orc, text, cuda)
+        want = orc.match(text)
+        assert (want > 0).mean() * 1536 > 80
+        _check_all(pf, orc, text[:700_001].copy(), cuda, n_owned=699_000)
+
+
 @pytest.mark.parametrize("policy", ["auto", "exact"])
 def test_random_dictionaries_vs_oracle(cuda, tmp_path, monkeypatch, policy):
     """Random alphabets (all three symbol codings), pattern lengths 1..40 with shared prefixes, texts
