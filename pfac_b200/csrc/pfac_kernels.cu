@@ -711,10 +711,10 @@ __device__ __forceinline__ void clip_windows(int tile_rem, int lb, uint32_t& can
 // Reduce kernel: fused match + ordered stream compaction, one pass.
 //
 // Same warp-autonomous pipeline as the dense kernel (persistent CTA per SM, per-warp TMA input
-// stages, prefilter, queue, walk), with 31 matcher warps and one scanner warp per CTA, but a warp
+// stages, prefilter, queue, walk), with 31 matcher warps and one scanner warp per CTA.  A warp
 // tile is kRedSub = 3 consecutive 512-position blocks (1536 positions, one bulk copy): the walker
 // entry, the survivor scan, the tile bookkeeping and the ordering protocol below are paid once per
-// 1.5 KB of input instead of once per 512 B, and nothing here needs a per-position result slice.
+// 1.5 KB of input instead of once per 512 B (the dense kernel took the tile over from here).
 // Ordering:
 //   * "CTA tile" c = 31 consecutive warp tiles; CTA b handles c = r*G + b in round r (G = grid);
 //     matcher warp w takes warp tile w of it.  The launch is cooperative, so all G CTAs are

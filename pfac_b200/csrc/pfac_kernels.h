@@ -55,7 +55,8 @@ struct LaunchConfig {
 
 // Shared-memory bytes the dense (or reduce) kernel can spare for next2 / hash rows / chains /
 // tails, given the longest pattern (which fixes the staged halo).  The table compiler is run
-// once per kernel with its budget; the two layouts differ only in what is marked hot.
+// once per kernel with its budget; the two layouts differ in what is marked hot and, for sparse
+// dictionaries, in the first stage (pair filter: reduce kernel only).
 size_t tableSmemBudget(int maxPatternLen, bool reduceKernel);
 
 // Look-back descriptor words needed by the reduce kernel for an n_owned-byte shard.

@@ -323,7 +323,7 @@ def test_unaligned_device_pointers(cuda, tmp_path):
 
 
 def test_high_match_density_compaction(cuda, tmp_path):
-    """More matches per 512-byte tile than a warp can park (reduce kernel's synchronous path), several
+    """More matches per tile than a warp can park (reduce kernel's spill ring, dense kernel's wait-and-patch path), several
     rounds of CTA tiles, 1-byte and 2-byte patterns (every occurrence of a byte matches)."""
     from pfac_b200 import PFAC
     pats = [b"AC", b"GT", b"TT", b"CA", b"G", b"ACGTAC", b"TTTT", b"CAT", b"GATTACA", b"AA", b"TG", b"CC"]
