@@ -633,20 +633,38 @@ __device__ __forceinline__ int walk_batch(const Tables& T, const unsigned char* 
                         const uint32_t mask = (len >= 4) ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
                         if ((text_word(at0, len) ^ rec.w) & mask) done = true;
                     }
-                    // the rest 16 bytes per trip: four independent tail loads in flight at once
+                    // the rest 16 bytes per trip: four independent tail loads in flight at once, and the 16
+                    // text bytes from five aligned words shifted by the walk's (constant) misalignment -- one
+                    // bounds check and five loads per trip instead of four checks and eight loads
                     const uint32_t* tw = reinterpret_cast<const uint32_t*>(T.tails + rec.x);
+                    const int sh = (at0 & 3) * 8;
                     for (int i = 4; i < len && !done; i += 16) {
-                        uint32_t t[4];
+                        uint32_t t[4], x[4];
 #pragma unroll
                         for (int k = 0; k < 4; k++) t[k] = (i + 4 * k < len) ? tw[(i >> 2) + k] : 0u;
+                        const int at = at0 + i;
+                        if (at + 20 <= stage_bytes) {
+                            const uint32_t* w = reinterpret_cast<const uint32_t*>(inb + (at & ~3));
+                            const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+                            x[0] = __funnelshift_r(a0, a1, sh);
+                            x[1] = __funnelshift_r(a1, a2, sh);
+                            x[2] = __funnelshift_r(a2, a3, sh);
+                            x[3] = __funnelshift_r(a3, a4, sh);
+                        } else {  // near or past the end of the staged bytes: word by word, never beyond the bytes that exist
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const int n = len - (i + 4 * k);
+                                x[k] = (n > 0) ? text_word(at + 4 * k, n) : 0u;
+                            }
+                        }
+                        uint32_t diff = 0;
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const int n = len - (i + 4 * k);
-                            if (n > 0 && !done) {
-                                const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
-                                if ((text_word(at0 + i + 4 * k, n) ^ t[k]) & mask) done = true;
-                            }
+                            const uint32_t mask = (n >= 4) ? 0xFFFFFFFFu : (n > 0 ? ((1u << (8 * n)) - 1u) : 0u);
+                            diff |= (x[k] ^ t[k]) & mask;
                         }
+                        if (diff) done = true;
                     }
                     if (!done) {
                         s = rec.z & ~kChainBit;
