@@ -39,6 +39,36 @@ __global__ void mix_rows_kernel(const uint4* __restrict__ in, uint4* out, size_t
     }
     if (acc == 0x12345678u) *sink = acc;
 }
+__device__ __forceinline__ void st256_zero(void* p) {
+    unsigned z = 0;
+    asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(z) : "memory");
+}
+// fill with 32-byte stores (sm_100: STG.E.ENL2.256): a warp instruction writes 1 KB
+__global__ void fill256_kernel(unsigned char* out, size_t n32) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n32; i += stride) st256_zero(out + 32 * i);
+}
+// the dense kernel's shape: a warp reads 1,536 + 64 bytes and writes 6 KB of zeros (twelve 16-byte or six 32-byte
+// stores per lane), warps of a CTA on consecutive tiles, tiles advancing by the grid
+template <bool V8>
+__global__ void mix_tiles_kernel(const unsigned char* __restrict__ in, unsigned char* out, size_t ntiles, unsigned* sink) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    unsigned acc = 0;
+    for (size_t t = size_t(blockIdx.x) * wpc + warp; t < ntiles; t += size_t(gridDim.x) * wpc) {
+        unsigned char* o = out + t * 6144;
+        if (V8) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) st256_zero(o + (k * 32 + lane) * 32);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; k++) reinterpret_cast<uint4*>(o)[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const uint4* i4 = reinterpret_cast<const uint4*>(in + t * 1536);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const uint4 v = i4[k * 32 + lane]; acc |= v.x & v.y & v.z & v.w; }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
 __global__ void copy_kernel(const uint4* __restrict__ in, uint4* out, size_t n16) {
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) out[i] = in[i];
@@ -74,11 +104,19 @@ int main() {
     const float mset = time_ms([&] { cudaMemsetAsync(out, 0, 4 * N); }, reps);
     const float mix = time_ms([&] { mix_kernel<<<grid, block>>>((const uint4*)in, (uint4*)out, N / 16, sink); }, reps);
     const float mixr = time_ms([&] { mix_rows_kernel<<<grid, block>>>((const uint4*)in, (uint4*)out, N / 16, sink); }, reps);
+    const float fill256 = time_ms([&] { fill256_kernel<<<grid, block>>>(out, 4 * N / 32); }, reps);
+    const size_t ntiles = N / 1536;
+    const float mixt = time_ms([&] { mix_tiles_kernel<false><<<sms, 1024>>>(in, out, ntiles, sink); }, reps);
+    const float mixt8 = time_ms([&] { mix_tiles_kernel<true><<<sms, 1024>>>(in, out, ntiles, sink); }, reps);
+    const float mixt8b = time_ms([&] { mix_tiles_kernel<true><<<sms * 2, 1024>>>(in, out, ntiles, sink); }, reps);
     const float copy = time_ms([&] { copy_kernel<<<grid, block>>>((const uint4*)in, (uint4*)out, (5 * N / 2) / 16); }, reps);
     const float mcpy = time_ms([&] { cudaMemcpyAsync(out, in, 5 * N / 2, cudaMemcpyDeviceToDevice); }, reps);
     CK(cudaGetLastError());
     auto gbs = [](double bytes, float ms) { return bytes / (ms * 1e-3) / 1e9; };
-    printf("{\"fill_4GiB_ms\": %.4f, \"fill_GBps\": %.1f, \"memset_4GiB_ms\": %.4f, \"memset_GBps\": %.1f, "
+    printf("{\"fill256_4GiB_ms\": %.4f, \"fill256_GBps\": %.1f, \"mix_tiles_ms\": %.4f, \"mix_tiles_GBps\": %.1f, "
+           "\"mix_tiles_st256_ms\": %.4f, \"mix_tiles_st256_GBps\": %.1f, \"mix_tiles_st256_2cta_ms\": %.4f, ",
+           fill256, gbs(4.0 * N, fill256), mixt, gbs(5.0 * N, mixt), mixt8, gbs(5.0 * N, mixt8), mixt8b);
+    printf("\"fill_4GiB_ms\": %.4f, \"fill_GBps\": %.1f, \"memset_4GiB_ms\": %.4f, \"memset_GBps\": %.1f, "
            "\"mix_1r4w_ms\": %.4f, \"mix_GBps\": %.1f, \"mix_rows_ms\": %.4f, \"mix_rows_GBps\": %.1f, "
            "\"copy_2.5GiB_ms\": %.4f, \"copy_GBps\": %.1f, \"memcpy_2.5GiB_ms\": %.4f, \"memcpy_GBps\": %.1f}\n",
            fill, gbs(4.0 * N, fill), mset, gbs(4.0 * N, mset), mix, gbs(5.0 * N, mix), mixr, gbs(5.0 * N, mixr),
