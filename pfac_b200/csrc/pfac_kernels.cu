@@ -1306,7 +1306,8 @@ __global__ void __launch_bounds__(kRedThreads, 1) pfac_reduce_kernel(const KPara
 // What the form buys: the walker is entered once per 1536 positions (with the row-indexed filter a batch
 // of 32 lanes is two thirds full on the 20,000-pattern dictionary), no per-tile clearing, and 64 KB of
 // shared memory for the tables (the 64 KB filter, or chains and tails of a 1,000-pattern dictionary):
-// C3 774 -> 945 GB/s; C2 unchanged at the HBM bound (profiles/r2_history.md).
+// C3 774 -> 946 GB/s (974 with the walker's cheaper chain compare); C2 at the rate of a plain kernel with its
+// traffic mix (profiles/r2_history.md).
 // shared memory: [mbarriers][root | pre2 | rank2 | lut][zeros 6 KB][per warp: queue 512 B | parked ids 256 B |
 // parked positions 128 B | 2 input stages][hfilt][chk2][next2][hot][chains][tails]
 // =================================================================================================
