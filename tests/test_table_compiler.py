@@ -281,6 +281,32 @@ def test_hashed_four_gram_filter_never_hides_a_match(monkeypatch, policy):
     assert TableCompiler(patterns=pats, hot_budget_bytes=16 * 1024).info()["hashed_filter"] == 0
 
 
+def test_row_indexed_filter_at_32_kb(monkeypatch):
+    """Dense dictionaries get the row-indexed two-bit filter with 16,384 words when the budget holds 64 KB and with
+    8,192 words (word = c0 | (c1 & 31) << 8) when it holds only 32 KB: same answers either way."""
+    monkeypatch.delenv("PFAC_B200_FILTER", raising=False)
+    pats = synth.patterns_snort_like(9000, seed=23) + [b"q", b"zq", b"xyz", b"e", b"th", b"\xff"]
+    pats = list(dict.fromkeys(pats))
+    n = 12000
+    text = synth.make_text("ascii", 199, 0, n, n, pats, 64)
+    for p in (b"q", b"zq", b"xyz", b"\xff"):
+        text[n - len(p):] = np.frombuffer(p, dtype=np.uint8)
+    want = brute_force_match(pats, text)
+    for budget, words in ((48 * 1024, 8192), (80 * 1024, 16384)):
+        tc = TableCompiler(patterns=pats, hot_budget_bytes=budget)
+        info = tc.info()
+        assert info["hashed_filter"] == 2 and info["hfilt_words"] == words, info
+        L = tc.layout()
+        got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=0xC3) for i in range(n)], dtype=np.int32)
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, "budget %d: first mismatch at %d" % (budget, bad[0])
+        # patterns shorter than the gram fill words of their own first byte and no others (a 3-byte pattern sets the
+        # bits of its 256 continuations in one word: all of them)
+        hf = L["hfilt"]
+        full = np.flatnonzero(hf == 0xFFFFFFFF)
+        assert full.size and set((full & 0xFF).tolist()) <= {p[0] for p in pats if len(p) < 4}
+
+
 def test_pair_filter_never_hides_a_match(monkeypatch):
     """Sparse byte dictionaries whose patterns all have three bytes or more get the pair filter: one lookup
     for the start positions q and q+1, keyed by the three text bytes they share (pfac_table.cpp).  It may pass
