@@ -143,6 +143,17 @@ def ncu_traffic():
         return None, None
 
 
+def traffic_mix_reference():
+    """What plain kernels reach with the dense kernel's 1:4 read:write mix on these GPUs (tools/micro/hbm_mix.cu,
+    committed run): context for `frac`, whose denominator is the 1:1 copy bandwidth."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_hbm_mix.json")))
+        return {"plain_kernel_read_1GiB_write_4GiB_GBps": d.get("mix_rows_GBps"), "cudaMemset_4GiB_GBps": d.get("memset_GBps"),
+                "copy_kernel_GBps": d.get("copy_GBps"), "source": "profiles/r2_hbm_mix.json (tools/micro/hbm_mix.cu)"}
+    except Exception:
+        return None
+
+
 def cpu_reference(pfile, text, threads, reps, budget_s=None):
     """Times the reference CPU_OMP matcher (oracle/_ref when built, else the oracle port)."""
     import oracle
@@ -470,7 +481,8 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_ms,
                 "median_launch_ms": float(np.median(per_launch_ms)), "best_launch_ms": float(np.min(per_launch_ms)),
-                "frac_of_8TBps_spec": achieved / 8000.0}
+                "frac_of_8TBps_spec": achieved / 8000.0,
+                "traffic_mix_reference": traffic_mix_reference()}
 
     # ---- end to end through the host-buffer API ---------------------------------------------------
     e2e = None
