@@ -393,6 +393,44 @@ def test_random_dictionaries_both_first_stages(monkeypatch, seed):
                 assert bad.size == 0, (seed, trial, policy, budget, int(bad[0]), int(got[bad[0]]), int(want[bad[0]]))
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_random_dictionaries_pair_filter(monkeypatch, seed):
+    """The same property check for dictionaries the pair filter takes (byte alphabets, every pattern three bytes or
+    longer, many 3-byte patterns, shared prefixes, overlapping and adjacent matches at both parities)."""
+    monkeypatch.delenv("PFAC_B200_FILTER", raising=False)
+    rng = np.random.default_rng(3000 + seed)
+    took = 0
+    for trial in range(8):
+        asize = int(rng.choice([17, 40, 256]))
+        alpha = rng.choice(256, size=asize, replace=False).astype(np.uint8)
+        pats = []
+        for _ in range(int(rng.integers(1, 80))):
+            ln = int(rng.integers(3, 13))
+            body = alpha[rng.integers(0, asize, size=ln)].tobytes()
+            if pats and rng.random() < 0.4:
+                body = (pats[int(rng.integers(0, len(pats)))] + body)[:14]
+            pats.append(body)
+        pats = list(dict.fromkeys(pats))
+        n = 701 + trial                                   # odd and even lengths
+        text = alpha[rng.integers(0, asize, size=n)].copy()
+        for p in pats[:20]:
+            at = int(rng.integers(0, n - len(p) + 1))
+            text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+        tail = pats[int(rng.integers(0, len(pats)))]
+        text[n - len(tail):] = np.frombuffer(tail, dtype=np.uint8)
+        want = brute_force_match(pats, text)
+        tc = TableCompiler(patterns=pats, hot_budget_bytes=64 * 1024)
+        info = tc.info()
+        assert info["code_bits"] == 8 and info["hashed_filter"] in (1, 3)
+        took += info["hashed_filter"] == 3
+        L = tc.layout()
+        for pad in (0, 0xFF, int(rng.integers(0, 256))):
+            got = np.array([emulate_layout_walk(L, len(pats), text, i, pad=pad) for i in range(n)], dtype=np.int32)
+            bad = np.flatnonzero(got != want)
+            assert bad.size == 0, (seed, trial, pad, int(bad[0]), int(got[bad[0]]), int(want[bad[0]]))
+    assert took >= 6      # the pair filter is what these dictionaries get
+
+
 def test_compiled_table_file_round_trip(tmp_path, golden_dir):
     """PFAC_tableSave / PFAC_tableLoad: the automaton and the layout come back bit for bit (info, every
     layout array, the text dump); truncated, corrupted and foreign files are rejected, a missing
